@@ -1,0 +1,260 @@
+"""numpy/ctypes front end for the two CPU checkers.  TEST INFRASTRUCTURE ONLY.
+
+* ``port()``  -> oracle/liboracle.so      (oracle.c, the plain-C restatement; always buildable)
+* ``ref()``   -> oracle/_ref/libgeomc_ref.so  (the reference's own headers compiled by oracle/Makefile;
+                 present wherever it was built from /root/reference and shipped with the snapshot)
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` / ``--impl reference``
+legs may import this module.  The product package ``geomc_b200`` never does.
+
+All batches are AoS: ``a`` has shape (B, n*n) (flat matrix per system, interpreted row- or
+column-major by the ``row_major`` flag, MatrixGlue.h:28-58), ``x`` has shape (B, n*m).
+Functions never modify their arguments; they return fresh arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SUF = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def build(verbose: bool = False) -> None:
+    """(Re)build liboracle.so and, when /root/reference exists, _ref/libgeomc_ref.so."""
+    r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout, r.stderr)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed")
+
+
+class CpuLinalg:
+    """One of the two checker libraries, behind one numpy interface."""
+
+    def __init__(self, path: str, prefix: str, kind: str):
+        self.path, self.prefix, self.kind = path, prefix, kind
+        self.lib = C.CDLL(path)
+
+    # ------------------------------------------------------------------ helpers
+    def _fn(self, name, dt):
+        f = getattr(self.lib, f"{self.prefix}_{name}_{_SUF[np.dtype(dt)]}")
+        f.restype = C.c_int
+        return f
+
+    @staticmethod
+    def _prep(a, cols=None):
+        a = np.ascontiguousarray(a).copy()
+        if a.dtype not in _SUF:
+            raise TypeError(a.dtype)
+        if a.ndim != 2:
+            raise ValueError("expected (B, elems)")
+        return a
+
+    def max_threads(self) -> int:
+        if self.kind != "reference":
+            return 1
+        self.lib.ref_max_threads.restype = C.c_int
+        return int(self.lib.ref_max_threads())
+
+    def set_threads(self, n: int) -> None:
+        if self.kind == "reference":
+            self.lib.ref_set_threads(C.c_int(n))
+
+    def build_info(self) -> str:
+        f = self.lib.ref_build_info if self.kind == "reference" else self.lib.orc_build_info
+        f.restype = C.c_char_p
+        return f().decode()
+
+    # ------------------------------------------------------------------ factorizations
+    def _decomp(self, which, m, rows, cols, row_major, n_reorder):
+        m = self._prep(m)
+        B = m.shape[0]
+        assert m.shape[1] == rows * cols
+        reorder = np.zeros((B, n_reorder), np.int64)
+        parity = np.zeros(B, np.uint8)
+        degen = np.zeros(B, np.int64)
+        rc = self._fn(which, m.dtype)(C.c_int(rows), C.c_int(cols), C.c_int64(B), _ptr(m), _ptr(reorder),
+                                      _ptr(parity), _ptr(degen), C.c_int(int(row_major)))
+        assert rc == 0
+        return m, reorder, parity, degen
+
+    def decomp_plu(self, m, rows, cols=None, row_major=True):
+        """geom::decomp_plu (LUDecomp.h:188) -> (lu, reorder[B,rows], parity[B], degenerate_ct[B])."""
+        cols = rows if cols is None else cols
+        return self._decomp("decomp_plu", m, rows, cols, row_major, rows)
+
+    def decomp_lup(self, m, rows, cols=None, row_major=True):
+        """geom::decomp_lup (LUDecomp.h:102) -> (lu, reorder[B,cols], parity[B], degenerate_ct[B])."""
+        cols = rows if cols is None else cols
+        return self._decomp("decomp_lup", m, rows, cols, row_major, cols)
+
+    def backsolve_lu(self, lu, x, n, m=1, skip=0, row_major=True):
+        """geom::backsolve_lu (LUDecomp.h:332) -> x."""
+        lu = self._prep(lu)
+        x = self._prep(x)
+        B = lu.shape[0]
+        rc = self._fn("backsolve_lu", lu.dtype)(C.c_int(n), C.c_int(m), C.c_int64(B), _ptr(lu), _ptr(x),
+                                                C.c_int(skip), C.c_int(int(row_major)))
+        assert rc == 0
+        return x
+
+    def backsolve_plu(self, plu, p, b, n, m=1, skip=0, row_major=True):
+        """geom::backsolve_plu (LUDecomp.h:271) -> x."""
+        plu = self._prep(plu)
+        b = self._prep(b)
+        p = np.ascontiguousarray(p, dtype=np.int64)
+        x = np.zeros_like(b)
+        B = plu.shape[0]
+        rc = self._fn("backsolve_plu", plu.dtype)(C.c_int(n), C.c_int(m), C.c_int64(B), _ptr(plu), _ptr(p), _ptr(x),
+                                                  _ptr(b), C.c_int(skip), C.c_int(int(row_major)))
+        assert rc == 0
+        return x
+
+    def apply_perm(self, p, a, n, m, row_major=True):
+        """geom::detail::destructive_apply_permutation (LUDecomp.h:35) -> (P a, clobbered p)."""
+        a = self._prep(a)
+        p = np.ascontiguousarray(p, dtype=np.int64).copy()
+        B = a.shape[0]
+        name = "apply_perm"
+        rc = self._fn(name, a.dtype)(C.c_int(n), C.c_int(m), C.c_int64(B), _ptr(p), _ptr(a), C.c_int(int(row_major)))
+        assert rc == 0
+        return a, p
+
+    def linear_solve(self, a, x, n, m=1, skip=0, row_major=True):
+        """geom::linear_solve pointer form (LUDecomp.h:388) -> (a_after (LU), x_after, ok[B])."""
+        a = self._prep(a)
+        x = self._prep(x)
+        B = a.shape[0]
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("linear_solve", a.dtype)(C.c_int(n), C.c_int(m), C.c_int64(B), _ptr(a), _ptr(x), C.c_int(skip),
+                                               _ptr(ok), C.c_int(int(row_major)))
+        assert rc == 0
+        return a, x, ok
+
+    def linear_solve_vec(self, bases, x, n, m=1, skip=0):
+        """geom::linear_solve Vec form (LUDecomp.h:417) -> (bases_after, x_after, ok[B])."""
+        bases = self._prep(bases)
+        x = self._prep(x)
+        B = bases.shape[0]
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("linear_solve_vec", bases.dtype)(C.c_int(n), C.c_int(m), C.c_int64(B), _ptr(bases), _ptr(x),
+                                                       C.c_int(skip), _ptr(ok))
+        assert rc == 0
+        return bases, x, ok
+
+    def cholesky(self, a, n, row_major=True):
+        """geom::cholesky<T,RowMajor>(T*, n) (Cholesky.h:37) -> (L (upper zeroed), ok[B])."""
+        a = self._prep(a)
+        B = a.shape[0]
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("cholesky", a.dtype)(C.c_int(n), C.c_int64(B), _ptr(a), _ptr(ok), C.c_int(int(row_major)))
+        assert rc == 0
+        return a, ok
+
+    def cholesky_mtx(self, a, n):
+        """geom::cholesky(SimpleMatrix*) (Cholesky.h:83); reference library only."""
+        a = self._prep(a)
+        B = a.shape[0]
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("cholesky_mtx", a.dtype)(C.c_int(n), C.c_int64(B), _ptr(a), _ptr(ok))
+        assert rc == 0
+        return a, ok
+
+    def cholesky_solve(self, l, x, n, m=1, row_major=True):
+        """Framework-defined L L^T x = b solve (no reference counterpart; port only)."""
+        if self.kind == "reference":
+            raise NotImplementedError("the reference has no Cholesky solve")
+        l = self._prep(l)
+        x = self._prep(x)
+        B = l.shape[0]
+        rc = self._fn("cholesky_solve", l.dtype)(C.c_int(n), C.c_int(m), C.c_int64(B), _ptr(l), _ptr(x),
+                                                 C.c_int(int(row_major)))
+        assert rc == 0
+        return x
+
+    def inv(self, src, n, src_row_major=True, dst_row_major=True, dst_init=None):
+        """geom::inv(Md*, const Mx&) (Matrix.h:717) -> (dst, ok[B]); dst keeps dst_init where ok == 0."""
+        src = self._prep(src)
+        B = src.shape[0]
+        dst = np.zeros_like(src) if dst_init is None else self._prep(dst_init)
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("inv", src.dtype)(C.c_int(n), C.c_int64(B), _ptr(src), _ptr(dst), _ptr(ok),
+                                        C.c_int(int(src_row_major)), C.c_int(int(dst_row_major)))
+        assert rc == 0
+        return dst, ok
+
+    def inv_raw(self, src, n, dst_init=None):
+        """inv2x2 / inv3x3 / inv4x4 / invNxN(T*,T*,n) on flat arrays (MatrixInv.h:49/75/117/186)."""
+        src = self._prep(src)
+        B = src.shape[0]
+        dst = np.zeros_like(src) if dst_init is None else self._prep(dst_init)
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("inv_raw", src.dtype)(C.c_int(n), C.c_int64(B), _ptr(src), _ptr(dst), _ptr(ok))
+        assert rc == 0
+        return dst, ok
+
+    # in-place, zero-copy variants used only by bench.py's CPU baseline timing loop
+    def linear_solve_inplace(self, a, x, ok, n, m=1, skip=0, row_major=True):
+        rc = self._fn("linear_solve", a.dtype)(C.c_int(n), C.c_int(m), C.c_int64(a.shape[0]), _ptr(a), _ptr(x),
+                                               C.c_int(skip), _ptr(ok), C.c_int(int(row_major)))
+        assert rc == 0
+
+
+_cache: dict = {}
+
+
+def port() -> CpuLinalg:
+    if "port" not in _cache:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _cache["port"] = CpuLinalg(path, "orc", "port")
+    return _cache["port"]
+
+
+def ref_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libgeomc_ref.so"))
+
+
+def ref() -> CpuLinalg:
+    if "ref" not in _cache:
+        path = os.path.join(_HERE, "_ref", "libgeomc_ref.so")
+        if not os.path.exists(path):
+            if os.path.isdir("/root/reference/geomc"):
+                build()
+            if not os.path.exists(path):
+                raise FileNotFoundError("oracle/_ref/libgeomc_ref.so not built (needs /root/reference)")
+        _cache["ref"] = CpuLinalg(path, "ref", "reference")
+    return _cache["ref"]
+
+
+def best() -> CpuLinalg:
+    """The reference itself when its compiled library is present, else the port."""
+    return ref() if ref_available() else port()
+
+
+# ---------------------------------------------------------------------- shared input generators
+def exact_grid(rng: np.random.Generator, shape, dtype, bits: int = 20, scale_log2: int = -17):
+    """Contraction-proof inputs: `bits`-bit signed integers times 2**scale_log2 (exact in f32 and f64).
+
+    Default: uniform on a grid of step 2^-17 in [-4, 4).  SURVEY.md section 7 item 2.
+    """
+    half = 1 << (bits - 1)
+    v = rng.integers(-half, half, size=shape, dtype=np.int64)
+    return (v.astype(np.float64) * (2.0 ** scale_log2)).astype(dtype)
+
+
+def spd_exact(rng: np.random.Generator, B: int, n: int, dtype):
+    """A = R R^T + I with R on a coarse exact grid, so that every product and sum is exact in f64
+    (and in f32 for the coarse grid used): 8-bit integers times 2^-5."""
+    R = exact_grid(rng, (B, n, n), np.float64, bits=8, scale_log2=-5)
+    A = R @ np.swapaxes(R, 1, 2) + np.eye(n)[None]
+    return A.reshape(B, n * n).astype(dtype)

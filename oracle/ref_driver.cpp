@@ -1,0 +1,297 @@
+// oracle/_ref driver -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Compiles the UNMODIFIED reference headers where they lie under /root/reference (geomc/linalg/*.h)
+// into oracle/_ref/libgeomc_ref.so and exposes the hot-path functions as a C ABI that loops over
+// an AoS batch (one reference object per system).  Used by tests/ as the parity checker, by
+// tests/golden/make_golden.py to generate the committed fixtures, and by bench.py's
+// `cpu_baseline` / `--impl reference` legs (kind = "reference").  Nothing under geomc_b200/
+// may link or load this.
+//
+// Each entry point calls exactly one reference function per system:
+//   ref_decomp_plu_*      geom::decomp_plu<T,RowMajor>          LUDecomp.h:188
+//   ref_decomp_lup_*      geom::decomp_lup<T,RowMajor>          LUDecomp.h:102
+//   ref_backsolve_lu_*    geom::backsolve_lu<T,RowMajor>        LUDecomp.h:332
+//   ref_backsolve_plu_*   geom::backsolve_plu<T,RowMajor>       LUDecomp.h:271
+//   ref_apply_perm_*      geom::detail::destructive_apply_permutation  LUDecomp.h:35
+//   ref_linear_solve_*    geom::linear_solve<T,RowMajor>(T*,n,m,T*,skip)   LUDecomp.h:388
+//   ref_linear_solve_vec_*  geom::linear_solve<T,N>(Vec<T,N>[N],m,Vec<T,N>*,skip)  LUDecomp.h:417
+//   ref_cholesky_*        geom::cholesky<T,RowMajor>(T*,n)      Cholesky.h:37
+//   ref_cholesky_mtx_*    geom::cholesky(SimpleMatrix*)         Cholesky.h:83
+//   ref_inv_*             geom::inv(Md*, const Mx&)             Matrix.h:717 (static N = 2..16)
+//   ref_inv_raw_*         geom::inv2x2/inv3x3/inv4x4 / invNxN(T*,T*,n)   MatrixInv.h:49/75/117/186
+//
+// Build: see oracle/Makefile (g++ -std=c++23 -O3 -mavx2 -mfma -ffp-contract=fast
+//        --param=avoid-fma-max-bits=0 -fno-tree-loop-vectorize -fopenmp; the Makefile explains each flag).
+#include <geomc/linalg/Matrix.h>
+#include <geomc/linalg/LUDecomp.h>
+#include <geomc/linalg/Cholesky.h>
+#include <geomc/linalg/Vec.h>
+
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+// index_t is the reference's global typedef (geomc_defs.h:85): std::ptrdiff_t
+static_assert(sizeof(index_t) == sizeof(int64_t), "index_t must be 64-bit");
+
+namespace {
+
+template <typename T, bool RM>
+void plu_batch(int rows, int cols, int64_t B, T* m, int64_t* reorder, uint8_t* parity, int64_t* degen) {
+    const int64_t sz = (int64_t)rows * cols;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        bool par = false;
+        index_t* p = reorder ? reinterpret_cast<index_t*>(reorder + s * rows) : nullptr;
+        index_t d = geom::decomp_plu<T, RM>(m + s * sz, rows, cols, p, &par);
+        if (parity) parity[s] = par ? 1 : 0;
+        if (degen) degen[s] = d;
+    }
+}
+
+template <typename T, bool RM>
+void lup_batch(int rows, int cols, int64_t B, T* m, int64_t* reorder, uint8_t* parity, int64_t* degen) {
+    const int64_t sz = (int64_t)rows * cols;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        bool par = false;
+        index_t* p = reorder ? reinterpret_cast<index_t*>(reorder + s * cols) : nullptr;
+        index_t d = geom::decomp_lup<T, RM>(m + s * sz, rows, cols, p, &par);
+        if (parity) parity[s] = par ? 1 : 0;
+        if (degen) degen[s] = d;
+    }
+}
+
+template <typename T, bool RM>
+void backsolve_lu_batch(int n, int m, int64_t B, const T* lu, T* x, int skip) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        geom::backsolve_lu<T, RM>(lu + s * n * n, n, m, x + s * n * m, skip);
+    }
+}
+
+template <typename T, bool RM>
+void backsolve_plu_batch(int n, int m, int64_t B, const T* plu, const int64_t* p, T* x, const T* b, int skip) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        geom::backsolve_plu<T, RM>(plu + s * n * n, reinterpret_cast<const index_t*>(p + s * n), n, m,
+                                   x + s * n * m, b + s * n * m, skip);
+    }
+}
+
+template <typename T, bool RM>
+void apply_perm_batch(int n, int m, int64_t B, int64_t* p, T* a) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        geom::detail::destructive_apply_permutation<T, RM>(reinterpret_cast<index_t*>(p + s * n), a + s * n * m, n, m);
+    }
+}
+
+template <typename T, bool RM>
+void linear_solve_batch(int n, int m, int64_t B, T* a, T* x, int skip, uint8_t* ok) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        bool r = geom::linear_solve<T, RM>(a + s * n * n, n, m, x + s * n * m, skip);
+        if (ok) ok[s] = r ? 1 : 0;
+    }
+}
+
+template <typename T, index_t N>
+void linear_solve_vec_batch(int m, int64_t B, T* bases, T* x, int skip, uint8_t* ok) {
+    static_assert(sizeof(geom::Vec<T, N>) == sizeof(T) * N);
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        auto* bs = reinterpret_cast<geom::Vec<T, N>*>(bases + s * N * N);
+        auto* xs = reinterpret_cast<geom::Vec<T, N>*>(x + s * N * m);
+        bool r = geom::linear_solve<T, N>(bs, m, xs, skip);
+        if (ok) ok[s] = r ? 1 : 0;
+    }
+}
+
+template <typename T, bool RM>
+void cholesky_batch(int n, int64_t B, T* a, uint8_t* ok) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        bool r = geom::cholesky<T, RM>(a + s * n * n, n);
+        if (ok) ok[s] = r ? 1 : 0;
+    }
+}
+
+template <typename T, index_t N>
+void cholesky_mtx_batch(int64_t B, T* a, uint8_t* ok) {
+    // sizeof(SimpleMatrix<float,3,3>) is 40, not 36 (alignof 8): the packed batch is copied
+    // through a local object rather than reinterpreted.
+    using Mx = geom::SimpleMatrix<T, N, N>;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        Mx mx;
+        std::memcpy(mx.data_begin(), a + s * N * N, sizeof(T) * N * N);
+        bool r = geom::cholesky(&mx);
+        std::memcpy(a + s * N * N, mx.data_begin(), sizeof(T) * N * N);
+        if (ok) ok[s] = r ? 1 : 0;
+    }
+}
+
+template <typename T, index_t N, geom::MatrixLayout LS, geom::MatrixLayout LD>
+void inv_mtx_batch(int64_t B, const T* src, T* dst, uint8_t* ok) {
+    using Ms = geom::SimpleMatrix<T, N, N, LS>;
+    using Md = geom::SimpleMatrix<T, N, N, LD>;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        Ms a;
+        Md d;
+        std::memcpy(a.data_begin(), src + s * N * N, sizeof(T) * N * N);
+        std::memcpy(d.data_begin(), dst + s * N * N, sizeof(T) * N * N);  // "untouched on failure" is observable
+        bool r = geom::inv(&d, a);
+        std::memcpy(dst + s * N * N, d.data_begin(), sizeof(T) * N * N);
+        if (ok) ok[s] = r ? 1 : 0;
+    }
+}
+
+template <typename T, index_t N>
+int inv_mtx_dispatch(int64_t B, const T* src, T* dst, uint8_t* ok, int srm, int drm) {
+    using geom::ROW_MAJOR;
+    using geom::COL_MAJOR;
+    if (srm && drm)        inv_mtx_batch<T, N, ROW_MAJOR, ROW_MAJOR>(B, src, dst, ok);
+    else if (srm && !drm)  inv_mtx_batch<T, N, ROW_MAJOR, COL_MAJOR>(B, src, dst, ok);
+    else if (!srm && drm)  inv_mtx_batch<T, N, COL_MAJOR, ROW_MAJOR>(B, src, dst, ok);
+    else                   inv_mtx_batch<T, N, COL_MAJOR, COL_MAJOR>(B, src, dst, ok);
+    return 0;
+}
+
+template <typename T>
+void inv_raw_batch(int n, int64_t B, T* src_destroyed, T* dst, uint8_t* ok) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        T* a = src_destroyed + s * n * n;
+        T* d = dst + s * n * n;
+        bool r;
+        switch (n) {
+            case 2: r = geom::inv2x2(d, a); break;
+            case 3: r = geom::inv3x3(d, a); break;
+            case 4: r = geom::inv4x4(d, a); break;
+            default: r = geom::invNxN(d, a, (index_t)n); break;
+        }
+        if (ok) ok[s] = r ? 1 : 0;
+    }
+}
+
+#define FOR_N_2_16(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
+
+template <typename T>
+int linear_solve_vec_dispatch(int n, int m, int64_t B, T* bases, T* x, int skip, uint8_t* ok) {
+    switch (n) {
+#define CASE(N) case N: linear_solve_vec_batch<T, N>(m, B, bases, x, skip, ok); return 0;
+        FOR_N_2_16(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+
+template <typename T>
+int cholesky_mtx_dispatch(int n, int64_t B, T* a, uint8_t* ok) {
+    switch (n) {
+#define CASE(N) case N: cholesky_mtx_batch<T, N>(B, a, ok); return 0;
+        FOR_N_2_16(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+
+template <typename T>
+int inv_dispatch(int n, int64_t B, const T* src, T* dst, uint8_t* ok, int srm, int drm) {
+    switch (n) {
+#define CASE(N) case N: return inv_mtx_dispatch<T, N>(B, src, dst, ok, srm, drm);
+        FOR_N_2_16(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+
+}  // namespace
+
+#define DEFINE_FOR_TYPE(SUF, T)                                                                                   \
+    extern "C" int ref_decomp_plu_##SUF(int rows, int cols, int64_t B, T* m, int64_t* reorder, uint8_t* parity,   \
+                                        int64_t* degen, int row_major) {                                          \
+        if (row_major) plu_batch<T, true>(rows, cols, B, m, reorder, parity, degen);                              \
+        else           plu_batch<T, false>(rows, cols, B, m, reorder, parity, degen);                             \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    extern "C" int ref_decomp_lup_##SUF(int rows, int cols, int64_t B, T* m, int64_t* reorder, uint8_t* parity,   \
+                                        int64_t* degen, int row_major) {                                          \
+        if (row_major) lup_batch<T, true>(rows, cols, B, m, reorder, parity, degen);                              \
+        else           lup_batch<T, false>(rows, cols, B, m, reorder, parity, degen);                             \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    extern "C" int ref_backsolve_lu_##SUF(int n, int m, int64_t B, const T* lu, T* x, int skip, int row_major) {  \
+        if (row_major) backsolve_lu_batch<T, true>(n, m, B, lu, x, skip);                                         \
+        else           backsolve_lu_batch<T, false>(n, m, B, lu, x, skip);                                        \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    extern "C" int ref_backsolve_plu_##SUF(int n, int m, int64_t B, const T* plu, const int64_t* p, T* x,         \
+                                           const T* b, int skip, int row_major) {                                 \
+        if (row_major) backsolve_plu_batch<T, true>(n, m, B, plu, p, x, b, skip);                                 \
+        else           backsolve_plu_batch<T, false>(n, m, B, plu, p, x, b, skip);                                \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    extern "C" int ref_apply_perm_##SUF(int n, int m, int64_t B, int64_t* p, T* a, int row_major) {               \
+        if (row_major) apply_perm_batch<T, true>(n, m, B, p, a);                                                  \
+        else           apply_perm_batch<T, false>(n, m, B, p, a);                                                 \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    extern "C" int ref_linear_solve_##SUF(int n, int m, int64_t B, T* a, T* x, int skip, uint8_t* ok,             \
+                                          int row_major) {                                                        \
+        if (row_major) linear_solve_batch<T, true>(n, m, B, a, x, skip, ok);                                      \
+        else           linear_solve_batch<T, false>(n, m, B, a, x, skip, ok);                                     \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    extern "C" int ref_linear_solve_vec_##SUF(int n, int m, int64_t B, T* bases, T* x, int skip, uint8_t* ok) {   \
+        return linear_solve_vec_dispatch<T>(n, m, B, bases, x, skip, ok);                                         \
+    }                                                                                                             \
+    extern "C" int ref_cholesky_##SUF(int n, int64_t B, T* a, uint8_t* ok, int row_major) {                       \
+        if (row_major) cholesky_batch<T, true>(n, B, a, ok);                                                      \
+        else           cholesky_batch<T, false>(n, B, a, ok);                                                     \
+        return 0;                                                                                                 \
+    }                                                                                                             \
+    extern "C" int ref_cholesky_mtx_##SUF(int n, int64_t B, T* a, uint8_t* ok) {                                  \
+        return cholesky_mtx_dispatch<T>(n, B, a, ok);                                                             \
+    }                                                                                                             \
+    extern "C" int ref_inv_##SUF(int n, int64_t B, const T* src, T* dst, uint8_t* ok, int src_row_major,          \
+                                 int dst_row_major) {                                                             \
+        return inv_dispatch<T>(n, B, src, dst, ok, src_row_major, dst_row_major);                                 \
+    }                                                                                                             \
+    extern "C" int ref_inv_raw_##SUF(int n, int64_t B, T* src_destroyed, T* dst, uint8_t* ok) {                   \
+        inv_raw_batch<T>(n, B, src_destroyed, dst, ok);                                                           \
+        return 0;                                                                                                 \
+    }
+
+DEFINE_FOR_TYPE(f32, float)
+DEFINE_FOR_TYPE(f64, double)
+
+extern "C" int ref_max_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+extern "C" void ref_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+extern "C" const char* ref_build_info() {
+    return "geomc reference headers (/root/reference), g++ " __VERSION__
+           " -std=c++23 -O3 -mavx2 -mfma -ffp-contract=fast --param=avoid-fma-max-bits=0 -fno-tree-loop-vectorize"
+#ifdef _OPENMP
+           " -fopenmp"
+#endif
+        ;
+}
