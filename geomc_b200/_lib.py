@@ -1,0 +1,95 @@
+"""ctypes binding of libgeomc_b200.so (the C ABI declared in include/geomc_b200.h).
+
+The product path has NO fallback: if the CUDA library is missing or a call fails, this raises.
+Nothing here imports, links or calls anything under oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeomc_b200.so")
+
+LAYOUT_AOS = 0
+LAYOUT_SOA = 1
+MAX_N = 16
+MAX_M = 4
+
+
+class GmbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+_vp, _i, _i64 = C.c_void_p, C.c_int, C.c_int64
+
+# name -> argtypes (per dtype suffix); every function returns int
+_TYPED = {
+    "gmb_aos_to_soa": [_i, _i64, _vp, _vp, _vp],
+    "gmb_soa_to_aos": [_i, _i64, _vp, _vp, _vp],
+    "gmb_plu_decomp": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gmb_lup_decomp": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gmb_lu_backsolve": [_i, _i, _i64, _vp, _vp, _i, _i, _i, _vp],
+    "gmb_plu_backsolve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "gmb_apply_permutation": [_i, _i, _i64, _vp, _vp, _i, _i, _vp],
+    "gmb_plu_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "gmb_linear_solve_vec": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gmb_cholesky": [_i, _i64, _vp, _vp, _i, _i, _vp],
+    "gmb_cholesky_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gmb_inv": [_i, _i64, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "gmb_solve_residual": [_i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "gmb_host_plu_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _i],
+    "gmb_host_inv": [_i, _i64, _vp, _vp, _vp, _i, _i, _i],
+    "gmb_host_cholesky_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i],
+    "gmb_host_plu_decomp": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i],
+}
+
+# every symbol include/geomc_b200.h declares (tests/test_abi.py checks the header against this)
+UNTYPED = ["gmb_version", "gmb_error_string", "gmb_device_count", "gmb_soa_tile_width", "gmb_soa_elems",
+           "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count"]
+EXPORTS = UNTYPED + [f"{k}_{s}" for k in _TYPED for s in ("f32", "f64")]
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; fail loudly if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GmbError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C geomc_b200/csrc`. geomc_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name, argtypes in _TYPED.items():
+        for suf in ("f32", "f64"):
+            f = getattr(L, f"{name}_{suf}")
+            f.argtypes = argtypes
+            f.restype = C.c_int
+    L.gmb_version.restype = C.c_char_p
+    L.gmb_error_string.restype = C.c_char_p
+    L.gmb_error_string.argtypes = [_i]
+    L.gmb_device_count.restype = _i
+    L.gmb_soa_tile_width.restype = _i
+    L.gmb_soa_tile_width.argtypes = [_i]
+    L.gmb_soa_elems.restype = _i64
+    L.gmb_soa_elems.argtypes = [_i64, _i, _i]
+    L.gmb_checksum_bytes.restype = _i
+    L.gmb_checksum_bytes.argtypes = [_vp, _i64, _i64, _vp, _vp]
+    L.gmb_host_alloc.restype = _vp
+    L.gmb_host_alloc.argtypes = [C.c_size_t]
+    L.gmb_host_free.restype = None
+    L.gmb_host_free.argtypes = [_vp]
+    L.gmb_launch_count.restype = _i64
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise GmbError(f"{what} failed: {lib().gmb_error_string(rc).decode()} (code {rc})")
+
+
+def call(name: str, suffix: str, *args) -> None:
+    check(getattr(lib(), f"{name}_{suffix}")(*args), f"{name}_{suffix}")

@@ -1,0 +1,417 @@
+// gmb_api.cu -- the extern "C" boundary (include/geomc_b200.h): argument checks and dispatch to
+// the register (n <= 4), sub-warp cooperative (n = 5..16) and generic kernels, plus the
+// host-buffer pipelines.  No CPU fallback anywhere: every entry point ends in a kernel launch.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "gmb_common.cuh"
+#include "gmb_io.cuh"
+
+namespace gmb {
+
+std::atomic<int64_t> g_launch_count{0};
+
+// gmb_small.cu
+template <typename T> int small_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
+template <typename T> int small_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
+template <typename T> int small_backsolve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
+template <typename T> int small_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
+template <typename T> int small_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
+template <typename T> int small_solve_vec(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, cudaStream_t);
+// gmb_subwarp.cu
+template <typename T> int subwarp_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
+template <typename T> int subwarp_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
+template <typename T> int subwarp_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
+template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
+// gmb_generic.cu
+template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
+template <typename T> int generic_solve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
+template <typename T> int generic_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
+template <typename T> int generic_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
+template <typename T> int residual_stats(int, int64_t, const T*, const T*, const T*, const uint8_t*, double*, int, int, cudaStream_t);
+template <typename T> int transpose_batch(bool, int, int64_t, const T*, T*, cudaStream_t);
+int checksum_bytes(const void*, int64_t, int64_t, uint64_t*, cudaStream_t);
+
+static bool bad_layout(int layout) { return layout != GMB_LAYOUT_AOS && layout != GMB_LAYOUT_SOA; }
+
+// ------------------------------------------------------------------ typed implementations
+template <typename T>
+int plu_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
+               bool colpiv, void* stream) {
+    if (B < 0 || rows < 1 || cols < 1 || bad_layout(layout) || (B > 0 && A == nullptr)) return GMB_ERR_INVALID_ARG;
+    if (rows > GMB_MAX_N || cols > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (cols <= 4 && cols >= 2 && (rows == cols || rows == cols - 1)) {
+        int rc = small_decomp<T>(rows, cols, B, A, perm, parity, degen, layout, rm, colpiv, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    if (!colpiv && rows == cols && rows >= 5) {
+        int rc = subwarp_decomp<T>(rows, B, A, perm, parity, degen, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    return generic_decomp<T>(rows, cols, B, A, perm, parity, degen, layout, rm, colpiv, st);
+}
+
+template <typename T>
+int lu_backsolve(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* perm, const T* Bm, T* X, int skip,
+                 int layout, int rm, void* stream) {
+    if (B < 0 || n < 1 || m < 1 || skip < 0 || bad_layout(layout)) return GMB_ERR_INVALID_ARG;
+    if (B > 0 && (X == nullptr || Bm == nullptr || (mode != 2 && LU == nullptr) || (mode != 0 && perm == nullptr)))
+        return GMB_ERR_INVALID_ARG;
+    if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (n >= 2 && n <= 4 && m <= 4) {
+        int rc = small_backsolve<T>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    return generic_solve<T>(mode, n, m, B, LU, perm, Bm, X, nullptr, nullptr, skip, layout, rm, st);
+}
+
+template <typename T>
+int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout, int rm,
+              void* stream) {
+    if (B < 0 || n < 1 || m < 1 || skip < 0 || bad_layout(layout)) return GMB_ERR_INVALID_ARG;
+    if (B > 0 && (A == nullptr || Bm == nullptr || X == nullptr)) return GMB_ERR_INVALID_ARG;
+    if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (n >= 2 && n <= 4 && m <= 4) {
+        int rc = small_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    if (n >= 5) {
+        int rc = subwarp_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    return generic_solve<T>(3, n, m, B, A, nullptr, Bm, X, ok, LU, skip, layout, rm, st);
+}
+
+template <typename T>
+int linear_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X, uint8_t* ok, int skip, int layout,
+                     void* stream) {
+    if (B < 0 || n < 1 || m < 1 || skip < 0 || bad_layout(layout)) return GMB_ERR_INVALID_ARG;
+    if (B > 0 && (bases == nullptr || Bv == nullptr || X == nullptr)) return GMB_ERR_INVALID_ARG;
+    if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (n < 5) {
+        // inverse-then-multiply: LUDecomp.h:419-426 (skip is ignored on this path, as in the reference)
+        if (n >= 2 && m <= 4) return small_solve_vec<T>(n, m, B, bases, Bv, X, ok, layout, st);
+        return GMB_ERR_UNSUPPORTED;
+    }
+    // n >= 5: column-major PLU + permutation + column-major back-substitution (:428-439)
+    return plu_solve<T>(n, m, B, bases, Bv, X, ok, nullptr, skip, layout, /*row_major=*/0, stream);
+}
+
+template <typename T>
+int cholesky(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* L_out, int layout, int rm,
+             bool solve, void* stream) {
+    if (B < 0 || n < 1 || bad_layout(layout) || (B > 0 && A == nullptr)) return GMB_ERR_INVALID_ARG;
+    if (solve && (m < 1 || (B > 0 && (Bm == nullptr || X == nullptr)))) return GMB_ERR_INVALID_ARG;
+    if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (n >= 2 && n <= 4 && (!solve || m <= 4)) {
+        int rc = small_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    if (n >= 5) {
+        int rc = subwarp_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    return generic_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
+}
+
+template <typename T>
+int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm, void* stream) {
+    if (B < 0 || n < 1 || bad_layout(layout) || (B > 0 && (A == nullptr || Ainv == nullptr))) return GMB_ERR_INVALID_ARG;
+    if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    cudaStream_t st = as_stream(stream);
+    if (n >= 2 && n <= 4) return small_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
+    if (n >= 5) {
+        if (A == Ainv) return GMB_ERR_INVALID_ARG;       // invNxN: m must not alias out (MatrixInv.h:174)
+        int rc = subwarp_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    return generic_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
+}
+
+// ------------------------------------------------------------------ host-buffer pipelines
+// AoS host batches are cut into chunks; each chunk goes H2D -> kernel -> D2H on its own stream
+// (3 slots round-robin) so uploads, kernels and downloads of neighbouring chunks overlap and both
+// PCIe directions stay busy.  Device staging buffers are cached per device.
+struct HostArg {
+    const void* src;     // host source (inputs) or nullptr
+    void* dst;           // host destination (outputs) or nullptr
+    size_t bytes_per_system;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void* buf = nullptr;
+    size_t cap = 0;
+};
+
+struct HostCtx {
+    int device = -1;
+    Slot slots[3];
+    std::mutex mu;
+};
+
+static HostCtx* host_ctx(int device) {
+    static std::mutex mu;
+    static std::vector<HostCtx*> all;
+    std::lock_guard<std::mutex> g(mu);
+    for (auto* c : all)
+        if (c->device == device) return c;
+    auto* c = new HostCtx();
+    c->device = device;
+    all.push_back(c);
+    return c;
+}
+
+template <class Launch>
+static int run_host_pipeline(int device, int64_t B, std::vector<HostArg>& args, Launch&& launch) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return GMB_ERR_NO_DEVICE;
+    if (device < 0 || device >= ndev) return GMB_ERR_INVALID_ARG;
+    if (B == 0) return GMB_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    HostCtx* ctx = host_ctx(device);
+    std::lock_guard<std::mutex> g(ctx->mu);
+
+    size_t per_sys = 0;
+    for (auto& a : args) per_sys += (a.bytes_per_system + 15) / 16 * 16;       // keeps every sub-buffer 16B aligned
+    // ~48 MiB per chunk, multiple of 1024 systems (keeps every sub-buffer 16-byte aligned)
+    int64_t chunk = (int64_t)((48u << 20) / per_sys);
+    chunk = chunk / 1024 * 1024;
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > B) chunk = (B + 1023) / 1024 * 1024;
+    const size_t need = (size_t)chunk * per_sys;
+    int rc = GMB_OK;
+    for (auto& s : ctx->slots) {
+        if (!s.stream) {
+            if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
+            if ((e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess) return (int)e;
+        }
+        if (s.cap < need) {
+            if (s.buf) cudaFree(s.buf);
+            s.buf = nullptr;
+            s.cap = 0;
+            if (cudaMalloc(&s.buf, need) != cudaSuccess) return GMB_ERR_ALLOC;
+            s.cap = need;
+        }
+    }
+    std::vector<void*> dptr(args.size());
+    int64_t done = 0;
+    int k = 0;
+    while (done < B && rc == GMB_OK) {
+        const int64_t nb = (B - done) < chunk ? (B - done) : chunk;
+        Slot& s = ctx->slots[k % 3];
+        // the slot's previous chunk must have drained before its buffers are reused (stream order does that)
+        size_t off = 0;
+        for (size_t i = 0; i < args.size(); ++i) {
+            dptr[i] = static_cast<char*>(s.buf) + off;
+            off += (size_t)chunk * ((args[i].bytes_per_system + 15) / 16 * 16);
+            if (args[i].src) {
+                e = cudaMemcpyAsync(dptr[i], static_cast<const char*>(args[i].src) + (size_t)done * args[i].bytes_per_system,
+                                    (size_t)nb * args[i].bytes_per_system, cudaMemcpyHostToDevice, s.stream);
+                if (e != cudaSuccess) rc = (int)e;
+            }
+        }
+        if (rc == GMB_OK) rc = launch(nb, dptr, (void*)s.stream);
+        for (size_t i = 0; i < args.size() && rc == GMB_OK; ++i) {
+            if (args[i].dst) {
+                e = cudaMemcpyAsync(static_cast<char*>(args[i].dst) + (size_t)done * args[i].bytes_per_system, dptr[i],
+                                    (size_t)nb * args[i].bytes_per_system, cudaMemcpyDeviceToHost, s.stream);
+                if (e != cudaSuccess) rc = (int)e;
+            }
+        }
+        done += nb;
+        ++k;
+    }
+    for (auto& s : ctx->slots) {
+        e = cudaStreamSynchronize(s.stream);
+        if (e != cudaSuccess && rc == GMB_OK) rc = (int)e;
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+template <typename T>
+int host_plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, int skip, int rm, int device) {
+    if (B < 0 || n < 1 || m < 1 || (B > 0 && (!A || !Bm || !X))) return GMB_ERR_INVALID_ARG;
+    std::vector<HostArg> args = {{A, nullptr, sizeof(T) * n * n}, {Bm, X, sizeof(T) * n * m}, {nullptr, ok, 1}};
+    return run_host_pipeline(device, B, args, [&](int64_t nb, std::vector<void*>& d, void* st) {
+        return plu_solve<T>(n, m, nb, (const T*)d[0], (const T*)d[1], (T*)d[1], (uint8_t*)d[2], nullptr, skip,
+                            GMB_LAYOUT_AOS, rm, st);
+    });
+}
+
+template <typename T>
+int host_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int srm, int drm, int device) {
+    if (B < 0 || n < 1 || (B > 0 && (!A || !Ainv))) return GMB_ERR_INVALID_ARG;
+    // "out untouched when singular": the destination's current contents travel too only when the
+    // caller passes distinct buffers and asks for ok flags; the common case uploads A only and
+    // writes A^-1 over a scratch copy of A (singular systems then return A itself -- documented).
+    std::vector<HostArg> args = {{A, nullptr, sizeof(T) * n * n}, {Ainv, Ainv, sizeof(T) * n * n}, {nullptr, ok, 1}};
+    return run_host_pipeline(device, B, args, [&](int64_t nb, std::vector<void*>& d, void* st) {
+        return inv<T>(n, nb, (const T*)d[0], (T*)d[1], (uint8_t*)d[2], GMB_LAYOUT_AOS, srm, drm, st);
+    });
+}
+
+template <typename T>
+int host_cholesky_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, int rm, int device) {
+    if (B < 0 || n < 1 || m < 1 || (B > 0 && (!A || !Bm || !X))) return GMB_ERR_INVALID_ARG;
+    std::vector<HostArg> args = {{A, nullptr, sizeof(T) * n * n}, {Bm, X, sizeof(T) * n * m}, {nullptr, ok, 1}};
+    return run_host_pipeline(device, B, args, [&](int64_t nb, std::vector<void*>& d, void* st) {
+        return cholesky<T>(n, m, nb, (const T*)d[0], (const T*)d[1], (T*)d[1], (uint8_t*)d[2], nullptr, GMB_LAYOUT_AOS, rm,
+                           true, st);
+    });
+}
+
+template <typename T>
+int host_plu_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int rm,
+                    int device) {
+    if (B < 0 || rows < 1 || cols < 1 || (B > 0 && !A)) return GMB_ERR_INVALID_ARG;
+    std::vector<HostArg> args = {{A, A, sizeof(T) * rows * cols}, {nullptr, perm, (size_t)rows}, {nullptr, parity, 1},
+                                 {nullptr, degen, 1}};
+    return run_host_pipeline(device, B, args, [&](int64_t nb, std::vector<void*>& d, void* st) {
+        return plu_decomp<T>(rows, cols, nb, (T*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], GMB_LAYOUT_AOS, rm,
+                             false, st);
+    });
+}
+
+}  // namespace gmb
+
+// ==================================================================== extern "C"
+using namespace gmb;
+
+extern "C" {
+
+const char* gmb_version(void) { return "geomc_b200 0.1 (sm_100a)"; }
+
+const char* gmb_error_string(int code) {
+    switch (code) {
+        case GMB_OK: return "ok";
+        case GMB_ERR_INVALID_ARG: return "invalid argument";
+        case GMB_ERR_UNSUPPORTED: return "unsupported dimension (n in 2..16, m in 1..4 for the register kernels)";
+        case GMB_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU fallback)";
+        case GMB_ERR_ALLOC: return "device allocation failed";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int gmb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int gmb_soa_tile_width(int elem_size) { return elem_size > 0 ? 512 / elem_size : 0; }
+
+int64_t gmb_soa_elems(int64_t B, int E, int elem_size) {
+    const int64_t W = gmb_soa_tile_width(elem_size);
+    if (W <= 0 || B < 0 || E < 0) return 0;
+    return (B + W - 1) / W * W * E;
+}
+
+int64_t gmb_launch_count(void) { return g_launch_count.load(); }
+
+void* gmb_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void gmb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+#define GMB_DEFINE(SUF, T)                                                                                            \
+    int gmb_aos_to_soa_##SUF(int E, int64_t B, const T* aos, T* soa, void* stream) {                                  \
+        if (B < 0 || E < 1 || (B > 0 && (!aos || !soa))) return GMB_ERR_INVALID_ARG;                                  \
+        return transpose_batch<T>(true, E, B, aos, soa, as_stream(stream));                                           \
+    }                                                                                                                 \
+    int gmb_soa_to_aos_##SUF(int E, int64_t B, const T* soa, T* aos, void* stream) {                                  \
+        if (B < 0 || E < 1 || (B > 0 && (!aos || !soa))) return GMB_ERR_INVALID_ARG;                                  \
+        return transpose_batch<T>(false, E, B, soa, aos, as_stream(stream));                                          \
+    }                                                                                                                 \
+    int gmb_plu_decomp_##SUF(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen,     \
+                             int layout, int row_major, void* stream) {                                               \
+        return plu_decomp<T>(rows, cols, B, A, perm, parity, degen, layout, row_major, false, stream);                \
+    }                                                                                                                 \
+    int gmb_lup_decomp_##SUF(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen,     \
+                             int layout, int row_major, void* stream) {                                               \
+        return plu_decomp<T>(rows, cols, B, A, perm, parity, degen, layout, row_major, true, stream);                 \
+    }                                                                                                                 \
+    int gmb_lu_backsolve_##SUF(int n, int m, int64_t B, const T* LU, T* X, int skip, int layout, int row_major,       \
+                               void* stream) {                                                                        \
+        return lu_backsolve<T>(0, n, m, B, LU, nullptr, X, X, skip, layout, row_major, stream);                       \
+    }                                                                                                                 \
+    int gmb_plu_backsolve_##SUF(int n, int m, int64_t B, const T* PLU, const uint8_t* perm, T* X, const T* Bm,        \
+                                int skip, int layout, int row_major, void* stream) {                                  \
+        return lu_backsolve<T>(1, n, m, B, PLU, perm, Bm, X, skip, layout, row_major, stream);                        \
+    }                                                                                                                 \
+    int gmb_apply_permutation_##SUF(int n, int m, int64_t B, const uint8_t* perm, T* A, int layout, int row_major,    \
+                                    void* stream) {                                                                   \
+        return lu_backsolve<T>(2, n, m, B, nullptr, perm, A, A, 0, layout, row_major, stream);                        \
+    }                                                                                                                 \
+    int gmb_plu_solve_##SUF(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU_out, int skip, \
+                            int layout, int row_major, void* stream) {                                                \
+        return plu_solve<T>(n, m, B, A, Bm, X, ok, LU_out, skip, layout, row_major, stream);                          \
+    }                                                                                                                 \
+    int gmb_linear_solve_vec_##SUF(int n, int m, int64_t B, const T* bases, const T* Bv, T* X, uint8_t* ok, int skip, \
+                                   int layout, void* stream) {                                                        \
+        return linear_solve_vec<T>(n, m, B, bases, Bv, X, ok, skip, layout, stream);                                  \
+    }                                                                                                                 \
+    int gmb_cholesky_##SUF(int n, int64_t B, T* A, uint8_t* ok, int layout, int row_major, void* stream) {            \
+        return cholesky<T>(n, 1, B, A, nullptr, nullptr, ok, A, layout, row_major, false, stream);                    \
+    }                                                                                                                 \
+    int gmb_cholesky_solve_##SUF(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* L_out,       \
+                                 int layout, int row_major, void* stream) {                                           \
+        return cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, row_major, true, stream);                            \
+    }                                                                                                                 \
+    int gmb_inv_##SUF(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_row_major,              \
+                      int dst_row_major, void* stream) {                                                              \
+        return inv<T>(n, B, A, Ainv, ok, layout, src_row_major, dst_row_major, stream);                               \
+    }                                                                                                                 \
+    int gmb_solve_residual_##SUF(int n, int64_t B, const T* A, const T* X, const T* Bm, const uint8_t* ok,            \
+                                 double* stats4, int layout, int row_major, void* stream) {                           \
+        if (B < 0 || n < 1 || (B > 0 && (!A || !X || !Bm || !stats4))) return GMB_ERR_INVALID_ARG;                    \
+        return residual_stats<T>(n, B, A, X, Bm, ok, stats4, layout, row_major, as_stream(stream));                   \
+    }                                                                                                                 \
+    int gmb_host_plu_solve_##SUF(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, int skip,       \
+                                 int row_major, int device) {                                                         \
+        return host_plu_solve<T>(n, m, B, A, Bm, X, ok, skip, row_major, device);                                     \
+    }                                                                                                                 \
+    int gmb_host_inv_##SUF(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int src_row_major, int dst_row_major,  \
+                           int device) {                                                                              \
+        return host_inv<T>(n, B, A, Ainv, ok, src_row_major, dst_row_major, device);                                  \
+    }                                                                                                                 \
+    int gmb_host_cholesky_solve_##SUF(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok,            \
+                                      int row_major, int device) {                                                    \
+        return host_cholesky_solve<T>(n, m, B, A, Bm, X, ok, row_major, device);                                      \
+    }                                                                                                                 \
+    int gmb_host_plu_decomp_##SUF(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity,                \
+                                  uint8_t* degen, int row_major, int device) {                                        \
+        return host_plu_decomp<T>(rows, cols, B, A, perm, parity, degen, row_major, device);                          \
+    }
+
+GMB_DEFINE(f32, float)
+GMB_DEFINE(f64, double)
+
+int gmb_checksum_bytes(const void* data, int64_t nbytes, int64_t word_offset, uint64_t* out, void* stream) {
+    if (nbytes < 0 || (nbytes > 0 && (!data || !out))) return GMB_ERR_INVALID_ARG;
+    return checksum_bytes(data, nbytes, word_offset, out, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,39 @@
+// gmb_common.cuh -- host-side helpers shared by the launchers.
+#pragma once
+#include <atomic>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+#include <cuda_runtime.h>
+
+#include "../../include/geomc_b200.h"
+
+namespace gmb {
+
+extern std::atomic<int64_t> g_launch_count;
+
+inline int after_launch() {
+    g_launch_count.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? GMB_OK : (int)e;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Call f(std::integral_constant<int, V>{}) for the V in Vs... equal to v; false if none matches.
+template <int... Vs, class F>
+inline bool dispatch_int(int v, F&& f) {
+    bool hit = false;
+    ((v == Vs ? (f(std::integral_constant<int, Vs>{}), hit = true) : false), ...);
+    return hit;
+}
+
+template <class F>
+inline void dispatch_bool(bool b, F&& f) {
+    if (b) f(std::true_type{});
+    else f(std::false_type{});
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace gmb

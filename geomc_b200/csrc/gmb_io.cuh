@@ -1,0 +1,176 @@
+// gmb_io.cuh -- how a thread reaches its systems in HBM.
+//
+// Two batch layouts (include/geomc_b200.h):
+//
+//   GMB_LAYOUT_AOS   the reference's per-object storage: system s, element e at  p[s*E + e]
+//                    (SimpleMatrix.h:145: contiguous T[M*N] per object; Vec: T[N], VecBase.h:112).
+//
+//   GMB_LAYOUT_SOA   the SoA-interleaved batch container: the batch is cut into tiles of
+//                    W = 32 * (16 / sizeof(T)) systems (128 float / 64 double); inside a tile,
+//                    element e of all W systems is contiguous:   p[(tile*E + e)*W + (s % W)].
+//                    A warp reads one element plane of one tile with ONE 128-bit load per lane
+//                    (lane l owns the V = 16/sizeof(T) consecutive systems l*V .. l*V+V-1):
+//                    512 contiguous bytes per warp instruction, every sector fully used.
+//                    Buffers are allocated in whole tiles (gmb_soa_elems()).
+//
+// Loads go through the non-coherent path with L1::no_allocate (streamed once); stores are plain
+// 128-bit STG.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace gmb {
+
+template <typename T> struct VecOf;
+template <> struct VecOf<float>  { using type = float4;  static constexpr int V = 4; };
+template <> struct VecOf<double> { using type = double2; static constexpr int V = 2; };
+
+template <typename T> constexpr int soa_v() { return 16 / (int)sizeof(T); }
+template <typename T> constexpr int soa_w() { return 32 * soa_v<T>(); }
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ldg_stream(const double2* p) {
+    double2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void unpack(const float4& v, float (&o)[4])  { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ float4  pack(const float (&o)[4])  { return make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ double2 pack(const double (&o)[2]) { return make_double2(o[0], o[1]); }
+
+// ---- SoA tile access: q[v][e] for the V systems owned by this lane -------------------------
+template <typename T, int E>
+__device__ __forceinline__ void soa_load(const T* __restrict__ base, int64_t tile, int lane, T (&q)[soa_v<T>()][E]) {
+    constexpr int V = soa_v<T>();
+    constexpr int W = soa_w<T>();
+    using VT = typename VecOf<T>::type;
+    const VT* p = reinterpret_cast<const VT*>(base + tile * (int64_t)(E * W)) + lane;
+    VT tmp[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) tmp[e] = ldg_stream(p + e * 32);      // all loads in flight first
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        T t[V];
+        unpack(tmp[e], t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) q[v][e] = t[v];
+    }
+}
+
+template <typename T, int E>
+__device__ __forceinline__ void soa_store(T* __restrict__ base, int64_t tile, int lane, const T (&q)[soa_v<T>()][E]) {
+    constexpr int V = soa_v<T>();
+    constexpr int W = soa_w<T>();
+    using VT = typename VecOf<T>::type;
+    VT* p = reinterpret_cast<VT*>(base + tile * (int64_t)(E * W)) + lane;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        T t[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) t[v] = q[v][e];
+        p[e * 32] = pack(t);
+    }
+}
+
+// ---- AoS access: one system per thread, widest vector the record size and alignment allow ---
+template <typename T, int E>
+__device__ __forceinline__ void aos_load(const T* __restrict__ base, int64_t s, T (&q)[E]) {
+    const T* p = base + s * (int64_t)E;
+    constexpr int BYTES = E * (int)sizeof(T);
+    if constexpr (BYTES % 16 == 0) {
+        using VT = typename VecOf<T>::type;
+        constexpr int V = soa_v<T>();
+        const VT* pv = reinterpret_cast<const VT*>(p);
+        VT tmp[E / V];
+#pragma unroll
+        for (int i = 0; i < E / V; ++i) tmp[i] = ldg_stream(pv + i);
+#pragma unroll
+        for (int i = 0; i < E / V; ++i) {
+            T t[V];
+            unpack(tmp[i], t);
+#pragma unroll
+            for (int v = 0; v < V; ++v) q[i * V + v] = t[v];
+        }
+    } else if constexpr (sizeof(T) == 4 && BYTES % 8 == 0) {
+        const float2* pv = reinterpret_cast<const float2*>(p);
+#pragma unroll
+        for (int i = 0; i < E / 2; ++i) {
+            float2 t = __ldg(pv + i);
+            q[2 * i] = t.x;
+            q[2 * i + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) q[e] = __ldg(p + e);
+    }
+}
+
+template <typename T, int E>
+__device__ __forceinline__ void aos_store(T* __restrict__ base, int64_t s, const T (&q)[E]) {
+    T* p = base + s * (int64_t)E;
+    constexpr int BYTES = E * (int)sizeof(T);
+    if constexpr (BYTES % 16 == 0) {
+        using VT = typename VecOf<T>::type;
+        constexpr int V = soa_v<T>();
+        VT* pv = reinterpret_cast<VT*>(p);
+#pragma unroll
+        for (int i = 0; i < E / V; ++i) {
+            T t[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) t[v] = q[i * V + v];
+            pv[i] = pack(t);
+        }
+    } else if constexpr (sizeof(T) == 4 && BYTES % 8 == 0) {
+        float2* pv = reinterpret_cast<float2*>(p);
+#pragma unroll
+        for (int i = 0; i < E / 2; ++i) pv[i] = make_float2(q[2 * i], q[2 * i + 1]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) p[e] = q[e];
+    }
+}
+
+// flat element index of logical (r, c): MxWrap, MatrixGlue.h:28-58
+template <int R, int C>
+__device__ __forceinline__ constexpr int flat(bool row_major, int r, int c) {
+    return row_major ? (C * r + c) : (R * c + r);
+}
+
+// flat -> logical register matrix (uniform branch on the runtime layout flag; all indices static)
+template <typename T, int R, int C>
+__device__ __forceinline__ void to_logical(const T (&q)[R * C], T (&a)[R][C], bool row_major) {
+    if (row_major) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) a[r][c] = q[C * r + c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) a[r][c] = q[R * c + r];
+    }
+}
+
+template <typename T, int R, int C>
+__device__ __forceinline__ void from_logical(const T (&a)[R][C], T (&q)[R * C], bool row_major) {
+    if (row_major) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) q[C * r + c] = a[r][c];
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int c = 0; c < C; ++c) q[R * c + r] = a[r][c];
+    }
+}
+
+}  // namespace gmb

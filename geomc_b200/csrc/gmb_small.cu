@@ -1,0 +1,468 @@
+// gmb_small.cu -- N <= 4 kernels: one system per thread slot, everything register-resident.
+//
+// SoA-interleaved batches: a warp owns one tile (W = 32*V systems); lane l holds the V = 16/sizeof(T)
+// consecutive systems l*V.. and moves every element plane with one 128-bit access.
+// AoS batches (the reference's per-object storage): one system per thread, widest vector access
+// the record size allows (the TMA-staged ingest for 64-byte records lives in gmb_tma.cu).
+//
+// No tensor cores: these are independent tiny systems (<= 0.6 flop/byte), bound by HBM; the
+// kernels are plain FFMA/DFMA + IEEE division on the CUDA cores.
+#include "gmb_common.cuh"
+#include "gmb_io.cuh"
+#include "gmb_math.cuh"
+
+namespace gmb {
+
+constexpr int kThreads = 128;
+
+template <typename T, bool SOA>
+struct Work {
+    static constexpr int V = SOA ? soa_v<T>() : 1;
+    static constexpr int W = soa_w<T>();
+    // unit = tile index (SOA) or system index (AOS); s0 = first system of this thread
+    __device__ static __forceinline__ bool locate(int64_t B, int64_t& unit, int& lane, int64_t& s0) {
+        if (SOA) {
+            lane = threadIdx.x & 31;
+            unit = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+            s0 = unit * W + lane * V;
+            return unit * W < B;
+        } else {
+            lane = 0;
+            unit = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+            s0 = unit;
+            return unit < B;
+        }
+    }
+    static int64_t grid(int64_t B) {
+        return SOA ? ceil_div(ceil_div(B, W), kThreads / 32) : ceil_div(B, kThreads);
+    }
+};
+
+template <typename T, int E, bool SOA>
+__device__ __forceinline__ void load_elems(const T* base, int64_t unit, int lane, T (&q)[Work<T, SOA>::V][E]) {
+    if constexpr (SOA) soa_load<T, E>(base, unit, lane, q);
+    else aos_load<T, E>(base, unit, q[0]);
+}
+template <typename T, int E, bool SOA>
+__device__ __forceinline__ void store_elems(T* base, int64_t unit, int lane, const T (&q)[Work<T, SOA>::V][E]) {
+    if constexpr (SOA) soa_store<T, E>(base, unit, lane, q);
+    else aos_store<T, E>(base, unit, q[0]);
+}
+
+// K bytes per system, V systems per thread, AoS byte array [B][K]
+template <int V, int K>
+__device__ __forceinline__ void store_bytes(uint8_t* p, int64_t s0, int64_t B, const uint8_t (&b)[V][K]) {
+    if (p == nullptr) return;
+    constexpr int TOT = V * K;
+    uint8_t* dst = p + s0 * K;
+    if constexpr (TOT % 4 == 0) {
+        if (s0 + V <= B && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+#pragma unroll
+            for (int w = 0; w < TOT / 4; ++w) {
+                uint32_t x = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = w * 4 + k;
+                    x |= (uint32_t)b[i / K][i % K] << (8 * k);
+                }
+                d32[w] = x;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+        if (s0 + v < B) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) dst[v * K + k] = b[v][k];
+        }
+}
+
+template <int V, int K>
+__device__ __forceinline__ void load_bytes(const uint8_t* p, int64_t s0, int64_t B, uint8_t (&b)[V][K]) {
+#pragma unroll
+    for (int v = 0; v < V; ++v)
+#pragma unroll
+        for (int k = 0; k < K; ++k) b[v][k] = (s0 + v < B) ? p[(s0 + v) * K + k] : (uint8_t)k;
+}
+
+template <typename T, int R, int C, bool RM>
+__device__ __forceinline__ void unflatten(const T (&q)[R * C], T (&a)[R][C]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) a[r][c] = q[RM ? C * r + c : R * c + r];
+}
+template <typename T, int R, int C, bool RM>
+__device__ __forceinline__ void flatten(const T (&a)[R][C], T (&q)[R * C]) {
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < C; ++c) q[RM ? C * r + c : R * c + r] = a[r][c];
+}
+
+// ============================================================ a6: fused linear_solve
+template <typename T, int N, int M, bool RM, bool SOA>
+__global__ void __launch_bounds__(kThreads)
+k_plu_solve(const T* __restrict__ A, const T* Bm, T* X, uint8_t* __restrict__ ok, T* __restrict__ LU, int skip,
+            int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    int64_t unit, s0;
+    int lane;
+    if (!Wk::locate(B, unit, lane, s0)) return;
+    T qa[V][N * N], qb[V][N * M];
+    load_elems<T, N * N, SOA>(A, unit, lane, qa);
+    load_elems<T, N * M, SOA>(Bm, unit, lane, qb);
+    uint8_t okv[V][1];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        T a[N][N], x[N][M];
+        unflatten<T, N, N, RM>(qa[v], a);
+        unflatten<T, N, M, RM>(qb[v], x);
+        uint8_t perm[N];
+        bool parity;
+        const int degenerate = plu_rows<T, N, N, M, false>(a, x, perm, parity);
+        backsolve_lu_regs<T, N, M, /*FORWARD=*/false>(a, x, skip);
+        const bool good = degenerate == 0;                      // LUDecomp.h:391-393
+        okv[v][0] = good ? 1 : 0;
+        T qx[N * M];
+        flatten<T, N, M, RM>(x, qx);
+#pragma unroll
+        for (int e = 0; e < N * M; ++e) qb[v][e] = good ? qx[e] : qb[v][e];   // x untouched on failure
+        if (LU != nullptr) flatten<T, N, N, RM>(a, qa[v]);
+    }
+    store_elems<T, N * M, SOA>(X, unit, lane, qb);
+    if (LU != nullptr) store_elems<T, N * N, SOA>(LU, unit, lane, qa);
+    store_bytes<V, 1>(ok, s0, B, okv);
+}
+
+// ============================================================ a1 / a2: decomp_plu / decomp_lup
+template <typename T, int R, int C, bool RM, bool SOA, bool COLPIV>
+__global__ void __launch_bounds__(kThreads)
+k_decomp(T* __restrict__ A, uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out,
+         uint8_t* __restrict__ degen_out, int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    constexpr int NP = COLPIV ? C : R;
+    int64_t unit, s0;
+    int lane;
+    if (!Wk::locate(B, unit, lane, s0)) return;
+    T qa[V][R * C];
+    load_elems<T, R * C, SOA>(A, unit, lane, qa);
+    uint8_t pv[V][NP], par[V][1], deg[V][1];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        T a[R][C];
+        unflatten<T, R, C, RM>(qa[v], a);
+        bool parity;
+        int d;
+        if constexpr (COLPIV) {
+            d = lup_cols<T, R, C>(a, pv[v], parity);
+        } else {
+            T dummy[R][1];
+            d = plu_rows<T, R, C, 0, true>(a, dummy, pv[v], parity);
+        }
+        par[v][0] = parity ? 1 : 0;
+        deg[v][0] = (uint8_t)d;
+        flatten<T, R, C, RM>(a, qa[v]);
+    }
+    store_elems<T, R * C, SOA>(A, unit, lane, qa);
+    store_bytes<V, NP>(perm_out, s0, B, pv);
+    store_bytes<V, 1>(parity_out, s0, B, par);
+    store_bytes<V, 1>(degen_out, s0, B, deg);
+}
+
+// ============================================================ a3 / a4 / a5
+// MODE 0: backsolve_lu (X in place); MODE 1: backsolve_plu (gather Bm rows through perm);
+// MODE 2: apply permutation only.
+template <typename T, int N, int M, bool RM, bool SOA, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_backsolve(const T* __restrict__ LU, const uint8_t* __restrict__ perm, const T* Bm, T* X, int skip, int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    int64_t unit, s0;
+    int lane;
+    if (!Wk::locate(B, unit, lane, s0)) return;
+    T qa[V][N * N], qb[V][N * M];
+    if (MODE != 2) load_elems<T, N * N, SOA>(LU, unit, lane, qa);
+    load_elems<T, N * M, SOA>(Bm, unit, lane, qb);
+    uint8_t pv[V][N];
+    if (MODE != 0) load_bytes<V, N>(perm, s0, B, pv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        T a[N][N], x[N][M];
+        unflatten<T, N, M, RM>(qb[v], x);
+        if (MODE != 0) {
+            // y[r] = b[perm[r]]  (LUDecomp.h:294 / :35-64): dynamic source row -> select chain
+            T y[N][M];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int i = 0; i < M; ++i) {
+                    T t = x[0][i];
+#pragma unroll
+                    for (int k = 1; k < N; ++k) t = (pv[v][r] == k) ? x[k][i] : t;
+                    y[r][i] = t;
+                }
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int i = 0; i < M; ++i) x[r][i] = y[r][i];
+        }
+        if (MODE != 2) {
+            unflatten<T, N, N, RM>(qa[v], a);
+            backsolve_lu_regs<T, N, M, /*FORWARD=*/true>(a, x, skip);
+        }
+        flatten<T, N, M, RM>(x, qb[v]);
+    }
+    store_elems<T, N * M, SOA>(X, unit, lane, qb);
+}
+
+// ============================================================ a8: cholesky, and fused cholesky + solve
+template <typename T, int N, int M, bool RM, bool SOA, bool SOLVE>
+__global__ void __launch_bounds__(kThreads)
+k_cholesky(const T* A, const T* __restrict__ Bm, T* X, uint8_t* __restrict__ ok, T* L_out, int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    int64_t unit, s0;
+    int lane;
+    if (!Wk::locate(B, unit, lane, s0)) return;
+    T qa[V][N * N], qb[V][SOLVE ? N * M : 1];
+    load_elems<T, N * N, SOA>(A, unit, lane, qa);
+    if constexpr (SOLVE) load_elems<T, N * M, SOA>(Bm, unit, lane, qb);
+    uint8_t okv[V][1];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        T a[N][N];
+        unflatten<T, N, N, RM>(qa[v], a);
+        okv[v][0] = cholesky_regs<T, N>(a) ? 1 : 0;
+        if constexpr (SOLVE) {
+            T x[N][M];
+            unflatten<T, N, M, RM>(qb[v], x);
+            cholesky_solve_regs<T, N, M>(a, x);
+            flatten<T, N, M, RM>(x, qb[v]);
+        }
+        flatten<T, N, N, RM>(a, qa[v]);
+    }
+    if constexpr (SOLVE) store_elems<T, N * M, SOA>(X, unit, lane, qb);
+    if (L_out != nullptr) store_elems<T, N * N, SOA>(L_out, unit, lane, qa);
+    store_bytes<V, 1>(ok, s0, B, okv);
+}
+
+// ============================================================ a10 / a13: inv, N <= 4 (adjugate)
+// The flat-array routine is layout-agnostic (inverse of the transpose is the transpose of the
+// inverse); when source and destination layouts differ the result is transposed
+// (MatrixInv.h:290-293, 311-314, 330-334).
+template <typename T, int N, bool SOA, bool TRANSPOSE_OUT>
+__global__ void __launch_bounds__(kThreads)
+k_inv_small(const T* A, T* Ainv, uint8_t* __restrict__ ok, int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    int64_t unit, s0;
+    int lane;
+    if (!Wk::locate(B, unit, lane, s0)) return;
+    T qa[V][N * N], qo[V][N * N];
+    load_elems<T, N * N, SOA>(A, unit, lane, qa);
+    uint8_t okv[V][1];
+    bool all_ok = true;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        T out[N * N];
+#pragma unroll
+        for (int e = 0; e < N * N; ++e) out[e] = qa[v][e];       // placeholder when singular (see below)
+        const bool good = inv_flat<T>(out, qa[v]);
+        okv[v][0] = good ? 1 : 0;
+        all_ok = all_ok && good;
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) qo[v][N * r + c] = out[TRANSPOSE_OUT ? N * c + r : N * r + c];
+    }
+    if (!all_ok) {
+        // "out is unchanged" for singular systems (MatrixInv.h:45-46): re-read the destination.
+        T qd[V][N * N];
+        load_elems<T, N * N, SOA>(Ainv, unit, lane, qd);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int e = 0; e < N * N; ++e) qo[v][e] = okv[v][0] ? qo[v][e] : qd[v][e];
+    }
+    store_elems<T, N * N, SOA>(Ainv, unit, lane, qo);
+    store_bytes<V, 1>(ok, s0, B, okv);
+}
+
+// ============================================================ a7: linear_solve(Vec), N < 5
+// m_inv = inv(bases) into a ROW_MAJOR matrix from a COL_MAJOR source (adjugate on the flat array,
+// then transpose), X <- m_inv * X with `sum = 0; sum = fma(a, b, sum)` n ascending
+// (LUDecomp.h:419-426, MatrixMult.h:54-64).  x holds m vectors of N (column-major N x m).
+template <typename T, int N, int M, bool SOA>
+__global__ void __launch_bounds__(kThreads)
+k_solve_vec_small(const T* __restrict__ bases, const T* Bv, T* X, uint8_t* __restrict__ ok, int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    int64_t unit, s0;
+    int lane;
+    if (!Wk::locate(B, unit, lane, s0)) return;
+    T qa[V][N * N], qb[V][N * M];
+    load_elems<T, N * N, SOA>(bases, unit, lane, qa);
+    load_elems<T, N * M, SOA>(Bv, unit, lane, qb);
+    uint8_t okv[V][1];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        T inv[N * N];
+#pragma unroll
+        for (int e = 0; e < N * N; ++e) inv[e] = (T)0;
+        const bool good = inv_flat<T>(inv, qa[v]);
+        okv[v][0] = good ? 1 : 0;
+        // transposed flat result: minv(r,k) row-major = inv[N*k + r]
+        T out[N * M];
+#pragma unroll
+        for (int c = 0; c < M; ++c)
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                T sum = (T)0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) sum = fma_rn(inv[N * k + r], qb[v][N * c + k], sum);
+                out[N * c + r] = sum;
+            }
+#pragma unroll
+        for (int e = 0; e < N * M; ++e) qb[v][e] = good ? out[e] : qb[v][e];
+    }
+    store_elems<T, N * M, SOA>(X, unit, lane, qb);
+    store_bytes<V, 1>(ok, s0, B, okv);
+}
+
+// ============================================================ launchers (called from gmb_api.cu)
+#define GMB_LAUNCH(kernel, grid, stream, ...)                                   \
+    do {                                                                        \
+        if ((grid) > 0) kernel<<<(unsigned)(grid), kThreads, 0, stream>>>(__VA_ARGS__); \
+        rc = after_launch();                                                    \
+    } while (0)
+
+template <typename T>
+int small_plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout,
+                    int row_major, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_int<1, 2, 3, 4>(m, [&](auto M) {
+            dispatch_bool(row_major != 0, [&](auto RM) {
+                dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                    GMB_LAUNCH((k_plu_solve<T, N.value, M.value, RM.value, SOA.value>), (Work<T, SOA.value>::grid(B)), st,
+                               A, Bm, X, ok, LU, skip, B);
+                });
+            });
+        });
+    });
+    return rc;
+}
+
+template <typename T>
+int small_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout,
+                 int row_major, bool colpiv, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(cols, [&](auto C) {
+        dispatch_bool(rows == cols, [&](auto SQ) {
+            constexpr int R = SQ.value ? C.value : C.value - 1;
+            if (rows != R) return;
+            if constexpr (R >= 1) {
+                dispatch_bool(row_major != 0, [&](auto RM) {
+                    dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                        dispatch_bool(colpiv, [&](auto CP) {
+                            GMB_LAUNCH((k_decomp<T, R, C.value, RM.value, SOA.value, CP.value>),
+                                       (Work<T, SOA.value>::grid(B)), st, A, perm, parity, degen, B);
+                        });
+                    });
+                });
+            }
+        });
+    });
+    return rc;
+}
+
+template <typename T>
+int small_backsolve(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* perm, const T* Bm, T* X, int skip,
+                    int layout, int row_major, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_int<1, 2, 3, 4>(m, [&](auto M) {
+            dispatch_bool(row_major != 0, [&](auto RM) {
+                dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                    dispatch_int<0, 1, 2>(mode, [&](auto MODE) {
+                        GMB_LAUNCH((k_backsolve<T, N.value, M.value, RM.value, SOA.value, MODE.value>),
+                                   (Work<T, SOA.value>::grid(B)), st, LU, perm, Bm, X, skip, B);
+                    });
+                });
+            });
+        });
+    });
+    return rc;
+}
+
+template <typename T>
+int small_cholesky(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* L_out, int layout,
+                   int row_major, bool solve, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_bool(row_major != 0, [&](auto RM) {
+            dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                if (solve) {
+                    dispatch_int<1, 2, 3, 4>(m, [&](auto M) {
+                        GMB_LAUNCH((k_cholesky<T, N.value, M.value, RM.value, SOA.value, true>),
+                                   (Work<T, SOA.value>::grid(B)), st, A, Bm, X, ok, L_out, B);
+                    });
+                } else {
+                    GMB_LAUNCH((k_cholesky<T, N.value, 1, RM.value, SOA.value, false>), (Work<T, SOA.value>::grid(B)),
+                               st, A, Bm, X, ok, L_out, B);
+                }
+            });
+        });
+    });
+    return rc;
+}
+
+template <typename T>
+int small_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+            dispatch_bool((src_rm != 0) != (dst_rm != 0), [&](auto TR) {
+                GMB_LAUNCH((k_inv_small<T, N.value, SOA.value, TR.value>), (Work<T, SOA.value>::grid(B)), st, A, Ainv,
+                           ok, B);
+            });
+        });
+    });
+    return rc;
+}
+
+template <typename T>
+int small_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X, uint8_t* ok, int layout,
+                    cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_int<1, 2, 3, 4>(m, [&](auto M) {
+            dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                GMB_LAUNCH((k_solve_vec_small<T, N.value, M.value, SOA.value>), (Work<T, SOA.value>::grid(B)), st, bases,
+                           Bv, X, ok, B);
+            });
+        });
+    });
+    return rc;
+}
+
+#define INSTANTIATE(T)                                                                                                 \
+    template int small_plu_solve<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int,            \
+                                    cudaStream_t);                                                                     \
+    template int small_decomp<T>(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);   \
+    template int small_backsolve<T>(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int,     \
+                                    cudaStream_t);                                                                     \
+    template int small_cholesky<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool,            \
+                                   cudaStream_t);                                                                      \
+    template int small_inv<T>(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);                      \
+    template int small_solve_vec<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, cudaStream_t);
+
+INSTANTIATE(float)
+INSTANTIATE(double)
+
+}  // namespace gmb

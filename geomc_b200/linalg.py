@@ -1,0 +1,300 @@
+"""Batched geomc/linalg on B200: Python mirror of the reference's function names, one call per BATCH.
+
+Every function takes either AoS CUDA tensors of shape (B, E) -- the reference's own per-object
+storage, E = n*n for matrices and n*m for right-hand sides, flat in the order the ``row_major``
+flag says (MatrixGlue.h:28-58) -- or :class:`BatchSoA` containers (the SoA-interleaved batch
+layout), and goes straight through the C ABI (include/geomc_b200.h) to the CUDA kernels.
+torch is used for device memory and streams only.  No CPU path exists.
+
+Reference function                                   -> here
+    decomp_plu            LUDecomp.h:188             -> decomp_plu
+    decomp_lup            LUDecomp.h:102             -> decomp_lup
+    backsolve_lu          LUDecomp.h:332             -> backsolve_lu
+    backsolve_plu         LUDecomp.h:271             -> backsolve_plu
+    destructive_apply_permutation  LUDecomp.h:35     -> apply_permutation
+    linear_solve(T*,...)  LUDecomp.h:388             -> linear_solve
+    linear_solve(Vec[],…) LUDecomp.h:417             -> linear_solve_vec
+    cholesky              Cholesky.h:37              -> cholesky
+    (none)                                           -> cholesky_solve   (new: fused factor + solve)
+    inv                   Matrix.h:717               -> inv
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple, Union
+
+import torch
+
+from . import _lib
+from ._lib import LAYOUT_AOS, LAYOUT_SOA
+
+_SUF = {torch.float32: "f32", torch.float64: "f64"}
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class BatchSoA:
+    """SoA-interleaved batch container (replaces an array of SimpleMatrix / Vec objects).
+
+    B systems of E elements each; tiles of W = 512/sizeof(T) systems; element e of system s lives
+    at ``data[(s // W * E + e) * W + s % W]``.  Storage is whole tiles.
+    """
+
+    def __init__(self, B: int, E: int, dtype=torch.float32, device="cuda", data: Optional[torch.Tensor] = None):
+        self.B, self.E, self.dtype = int(B), int(E), dtype
+        self.W = _lib.lib().gmb_soa_tile_width(torch.empty(0, dtype=dtype).element_size())
+        n = _lib.lib().gmb_soa_elems(self.B, self.E, torch.empty(0, dtype=dtype).element_size())
+        if data is None:
+            data = torch.zeros(n, dtype=dtype, device=device)
+        assert data.numel() == n and data.dtype == dtype and data.is_cuda and data.is_contiguous()
+        self.data = data
+
+    @property
+    def device(self):
+        return self.data.device
+
+    @property
+    def tiles(self) -> int:
+        return (self.B + self.W - 1) // self.W
+
+    @classmethod
+    def from_aos(cls, aos: torch.Tensor) -> "BatchSoA":
+        """Coalesced AoS -> SoA ingest (gmb_aos_to_soa_*)."""
+        assert aos.is_cuda and aos.dim() == 2 and aos.is_contiguous()
+        B, E = aos.shape
+        out = cls(B, E, aos.dtype, aos.device)
+        _lib.call("gmb_aos_to_soa", _SUF[aos.dtype], E, B, aos.data_ptr(), out.data.data_ptr(), _stream_ptr(aos.device))
+        return out
+
+    def to_aos(self) -> torch.Tensor:
+        out = torch.empty((self.B, self.E), dtype=self.dtype, device=self.device)
+        _lib.call("gmb_soa_to_aos", _SUF[self.dtype], self.E, self.B, self.data.data_ptr(), out.data_ptr(),
+                  _stream_ptr(self.device))
+        return out
+
+    def clone(self) -> "BatchSoA":
+        return BatchSoA(self.B, self.E, self.dtype, self.device, self.data.clone())
+
+    def empty_like(self, E: Optional[int] = None) -> "BatchSoA":
+        return BatchSoA(self.B, self.E if E is None else E, self.dtype, self.device)
+
+
+Batch = Union[torch.Tensor, BatchSoA]
+
+
+def _info(a: Batch):
+    if isinstance(a, BatchSoA):
+        return LAYOUT_SOA, a.B, a.E, a.dtype, a.device, a.data.data_ptr()
+    assert a.is_cuda and a.dim() == 2 and a.is_contiguous(), "AoS batches are contiguous CUDA tensors of shape (B, E)"
+    return LAYOUT_AOS, a.shape[0], a.shape[1], a.dtype, a.device, a.data_ptr()
+
+
+def _clone(a: Batch) -> Batch:
+    return a.clone()
+
+
+def _new_like(a: Batch, E: Optional[int] = None) -> Batch:
+    if isinstance(a, BatchSoA):
+        return a.empty_like(E)
+    return torch.empty((a.shape[0], a.shape[1] if E is None else E), dtype=a.dtype, device=a.device)
+
+
+def _ptr(a: Optional[Batch]) -> Optional[int]:
+    if a is None:
+        return None
+    return a.data.data_ptr() if isinstance(a, BatchSoA) else a.data_ptr()
+
+
+def _u8(B: int, k: int, device) -> torch.Tensor:
+    return torch.zeros((B, k) if k > 1 else (B,), dtype=torch.uint8, device=device)
+
+
+def decomp_plu(m: Batch, rows: int, cols: Optional[int] = None, row_major: bool = True, inplace: bool = False):
+    """LU = P M with row pivoting.  -> (lu, reorder uint8[B,rows], parity uint8[B], degenerate_ct uint8[B])."""
+    cols = rows if cols is None else cols
+    layout, B, E, dt, dev, _ = _info(m)
+    assert E == rows * cols
+    lu = m if inplace else _clone(m)
+    perm, parity, degen = _u8(B, rows, dev).reshape(B, rows), _u8(B, 1, dev), _u8(B, 1, dev)
+    _lib.call("gmb_plu_decomp", _SUF[dt], rows, cols, B, _ptr(lu), perm.data_ptr(), parity.data_ptr(), degen.data_ptr(),
+              layout, int(row_major), _stream_ptr(dev))
+    return lu, perm, parity, degen
+
+
+def decomp_lup(m: Batch, rows: int, cols: Optional[int] = None, row_major: bool = True, inplace: bool = False):
+    """LU = M P with column pivoting.  -> (lu, reorder uint8[B,cols], parity, degenerate_ct)."""
+    cols = rows if cols is None else cols
+    layout, B, E, dt, dev, _ = _info(m)
+    assert E == rows * cols
+    lu = m if inplace else _clone(m)
+    perm, parity, degen = _u8(B, cols, dev).reshape(B, cols), _u8(B, 1, dev), _u8(B, 1, dev)
+    _lib.call("gmb_lup_decomp", _SUF[dt], rows, cols, B, _ptr(lu), perm.data_ptr(), parity.data_ptr(), degen.data_ptr(),
+              layout, int(row_major), _stream_ptr(dev))
+    return lu, perm, parity, degen
+
+
+def backsolve_lu(lu: Batch, x: Batch, n: int, m: int = 1, skip: int = 0, row_major: bool = True, inplace: bool = False):
+    """Solve L U X = X_in (X already permuted).  -> X."""
+    layout, B, E, dt, dev, _ = _info(lu)
+    assert E == n * n and _info(x)[2] == n * m and _info(x)[0] == layout
+    out = x if inplace else _clone(x)
+    _lib.call("gmb_lu_backsolve", _SUF[dt], n, m, B, _ptr(lu), _ptr(out), skip, layout, int(row_major), _stream_ptr(dev))
+    return out
+
+
+def backsolve_plu(plu: Batch, p: torch.Tensor, b: Batch, n: int, m: int = 1, skip: int = 0, row_major: bool = True):
+    """Solve L U X = P B given the row-source array p (uint8[B,n]).  -> X."""
+    layout, B, E, dt, dev, _ = _info(plu)
+    assert E == n * n and p.dtype == torch.uint8 and p.is_contiguous()
+    x = _new_like(b)
+    _lib.call("gmb_plu_backsolve", _SUF[dt], n, m, B, _ptr(plu), p.data_ptr(), _ptr(x), _ptr(b), skip, layout,
+              int(row_major), _stream_ptr(dev))
+    return x
+
+
+def apply_permutation(p: torch.Tensor, a: Batch, n: int, m: int, row_major: bool = True, inplace: bool = False):
+    """A <- P A (row i <- row p[i]).  p is left intact."""
+    layout, B, E, dt, dev, _ = _info(a)
+    assert E == n * m and p.dtype == torch.uint8
+    out = a if inplace else _clone(a)
+    _lib.call("gmb_apply_permutation", _SUF[dt], n, m, B, p.data_ptr(), _ptr(out), layout, int(row_major), _stream_ptr(dev))
+    return out
+
+
+def linear_solve(a: Batch, b: Batch, n: int, m: int = 1, skip: int = 0, row_major: bool = True,
+                 x_out: Optional[Batch] = None, ok_out: Optional[torch.Tensor] = None, want_lu: bool = False):
+    """Fused PLU solve of A X = B (pointer-form linear_solve).  -> (x, ok uint8[B][, lu]).
+
+    ok[s] == 0 iff the reference returns false; then x[s] == b[s] ("x untouched").
+    """
+    layout, B, E, dt, dev, _ = _info(a)
+    assert E == n * n and _info(b)[2] == n * m and _info(b)[0] == layout
+    x = _new_like(b) if x_out is None else x_out
+    ok = _u8(B, 1, dev) if ok_out is None else ok_out
+    lu = _new_like(a) if want_lu else None
+    _lib.call("gmb_plu_solve", _SUF[dt], n, m, B, _ptr(a), _ptr(b), _ptr(x), ok.data_ptr(), _ptr(lu), skip, layout,
+              int(row_major), _stream_ptr(dev))
+    return (x, ok, lu) if want_lu else (x, ok)
+
+
+def linear_solve_vec(bases: Batch, b: Batch, n: int, m: int = 1, skip: int = 0):
+    """Vec-form linear_solve: bases = n column vectors; n < 5 is inverse-then-multiply.  -> (x, ok)."""
+    layout, B, E, dt, dev, _ = _info(bases)
+    assert E == n * n and _info(b)[2] == n * m
+    x = _new_like(b)
+    ok = _u8(B, 1, dev)
+    _lib.call("gmb_linear_solve_vec", _SUF[dt], n, m, B, _ptr(bases), _ptr(b), _ptr(x), ok.data_ptr(), skip, layout,
+              _stream_ptr(dev))
+    return x, ok
+
+
+def cholesky(a: Batch, n: int, row_major: bool = True, inplace: bool = False):
+    """In-place lower Cholesky factor.  -> (L, ok)."""
+    layout, B, E, dt, dev, _ = _info(a)
+    assert E == n * n
+    l = a if inplace else _clone(a)
+    ok = _u8(B, 1, dev)
+    _lib.call("gmb_cholesky", _SUF[dt], n, B, _ptr(l), ok.data_ptr(), layout, int(row_major), _stream_ptr(dev))
+    return l, ok
+
+
+def cholesky_solve(a: Batch, b: Batch, n: int, m: int = 1, row_major: bool = True, x_out: Optional[Batch] = None,
+                   ok_out: Optional[torch.Tensor] = None, want_l: bool = False):
+    """Fused Cholesky factor + solve (framework-defined; the reference has no Cholesky solve).  -> (x, ok[, L])."""
+    layout, B, E, dt, dev, _ = _info(a)
+    assert E == n * n and _info(b)[2] == n * m
+    x = _new_like(b) if x_out is None else x_out
+    ok = _u8(B, 1, dev) if ok_out is None else ok_out
+    l = _new_like(a) if want_l else None
+    _lib.call("gmb_cholesky_solve", _SUF[dt], n, m, B, _ptr(a), _ptr(b), _ptr(x), ok.data_ptr(), _ptr(l), layout,
+              int(row_major), _stream_ptr(dev))
+    return (x, ok, l) if want_l else (x, ok)
+
+
+def inv(a: Batch, n: int, src_row_major: bool = True, dst_row_major: bool = True, out: Optional[Batch] = None,
+        ok_out: Optional[torch.Tensor] = None):
+    """Matrix inverse (adjugate for n <= 4, PLU for n >= 5).  -> (inverse, ok); out[s] untouched where ok == 0."""
+    layout, B, E, dt, dev, _ = _info(a)
+    assert E == n * n
+    if out is None:
+        out = _new_like(a)
+        (out.data if isinstance(out, BatchSoA) else out).zero_()
+    ok = _u8(B, 1, dev) if ok_out is None else ok_out
+    _lib.call("gmb_inv", _SUF[dt], n, B, _ptr(a), _ptr(out), ok.data_ptr(), layout, int(src_row_major),
+              int(dst_row_major), _stream_ptr(dev))
+    return out, ok
+
+
+def solve_residual(a: Batch, x: Batch, b: Batch, ok: Optional[torch.Tensor], n: int, row_major: bool = True) -> torch.Tensor:
+    """Device-side batch statistics: [sum of per-system max|Ax-b|, max, #ok==0, #non-finite] (float64[4])."""
+    layout, B, E, dt, dev, _ = _info(a)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    _lib.call("gmb_solve_residual", _SUF[dt], n, B, _ptr(a), _ptr(x), _ptr(b), None if ok is None else ok.data_ptr(),
+              stats.data_ptr(), layout, int(row_major), _stream_ptr(dev))
+    return stats
+
+
+def checksum(t: torch.Tensor, word_offset: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Additive 64-bit checksum of a device buffer's bytes (int64[1], wraps mod 2^64).
+
+    Shards hashed with their global 8-byte-word offsets sum to the checksum of the whole buffer."""
+    assert t.is_cuda and t.is_contiguous()
+    if out is None:
+        out = torch.zeros(1, dtype=torch.int64, device=t.device)
+    _lib.check(_lib.lib().gmb_checksum_bytes(t.data_ptr(), t.numel() * t.element_size(), word_offset, out.data_ptr(),
+                                             _stream_ptr(t.device)), "gmb_checksum_bytes")
+    return out
+
+
+def checksum_host(buf) -> int:
+    """The same checksum computed with numpy on the host (for tests / cross-checks of small buffers)."""
+    import numpy as np
+    b = np.frombuffer(np.ascontiguousarray(buf).tobytes(), dtype=np.uint8)
+    pad = (-len(b)) % 8
+    w = np.concatenate([b, np.zeros(pad, np.uint8)]).view(np.uint64)
+    with np.errstate(over="ignore"):
+        z = w + np.uint64(0x9E3779B97F4A7C15) * (np.arange(len(w), dtype=np.uint64) + np.uint64(1))
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+        return int(z.sum(dtype=np.uint64))
+
+
+# ------------------------------------------------------------------------- host-buffer entry points
+def _host_ptr(t):
+    import numpy as np
+    if isinstance(t, np.ndarray):
+        assert t.flags["C_CONTIGUOUS"]
+        return t.ctypes.data, t.dtype.itemsize
+    assert not t.is_cuda and t.is_contiguous()
+    return t.data_ptr(), t.element_size()
+
+
+def host_linear_solve(a, b, x, ok, n: int, m: int = 1, skip: int = 0, row_major: bool = True, device: int = 0) -> None:
+    """Host AoS buffers in, host buffers out (pipelined H2D / kernel / D2H).  numpy or CPU torch tensors."""
+    pa, sz = _host_ptr(a)
+    B = a.shape[0]
+    _lib.call("gmb_host_plu_solve", "f32" if sz == 4 else "f64", n, m, B, pa, _host_ptr(b)[0], _host_ptr(x)[0],
+              _host_ptr(ok)[0], skip, int(row_major), device)
+
+
+def host_inv(a, out, ok, n: int, src_row_major: bool = True, dst_row_major: bool = True, device: int = 0) -> None:
+    pa, sz = _host_ptr(a)
+    _lib.call("gmb_host_inv", "f32" if sz == 4 else "f64", n, a.shape[0], pa, _host_ptr(out)[0], _host_ptr(ok)[0],
+              int(src_row_major), int(dst_row_major), device)
+
+
+def host_cholesky_solve(a, b, x, ok, n: int, m: int = 1, row_major: bool = True, device: int = 0) -> None:
+    pa, sz = _host_ptr(a)
+    _lib.call("gmb_host_cholesky_solve", "f32" if sz == 4 else "f64", n, m, a.shape[0], pa, _host_ptr(b)[0],
+              _host_ptr(x)[0], _host_ptr(ok)[0], int(row_major), device)
+
+
+def host_decomp_plu(a, perm, parity, degen, rows: int, cols: Optional[int] = None, row_major: bool = True,
+                    device: int = 0) -> None:
+    cols = rows if cols is None else cols
+    pa, sz = _host_ptr(a)
+    _lib.call("gmb_host_plu_decomp", "f32" if sz == 4 else "f64", rows, cols, a.shape[0], pa, _host_ptr(perm)[0],
+              _host_ptr(parity)[0], _host_ptr(degen)[0], int(row_major), device)

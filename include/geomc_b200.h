@@ -1,0 +1,192 @@
+/* geomc_b200.h -- C ABI of the B200-native batched small-matrix factor/solve engine.
+ *
+ * Drop-in boundary for ONE hot path of trbabb/geomc: the geomc/linalg factor / solve / inverse
+ * functions, applied to a BATCH of B independent systems per call instead of one object per
+ * call.  The reference has no FFI layer of its own (it is a header-only C++ template library),
+ * so each entry point below names the reference template it replaces (file:line under
+ * geomc/linalg/ of the reference) and keeps that function's argument meaning, return meaning
+ * and error behaviour per system.  include/geomc_b200/batch.hpp wraps these in C++ templates
+ * with the reference's names (geom::batch::linear_solve, ...); INTEGRATION.md shows the binding
+ * a geomc maintainer would add.
+ *
+ * Conventions
+ *   - T in {float (suffix _f32), double (suffix _f64)}.  n = matrix dimension, m = number of
+ *     right-hand-side columns, B = number of systems.  2 <= n <= 16 (register/sub-warp kernels).
+ *   - Every pointer in the gmb_* (non gmb_host_*) functions is a DEVICE pointer; `stream` is a
+ *     cudaStream_t passed as void* (NULL = default stream).  Calls are asynchronous.
+ *   - `layout`: GMB_LAYOUT_AOS = the reference's own per-object storage, system s / element e at
+ *     p[s*E + e] (SimpleMatrix.h:145, VecBase.h:112; records must be packed: E = n*n or n*m).
+ *     GMB_LAYOUT_SOA = the SoA-interleaved batch container: tiles of W = 512/sizeof(T) systems
+ *     (128 float / 64 double); p[(s/W * E + e) * W + s%W]; allocate gmb_soa_elems(B, E, sizeof(T))
+ *     elements (whole tiles).  gmb_aos_to_soa_* / gmb_soa_to_aos_* convert.
+ *   - `row_major`: how the E = n*n (or n*m) elements of ONE system map to (r, c), exactly as the
+ *     reference's RowMajor template flag (MatrixGlue.h:28-58): 1 -> e = cols*r + c, 0 -> e = rows*c + r.
+ *   - Per-system results mirror the reference's return values: `ok` (uint8, 1 = true), `parity`
+ *     (uint8), `degenerate` (uint8 count), `perm` (uint8[B][n], AoS in every layout: the reference's
+ *     index_t reorder[] narrowed; row i of P*M is row perm[i] of M, LUDecomp.h:182-183).  Any of
+ *     these output pointers may be NULL.
+ *   - Return value: 0 = success; < 0 = GMB_ERR_*; > 0 = a cudaError_t from the launch.
+ *     There is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef GEOMC_B200_H
+#define GEOMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMB_LAYOUT_AOS 0
+#define GMB_LAYOUT_SOA 1
+
+#define GMB_OK 0
+#define GMB_ERR_INVALID_ARG (-1)
+#define GMB_ERR_UNSUPPORTED (-2)   /* n or m outside the compiled template range */
+#define GMB_ERR_NO_DEVICE (-3)
+#define GMB_ERR_ALLOC (-4)
+
+#define GMB_MAX_N 16
+#define GMB_MAX_M 4                /* right-hand-side columns per call (n for the inverse kernels) */
+
+/* ---- library / container helpers --------------------------------------------------------- */
+const char* gmb_version(void);
+const char* gmb_error_string(int code);
+int gmb_device_count(void);
+/* Systems per SoA tile for an element size (128 for 4-byte, 64 for 8-byte elements). */
+int gmb_soa_tile_width(int elem_size);
+/* Elements to allocate for a SoA batch of B systems with E elements each (whole tiles). */
+int64_t gmb_soa_elems(int64_t B, int E, int elem_size);
+
+/* AoS <-> SoA-interleaved conversion of a batch of B records of E elements (coalesced both
+ * sides through a shared-memory transpose).  Replaces: per-object storage, SimpleMatrix.h:145. */
+int gmb_aos_to_soa_f32(int E, int64_t B, const float* aos, float* soa, void* stream);
+int gmb_aos_to_soa_f64(int E, int64_t B, const double* aos, double* soa, void* stream);
+int gmb_soa_to_aos_f32(int E, int64_t B, const float* soa, float* aos, void* stream);
+int gmb_soa_to_aos_f64(int E, int64_t B, const double* soa, double* aos, void* stream);
+
+/* ---- a1: decomp_plu  (LUDecomp.h:188-250) -------------------------------------------------
+ * In-place Doolittle LU with partial ROW pivoting of a rows x cols matrix: LU = P M.
+ * rows == cols, or rows == cols - 1 (the rectangular case Orthogonal.h:83,161 uses).
+ * perm: uint8[B][rows]; parity: 1 if an odd number of row exchanges; degenerate: number of
+ * zero-pivot columns (the reference's return value). */
+int gmb_plu_decomp_f32(int rows, int cols, int64_t B, float* A_inout, uint8_t* perm, uint8_t* parity,
+                       uint8_t* degenerate, int layout, int row_major, void* stream);
+int gmb_plu_decomp_f64(int rows, int cols, int64_t B, double* A_inout, uint8_t* perm, uint8_t* parity,
+                       uint8_t* degenerate, int layout, int row_major, void* stream);
+
+/* ---- a2: decomp_lup  (LUDecomp.h:102-165) -- COLUMN pivoting, LU = M P; perm: uint8[B][cols]. */
+int gmb_lup_decomp_f32(int rows, int cols, int64_t B, float* A_inout, uint8_t* perm, uint8_t* parity,
+                       uint8_t* degenerate, int layout, int row_major, void* stream);
+int gmb_lup_decomp_f64(int rows, int cols, int64_t B, double* A_inout, uint8_t* perm, uint8_t* parity,
+                       uint8_t* degenerate, int layout, int row_major, void* stream);
+
+/* ---- a3: backsolve_lu  (LUDecomp.h:332-366) -----------------------------------------------
+ * Solves L U X = X_in in place for the n x m matrix X (already row-permuted).  Rows < skip are
+ * left as forward-substituted values ("nonsense" by the reference's contract). */
+int gmb_lu_backsolve_f32(int n, int m, int64_t B, const float* LU, float* X_inout, int skip, int layout,
+                         int row_major, void* stream);
+int gmb_lu_backsolve_f64(int n, int m, int64_t B, const double* LU, double* X_inout, int skip, int layout,
+                         int row_major, void* stream);
+
+/* ---- a4: backsolve_plu  (LUDecomp.h:271-312) -- Y(r,:) = Bm(perm[r],:), then as a3. */
+int gmb_plu_backsolve_f32(int n, int m, int64_t B, const float* PLU, const uint8_t* perm, float* X_out,
+                          const float* Bm, int skip, int layout, int row_major, void* stream);
+int gmb_plu_backsolve_f64(int n, int m, int64_t B, const double* PLU, const uint8_t* perm, double* X_out,
+                          const double* Bm, int skip, int layout, int row_major, void* stream);
+
+/* ---- a5: detail::destructive_apply_permutation  (LUDecomp.h:35-64) -------------------------
+ * A <- P A for the n x m matrix A (row i <- row perm[i]).  perm is NOT clobbered here. */
+int gmb_apply_permutation_f32(int n, int m, int64_t B, const uint8_t* perm, float* A_inout, int layout,
+                              int row_major, void* stream);
+int gmb_apply_permutation_f64(int n, int m, int64_t B, const uint8_t* perm, double* A_inout, int layout,
+                              int row_major, void* stream);
+
+/* ---- a6: linear_solve, pointer form  (LUDecomp.h:388-399) -- THE METRIC KERNEL -------------
+ * Fused decomp_plu + permutation + backsolve_lu: solves A X = Bm.  ok[s] = 0 iff the reference
+ * returns false (degenerate_ct > 0); then X[s] = Bm[s] ("x untouched").  A is not modified
+ * (the reference destroys `a`; pass LU_out != NULL to receive what it would hold: the packed
+ * LU factors, only partially reduced for degenerate systems).  X may alias Bm. */
+int gmb_plu_solve_f32(int n, int m, int64_t B, const float* A, const float* Bm, float* X, uint8_t* ok,
+                      float* LU_out, int skip, int layout, int row_major, void* stream);
+int gmb_plu_solve_f64(int n, int m, int64_t B, const double* A, const double* Bm, double* X, uint8_t* ok,
+                      double* LU_out, int skip, int layout, int row_major, void* stream);
+
+/* ---- a7: linear_solve, Vec form  (LUDecomp.h:417-441) --------------------------------------
+ * bases = n column vectors (column-major n x n), x = m vectors of n.  n < 5: inverse-then-
+ * multiply (inv + mul, :419-426; bases unchanged).  n >= 5: column-major PLU + backsolve
+ * (bases would hold the LU in the reference; here bases is const and LU is discarded). */
+int gmb_linear_solve_vec_f32(int n, int m, int64_t B, const float* bases, const float* Bv, float* X,
+                             uint8_t* ok, int skip, int layout, void* stream);
+int gmb_linear_solve_vec_f64(int n, int m, int64_t B, const double* bases, const double* Bv, double* X,
+                             uint8_t* ok, int skip, int layout, void* stream);
+
+/* ---- a8/a9: cholesky  (Cholesky.h:37-58 / 83-88) -------------------------------------------
+ * In-place lower Cholesky factor (strict upper triangle zeroed); ok = 0 if some pivot <= 0
+ * (the factorization still runs to the end, like the reference). */
+int gmb_cholesky_f32(int n, int64_t B, float* A_inout, uint8_t* ok, int layout, int row_major, void* stream);
+int gmb_cholesky_f64(int n, int64_t B, double* A_inout, uint8_t* ok, int layout, int row_major, void* stream);
+
+/* ---- NEW (no reference counterpart): fused Cholesky factor + solve A X = Bm ---------------
+ * L as a8, then L y = b, L^T x = y (one fma per term, one IEEE division per row).  X is written
+ * for every system (NaNs where ok = 0).  L_out may be NULL. */
+int gmb_cholesky_solve_f32(int n, int m, int64_t B, const float* A, const float* Bm, float* X, uint8_t* ok,
+                           float* L_out, int layout, int row_major, void* stream);
+int gmb_cholesky_solve_f64(int n, int m, int64_t B, const double* A, const double* Bm, double* X, uint8_t* ok,
+                           double* L_out, int layout, int row_major, void* stream);
+
+/* ---- a10/a12/a13: inv  (Matrix.h:717-735 -> MatrixInv.h:49-165, 219-231, 241-337) ---------
+ * n <= 4: adjugate with the reference's diff_of_products call tree; n >= 5: row-major PLU in the
+ * destination's layout + back-substitution against the permuted identity.  ok = 0 -> Ainv[s] is
+ * left untouched.  Ainv may alias A for n <= 4 only (as in the reference). */
+int gmb_inv_f32(int n, int64_t B, const float* A, float* Ainv, uint8_t* ok, int layout, int src_row_major,
+                int dst_row_major, void* stream);
+int gmb_inv_f64(int n, int64_t B, const double* A, double* Ainv, uint8_t* ok, int layout, int src_row_major,
+                int dst_row_major, void* stream);
+
+/* ---- batch statistics (what the reference's tests assert, reduced on the device) ------------
+ * stats[0] = sum over systems of max_i |(A x - b)_i| (only systems with ok != 0),
+ * stats[1] = max of the same, stats[2] = number of systems with ok == 0,
+ * stats[3] = number of systems whose residual is not finite.   (double[4], device memory;
+ * accumulated into -- zero it first.)  m = 1. */
+int gmb_solve_residual_f32(int n, int64_t B, const float* A, const float* X, const float* Bm, const uint8_t* ok,
+                           double* stats4, int layout, int row_major, void* stream);
+int gmb_solve_residual_f64(int n, int64_t B, const double* A, const double* X, const double* Bm, const uint8_t* ok,
+                           double* stats4, int layout, int row_major, void* stream);
+/* Additive 64-bit checksum of a byte buffer: sum (mod 2^64) over 8-byte words w of
+ * mix64(word + K * (word_offset + w + 1)).  Shards of one buffer hashed with their global word
+ * offsets add up to the checksum of the whole ("checksum of checksums" across GPUs; a shard must
+ * start on an 8-byte boundary of the whole).  *out (device) is accumulated into. */
+int gmb_checksum_bytes(const void* data, int64_t nbytes, int64_t word_offset, uint64_t* out, void* stream);
+
+/* ---- host-buffer entry points (the call a host application makes) ---------------------------
+ * All pointers are HOST pointers to AoS batches (the reference's own arrays of objects).  The
+ * call copies host->device, runs the kernel and copies the results back, pipelined in chunks
+ * over several streams on `device`; it returns when the results are in the host buffers.
+ * Pinned buffers (gmb_host_alloc, or cudaHostRegister'ed memory) give full PCIe bandwidth. */
+void* gmb_host_alloc(size_t bytes);
+void gmb_host_free(void* p);
+int gmb_host_plu_solve_f32(int n, int m, int64_t B, const float* A, const float* Bm, float* X, uint8_t* ok,
+                           int skip, int row_major, int device);
+int gmb_host_plu_solve_f64(int n, int m, int64_t B, const double* A, const double* Bm, double* X, uint8_t* ok,
+                           int skip, int row_major, int device);
+int gmb_host_inv_f32(int n, int64_t B, const float* A, float* Ainv, uint8_t* ok, int src_row_major,
+                     int dst_row_major, int device);
+int gmb_host_inv_f64(int n, int64_t B, const double* A, double* Ainv, uint8_t* ok, int src_row_major,
+                     int dst_row_major, int device);
+int gmb_host_cholesky_solve_f64(int n, int m, int64_t B, const double* A, const double* Bm, double* X,
+                                uint8_t* ok, int row_major, int device);
+int gmb_host_cholesky_solve_f32(int n, int m, int64_t B, const float* A, const float* Bm, float* X,
+                                uint8_t* ok, int row_major, int device);
+int gmb_host_plu_decomp_f64(int rows, int cols, int64_t B, double* A_inout, uint8_t* perm, uint8_t* parity,
+                            uint8_t* degenerate, int row_major, int device);
+int gmb_host_plu_decomp_f32(int rows, int cols, int64_t B, float* A_inout, uint8_t* perm, uint8_t* parity,
+                            uint8_t* degenerate, int row_major, int device);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t gmb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOMC_B200_H */

@@ -1,0 +1,244 @@
+"""GPU suite: the CUDA path, called through the C ABI, against the CPU oracle.
+
+* the committed golden fixtures (outputs of the reference itself, tests/golden/),
+* seeded random batches against oracle.c (which test_oracle_vs_ref.py pins to the reference),
+for every hot-path function, float and double, AoS and SoA-interleaved layouts, row- and
+column-major, N = 2..16, including singular / non-SPD / non-finite systems.
+
+Bar (BASELINE.json north_star): pivot permutation, parity, degenerate counts and ok flags are
+bit-exact.  Factors and solutions are ALSO required bit-exact here (tolerance 0 ulp; NaN == NaN),
+which is stricter than the stated "float <= 4 ulp / double <= 1e-12": the kernels spell the same
+IEEE operation sequence as the reference.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_SIZES, bits_equal, first_diff, load_golden
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TDT = {np.dtype(np.float32): "float32", np.dtype(np.float64): "float64"}
+
+
+@pytest.fixture(scope="module")
+def gm():
+    import geomc_b200 as gm
+    gm.lib()   # raises if the CUDA library is missing -- no fallback
+    assert torch.cuda.is_available()
+    return gm
+
+
+def up(gm, a, soa):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return gm.BatchSoA.from_aos(t) if soa else t
+
+
+def down(x):
+    if hasattr(x, "to_aos"):
+        x = x.to_aos()
+    return x.cpu().numpy()
+
+
+def check(got, want, what):
+    assert bits_equal(got, want), f"{what}: {first_diff(got, want)}"
+
+
+def run_all(gm, port, n, A, b1, b3, S, soa, expect=None):
+    """Run every entry point on one input set and compare with `expect` (golden dict) or the port."""
+    with np.errstate(all="ignore"):
+        for rm, r in ((True, "rm"), (False, "cm")):
+            tag = f"n={n} soa={soa} {r}"
+            dA, db1, db3, dS = up(gm, A, soa), up(gm, b1, soa), up(gm, b3, soa), up(gm, S, soa)
+            # a1 decomp_plu
+            lu, p, par, dg = gm.decomp_plu(dA, n, n, rm)
+            e = expect and (expect[f"plu_{r}_lu"], expect[f"plu_{r}_p"], expect[f"plu_{r}_parity"], expect[f"plu_{r}_degen"]) \
+                or port.decomp_plu(A, n, n, rm)
+            check(down(lu), e[0], f"decomp_plu lu {tag}")
+            check(down(p).astype(np.int64), e[1], f"decomp_plu reorder {tag}")
+            check(down(par), e[2], f"decomp_plu parity {tag}")
+            check(down(dg).astype(np.int64), e[3], f"decomp_plu degenerate {tag}")
+            # a2 decomp_lup
+            lu2, p2, par2, dg2 = gm.decomp_lup(dA, n, n, rm)
+            e = expect and (expect[f"lup_{r}_lu"], expect[f"lup_{r}_p"], expect[f"lup_{r}_parity"], expect[f"lup_{r}_degen"]) \
+                or port.decomp_lup(A, n, n, rm)
+            check(down(lu2), e[0], f"decomp_lup lu {tag}")
+            check(down(p2).astype(np.int64), e[1], f"decomp_lup reorder {tag}")
+            check(down(par2), e[2], f"decomp_lup parity {tag}")
+            check(down(dg2).astype(np.int64), e[3], f"decomp_lup degenerate {tag}")
+            # a6 linear_solve (fused), m = 1 and m = 3 / skip = 1, plus the LU it leaves in `a`
+            x, ok, lua = gm.linear_solve(dA, db1, n, 1, 0, rm, want_lu=True)
+            e = expect and (expect[f"solve_{r}_a"], expect[f"solve_{r}_x"], expect[f"solve_{r}_ok"]) \
+                or port.linear_solve(A, b1, n, 1, 0, rm)
+            check(down(x), e[1], f"linear_solve x {tag}")
+            check(down(ok), e[2], f"linear_solve ok {tag}")
+            check(down(lua), e[0], f"linear_solve a (LU) {tag}")
+            x3, ok3 = gm.linear_solve(dA, db3, n, 3, 1, rm)
+            e = expect and (None, expect[f"solve3s1_{r}_x"], expect[f"solve3s1_{r}_ok"]) or port.linear_solve(A, b3, n, 3, 1, rm)
+            check(down(x3), e[1], f"linear_solve m=3 skip=1 x {tag}")
+            check(down(ok3), e[2], f"linear_solve m=3 skip=1 ok {tag}")
+            # a3 / a4 / a5 on the reference LU
+            lu_np, p_np = down(lu), down(p)
+            e = expect and expect[f"bslu_{r}_x"] or port.backsolve_lu(lu_np, b3, n, 3, 0, rm)
+            check(down(gm.backsolve_lu(lu, db3, n, 3, 0, rm)), e, f"backsolve_lu {tag}")
+            e = expect and expect[f"bsplu_{r}_x"] or port.backsolve_plu(lu_np, p_np.astype(np.int64), b3, n, 3, 0, rm)
+            check(down(gm.backsolve_plu(lu, p, db3, n, 3, 0, rm)), e, f"backsolve_plu {tag}")
+            e = expect and expect[f"perm_{r}_a"] or port.apply_perm(p_np.astype(np.int64), b3, n, 3, rm)[0]
+            check(down(gm.apply_permutation(p, db3, n, 3, rm)), e, f"apply_permutation {tag}")
+            # a8 cholesky
+            L, okc = gm.cholesky(dS, n, rm)
+            e = expect and (expect[f"chol_{r}_l"], expect[f"chol_{r}_ok"]) or port.cholesky(S, n, rm)
+            check(down(L), e[0], f"cholesky L {tag}")
+            check(down(okc), e[1], f"cholesky ok {tag}")
+            # new: cholesky_solve against the port's definition
+            Lp, okp = port.cholesky(S, n, rm)
+            xs, oks, Ls = gm.cholesky_solve(dS, db1, n, 1, rm, want_l=True)
+            check(down(Ls), Lp, f"cholesky_solve L {tag}")
+            check(down(oks), okp, f"cholesky_solve ok {tag}")
+            check(down(xs), port.cholesky_solve(Lp, b1, n, 1, rm), f"cholesky_solve x {tag}")
+            # a13 inv, all four layout combinations, destination pre-filled with 7
+            for drm, q in ((True, "rm"), (False, "cm")):
+                init = np.full_like(A, 7)
+                out, oki = gm.inv(dA, n, rm, drm, out=up(gm, init, soa))
+                e = expect and (expect[f"inv_{r}_{q}"], expect[f"inv_{r}_{q}_ok"]) or port.inv(A, n, rm, drm, init)
+                check(down(out), e[0], f"inv {r}->{q} {tag}")
+                check(down(oki), e[1], f"inv ok {r}->{q} {tag}")
+        # a7 Vec-form linear_solve
+        xv, okv = gm.linear_solve_vec(up(gm, A, soa), up(gm, b1, soa), n, 1, 0)
+        e = expect and (None, expect["solvevec_x"], expect["solvevec_ok"]) or port.linear_solve_vec(A, b1, n, 1, 0)
+        check(down(xv), e[1], f"linear_solve(Vec) x n={n} soa={soa}")
+        check(down(okv), e[2], f"linear_solve(Vec) ok n={n} soa={soa}")
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+@pytest.mark.parametrize("n", GOLDEN_SIZES)
+def test_golden(gm, port, tag, n, soa):
+    g = load_golden(tag, n)
+    run_all(gm, port, n, g["A"], g["b1"], g["b3"], g["S"], soa, expect=g)
+    # rectangular decomp_plu ((n-1) x n), as used by nullspace / orthogonal
+    lur, pr, parr, dgr = gm.decomp_plu(up(gm, g["rect_m"], soa), n - 1, n, True)
+    check(down(lur), g["rect_lu"], "rect lu")
+    check(down(pr).astype(np.int64).reshape(g["rect_p"].shape), g["rect_p"], "rect reorder")
+    check(down(parr), g["rect_parity"], "rect parity")
+    check(down(dgr).astype(np.int64), g["rect_degen"], "rect degen")
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", list(range(2, 17)))
+def test_random_vs_oracle(gm, port, dt, n, soa):
+    """Seeded random batches whose size is NOT a multiple of the tile width (ragged last tile)."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(4242 + 100 * n + np.dtype(dt).itemsize)
+    B = 1000 + 37 if n <= 8 else 300 + 5
+    A = rng.standard_normal((B, n * n)).astype(dt)
+    A[::97] = 0
+    A[5::101, 0::n] = 0
+    b1 = rng.standard_normal((B, n)).astype(dt)
+    b3 = rng.standard_normal((B, n * 3)).astype(dt)
+    S = po.spd_exact(rng, B, n, dt)
+    S[::53, 0] = -1
+    run_all(gm, port, n, A, b1, b3, S, soa)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_empty_and_tiny_batches(gm, dt):
+    for B in (0, 1, 3):
+        for soa in (False, True):
+            A = np.tile(np.eye(4, dtype=dt).reshape(1, 16), (B, 1)) * 2
+            b = np.ones((B, 4), dt)
+            x, ok = gm.linear_solve(up(gm, A, soa) if B else (gm.BatchSoA(0, 16, getattr(torch, TDT[np.dtype(dt)])) if soa else torch.empty((0, 16), dtype=getattr(torch, TDT[np.dtype(dt)]), device="cuda")),
+                                    up(gm, b, soa) if B else (gm.BatchSoA(0, 4, getattr(torch, TDT[np.dtype(dt)])) if soa else torch.empty((0, 4), dtype=getattr(torch, TDT[np.dtype(dt)]), device="cuda")),
+                                    4)
+            assert down(ok).shape == (B,)
+            if B:
+                assert np.array_equal(down(x), np.full((B, 4), 0.5, dt))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("E", [4, 9, 16, 3, 25, 64, 256])
+def test_aos_soa_round_trip(gm, dt, E):
+    rng = np.random.default_rng(E)
+    for B in (1, 127, 128, 129, 1000):
+        a = rng.standard_normal((B, E)).astype(dt)
+        soa = up(gm, a, True)
+        assert np.array_equal(down(soa), a)
+        # container layout: element e of system s at ((s // W) * E + e) * W + s % W
+        W = soa.W
+        flat = soa.data.cpu().numpy()
+        s = B - 1
+        for e in (0, E - 1):
+            assert flat[((s // W) * E + e) * W + s % W] == a[s, e]
+
+
+def test_host_api_matches_device_api(gm, port):
+    rng = np.random.default_rng(9)
+    B, n = 70001, 4
+    A = rng.standard_normal((B, n * n)).astype(np.float32)
+    A[::1000] = 0
+    b = rng.standard_normal((B, n)).astype(np.float32)
+    x = np.zeros_like(b)
+    ok = np.zeros(B, np.uint8)
+    gm.host_linear_solve(A, b, x, ok, n)
+    _, xe, oke = port.linear_solve(A, b, n)
+    check(x, xe, "host linear_solve x")
+    check(ok, oke, "host linear_solve ok")
+    out = np.full_like(A, 3)
+    gm.host_inv(A, out, ok, n)
+    oe, oke = port.inv(A, n, True, True, np.full_like(A, 3))
+    check(out, oe, "host inv")
+    check(ok, oke, "host inv ok")
+    from oracle import pyoracle as po
+    S = po.spd_exact(rng, B, 3, np.float64)
+    b3 = po.exact_grid(rng, (B, 3), np.float64)
+    x3 = np.zeros_like(b3)
+    gm.host_cholesky_solve(S, b3, x3, ok, 3)
+    L, okc = port.cholesky(S, 3)
+    check(x3, port.cholesky_solve(L, b3, 3), "host cholesky_solve")
+    check(ok, okc, "host cholesky ok")
+    A8 = rng.standard_normal((B // 7, 64))
+    lu = A8.copy()
+    p = np.zeros((B // 7, 8), np.uint8)
+    par = np.zeros(B // 7, np.uint8)
+    dg = np.zeros(B // 7, np.uint8)
+    gm.host_decomp_plu(lu, p, par, dg, 8)
+    e = port.decomp_plu(A8, 8)
+    check(lu, e[0], "host decomp lu")
+    check(p.astype(np.int64), e[1], "host decomp perm")
+    check(par, e[2], "host decomp parity")
+
+
+def test_full_size_properties(gm):
+    """BASELINE-size batch (2^24 4x4 float systems): size-independent properties instead of the oracle.
+    (1) residual of A x = b stays small on every system, (2) inverse round trip inv(inv(A)) ~ A,
+    (3) the SoA and AoS paths produce the same bits, (4) the checksum of checksums over two halves
+    equals the checksum of the whole."""
+    B, n = 1 << 24, 4
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = (torch.randint(-(1 << 19), 1 << 19, (B, 16), device="cuda", generator=g).float() * 2.0 ** -17)
+    b = (torch.randint(-(1 << 19), 1 << 19, (B, 4), device="cuda", generator=g).float() * 2.0 ** -17)
+    x, ok = gm.linear_solve(A, b, n)
+    stats = gm.solve_residual(A, x, b, ok, n).cpu().numpy()
+    n_ok = B - stats[2]
+    assert stats[2] < 10 and stats[3] < 10
+    assert stats[0] / n_ok < 1e-4          # mean max-residual (float, |entries| < 4)
+    xs, oks = gm.linear_solve(gm.BatchSoA.from_aos(A), gm.BatchSoA.from_aos(b), n)
+    assert torch.equal(xs.to_aos().view(torch.int32), x.view(torch.int32))
+    assert torch.equal(oks, ok)
+    half = B // 2
+    c = gm.checksum(ok).item()
+    acc = gm.checksum(ok[:half], 0)
+    gm.checksum(ok[half:], half // 8, out=acc)               # checksum of checksums
+    assert acc.item() == c
+    okf = ok.clone()
+    okf[12345] ^= 1
+    assert gm.checksum(okf).item() != c
+    small = ok[:100003].contiguous()
+    from geomc_b200.linalg import checksum_host
+    assert gm.checksum(small).item() % (1 << 64) == checksum_host(small.cpu().numpy()) % (1 << 64)
+    inv1, ok1 = gm.inv(A, n)
+    inv2, ok2 = gm.inv(inv1, n)
+    good = (ok1 == 1) & (ok2 == 1)
+    rel = ((inv2 - A).abs().amax(dim=1) / A.abs().amax(dim=1))[good]
+    assert rel.median().item() < 1e-4
