@@ -33,6 +33,14 @@ def first_diff(a, b):
     a = np.asarray(a)
     b = np.asarray(b)
     bad = np.argwhere(~((a == b) | (np.isnan(a) & np.isnan(b)))) if a.dtype.kind == "f" else np.argwhere(a != b)
+    if len(bad) == 0 and a.dtype.kind == "f":
+        u = f"u{a.itemsize}"
+        ok = np.isnan(a) & np.isnan(b)
+        bad = np.argwhere((a.view(u) != b.view(u)) & ~ok)
+        if len(bad):
+            i = tuple(bad[0])
+            return (f"{len(bad)} bit-level diffs (signed zero), first at {i}: {a[i]!r} ({a.view(u)[i]:#x}) vs "
+                    f"{b[i]!r} ({b.view(u)[i]:#x}); rows {sorted(set(int(x[0]) for x in bad))[:8]}")
     if len(bad) == 0:
         return "no value difference (signed zero?)"
     i = tuple(bad[0])

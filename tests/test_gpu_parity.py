@@ -52,42 +52,39 @@ def run_all(gm, port, n, A, b1, b3, S, soa, expect=None):
             dA, db1, db3, dS = up(gm, A, soa), up(gm, b1, soa), up(gm, b3, soa), up(gm, S, soa)
             # a1 decomp_plu
             lu, p, par, dg = gm.decomp_plu(dA, n, n, rm)
-            e = expect and (expect[f"plu_{r}_lu"], expect[f"plu_{r}_p"], expect[f"plu_{r}_parity"], expect[f"plu_{r}_degen"]) \
-                or port.decomp_plu(A, n, n, rm)
+            e = (expect[f"plu_{r}_lu"], expect[f"plu_{r}_p"], expect[f"plu_{r}_parity"], expect[f"plu_{r}_degen"]) if expect is not None else port.decomp_plu(A, n, n, rm)
             check(down(lu), e[0], f"decomp_plu lu {tag}")
             check(down(p).astype(np.int64), e[1], f"decomp_plu reorder {tag}")
             check(down(par), e[2], f"decomp_plu parity {tag}")
             check(down(dg).astype(np.int64), e[3], f"decomp_plu degenerate {tag}")
             # a2 decomp_lup
             lu2, p2, par2, dg2 = gm.decomp_lup(dA, n, n, rm)
-            e = expect and (expect[f"lup_{r}_lu"], expect[f"lup_{r}_p"], expect[f"lup_{r}_parity"], expect[f"lup_{r}_degen"]) \
-                or port.decomp_lup(A, n, n, rm)
+            e = (expect[f"lup_{r}_lu"], expect[f"lup_{r}_p"], expect[f"lup_{r}_parity"], expect[f"lup_{r}_degen"]) if expect is not None else port.decomp_lup(A, n, n, rm)
             check(down(lu2), e[0], f"decomp_lup lu {tag}")
             check(down(p2).astype(np.int64), e[1], f"decomp_lup reorder {tag}")
             check(down(par2), e[2], f"decomp_lup parity {tag}")
             check(down(dg2).astype(np.int64), e[3], f"decomp_lup degenerate {tag}")
             # a6 linear_solve (fused), m = 1 and m = 3 / skip = 1, plus the LU it leaves in `a`
             x, ok, lua = gm.linear_solve(dA, db1, n, 1, 0, rm, want_lu=True)
-            e = expect and (expect[f"solve_{r}_a"], expect[f"solve_{r}_x"], expect[f"solve_{r}_ok"]) \
-                or port.linear_solve(A, b1, n, 1, 0, rm)
+            e = (expect[f"solve_{r}_a"], expect[f"solve_{r}_x"], expect[f"solve_{r}_ok"]) if expect is not None else port.linear_solve(A, b1, n, 1, 0, rm)
             check(down(x), e[1], f"linear_solve x {tag}")
             check(down(ok), e[2], f"linear_solve ok {tag}")
             check(down(lua), e[0], f"linear_solve a (LU) {tag}")
             x3, ok3 = gm.linear_solve(dA, db3, n, 3, 1, rm)
-            e = expect and (None, expect[f"solve3s1_{r}_x"], expect[f"solve3s1_{r}_ok"]) or port.linear_solve(A, b3, n, 3, 1, rm)
+            e = (None, expect[f"solve3s1_{r}_x"], expect[f"solve3s1_{r}_ok"]) if expect is not None else port.linear_solve(A, b3, n, 3, 1, rm)
             check(down(x3), e[1], f"linear_solve m=3 skip=1 x {tag}")
             check(down(ok3), e[2], f"linear_solve m=3 skip=1 ok {tag}")
             # a3 / a4 / a5 on the reference LU
             lu_np, p_np = down(lu), down(p)
-            e = expect and expect[f"bslu_{r}_x"] or port.backsolve_lu(lu_np, b3, n, 3, 0, rm)
+            e = expect[f"bslu_{r}_x"] if expect is not None else port.backsolve_lu(lu_np, b3, n, 3, 0, rm)
             check(down(gm.backsolve_lu(lu, db3, n, 3, 0, rm)), e, f"backsolve_lu {tag}")
-            e = expect and expect[f"bsplu_{r}_x"] or port.backsolve_plu(lu_np, p_np.astype(np.int64), b3, n, 3, 0, rm)
+            e = expect[f"bsplu_{r}_x"] if expect is not None else port.backsolve_plu(lu_np, p_np.astype(np.int64), b3, n, 3, 0, rm)
             check(down(gm.backsolve_plu(lu, p, db3, n, 3, 0, rm)), e, f"backsolve_plu {tag}")
-            e = expect and expect[f"perm_{r}_a"] or port.apply_perm(p_np.astype(np.int64), b3, n, 3, rm)[0]
+            e = expect[f"perm_{r}_a"] if expect is not None else port.apply_perm(p_np.astype(np.int64), b3, n, 3, rm)[0]
             check(down(gm.apply_permutation(p, db3, n, 3, rm)), e, f"apply_permutation {tag}")
             # a8 cholesky
             L, okc = gm.cholesky(dS, n, rm)
-            e = expect and (expect[f"chol_{r}_l"], expect[f"chol_{r}_ok"]) or port.cholesky(S, n, rm)
+            e = (expect[f"chol_{r}_l"], expect[f"chol_{r}_ok"]) if expect is not None else port.cholesky(S, n, rm)
             check(down(L), e[0], f"cholesky L {tag}")
             check(down(okc), e[1], f"cholesky ok {tag}")
             # new: cholesky_solve against the port's definition
@@ -100,12 +97,12 @@ def run_all(gm, port, n, A, b1, b3, S, soa, expect=None):
             for drm, q in ((True, "rm"), (False, "cm")):
                 init = np.full_like(A, 7)
                 out, oki = gm.inv(dA, n, rm, drm, out=up(gm, init, soa))
-                e = expect and (expect[f"inv_{r}_{q}"], expect[f"inv_{r}_{q}_ok"]) or port.inv(A, n, rm, drm, init)
+                e = (expect[f"inv_{r}_{q}"], expect[f"inv_{r}_{q}_ok"]) if expect is not None else port.inv(A, n, rm, drm, init)
                 check(down(out), e[0], f"inv {r}->{q} {tag}")
                 check(down(oki), e[1], f"inv ok {r}->{q} {tag}")
         # a7 Vec-form linear_solve
         xv, okv = gm.linear_solve_vec(up(gm, A, soa), up(gm, b1, soa), n, 1, 0)
-        e = expect and (None, expect["solvevec_x"], expect["solvevec_ok"]) or port.linear_solve_vec(A, b1, n, 1, 0)
+        e = (None, expect["solvevec_x"], expect["solvevec_ok"]) if expect is not None else port.linear_solve_vec(A, b1, n, 1, 0)
         check(down(xv), e[1], f"linear_solve(Vec) x n={n} soa={soa}")
         check(down(okv), e[2], f"linear_solve(Vec) ok n={n} soa={soa}")
 
