@@ -1,24 +1,331 @@
-// gmb_subwarp.cu -- sub-warp cooperative kernels for n = 5..16 (placeholder: falls through to the
-// generic one-thread-per-system kernels until the cooperative kernels land).
+// gmb_subwarp.cu -- sub-warp cooperative PLU kernels for n = 5..16.
+//
+// A group of G lanes (G = 1, 2, 4, 8 -- the smallest that keeps the working set in registers)
+// owns one system.  The augmented matrix [A | riders] (N rows, N + XC columns) is split into
+// blocks of LC = ceil((N + XC) / G) consecutive columns; lane l of the group holds all N rows of
+// its LC columns in registers.  Per elimination step i (fully unrolled, every register index
+// static):
+//   * the lane owning column i searches the pivot (first strict maximum of |a(p,i)|, p >= i,
+//     LUDecomp.h:205-213) and broadcasts it with ONE shuffle as a one-hot row mask (+ the
+//     `biggest == 0` flag) -- a mask, not an index, so the exchange below stays in registers;
+//   * every lane exchanges rows i and pvt in its own columns (whole rows, L part included, :222);
+//   * the owner computes the multipliers b_r = a(r,i) / a(i,i) (IEEE division, :234) and
+//     broadcasts them (N-1-i shuffles); every lane applies the rank-1 update
+//     a(r,c) = fma(-b_r, a(i,c), a(r,c)) to its own columns c > i, skipped where b_r == 0 (:235-241).
+// Riders (right-hand sides for linear_solve, the permuted identity for invNxN) are extra
+// columns: exchanged in lock-step (= destructive_apply_permutation, :35) and eliminated with the
+// same multipliers without the b == 0 skip (= backsolve_lu's forward sweep, :345-353).
+// The backward sweep is column-oriented: for c = N-1..0, x(c) /= u(c,c), then x(r) =
+// fma(-x(c), u(r,c), x(r)) for r < c -- for every row the terms arrive in the reference's
+// order (c descending, :356-365), so the result is bit-identical.
+//
+// No tensor cores: the systems are independent, 16x16 at most, and the pivot search is
+// sequential in i; this is FFMA/DFMA + IEEE division + SHFL.
 #include "gmb_common.cuh"
+#include "gmb_io.cuh"
+#include "gmb_math.cuh"
 
 namespace gmb {
 
-template <typename T>
-int subwarp_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t) {
-    return GMB_ERR_UNSUPPORTED;
+constexpr int kSubThreads = 128;
+constexpr int kRegBudgetWords = 100;      // register words for the local block
+
+constexpr int MODE_SOLVE = 0;   // A, Bm -> X, ok (, LU)
+constexpr int MODE_DECOMP = 1;  // A in place, perm, parity, degenerate
+constexpr int MODE_INV = 2;     // A -> Ainv, ok
+
+constexpr int sub_lc(int n, int xc, int g) { return (n + xc + g - 1) / g; }
+// does ANY lane of the group hold a rider column / a column beyond `i` at local index j?  (static)
+constexpr bool sub_any_rider(int n, int xc, int g, int j) {
+    const int lc = sub_lc(n, xc, g);
+    for (int l = 0; l < g; ++l)
+        if (l * lc + j >= n && l * lc + j < n + xc) return true;
+    return false;
 }
-template <typename T>
-int subwarp_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t) {
-    return GMB_ERR_UNSUPPORTED;
+constexpr int sub_group(int n, int xc, int words) {
+    for (int g = 1; g <= 16; g *= 2)
+        if (n * sub_lc(n, xc, g) * words <= kRegBudgetWords) return g;
+    return 16;
 }
-template <typename T>
-int subwarp_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t) {
-    return GMB_ERR_UNSUPPORTED;
+
+template <int G>
+__device__ __forceinline__ unsigned shfl_u(unsigned v, int src_in_group) {
+    if constexpr (G == 1) return v;
+    else return __shfl_sync(0xffffffffu, v, src_in_group, G);
 }
+template <int G>
+__device__ __forceinline__ float shfl_t(float v, int src_in_group) {
+    if constexpr (G == 1) return v;
+    else return __shfl_sync(0xffffffffu, v, src_in_group, G);
+}
+template <int G>
+__device__ __forceinline__ double shfl_t(double v, int src_in_group) {
+    if constexpr (G == 1) return v;
+    else return __shfl_sync(0xffffffffu, v, src_in_group, G);
+}
+
+template <typename T>
+struct BatchAddr {          // element e of system s: p[s_base + e * e_stride]
+    int64_t s_base;
+    int64_t e_stride;
+    __device__ __forceinline__ BatchAddr(int64_t s, int E, bool soa) {
+        constexpr int W = soa_w<T>();
+        if (soa) {
+            s_base = (s / W) * (int64_t)E * W + (s % W);
+            e_stride = W;
+        } else {
+            s_base = s * (int64_t)E;
+            e_stride = 1;
+        }
+    }
+    __device__ __forceinline__ int64_t operator()(int e) const { return s_base + e * e_stride; }
+};
+
+template <typename T, int N, int XC, int MODE>
+__global__ void __launch_bounds__(kSubThreads)
+k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ perm_out,
+          uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B, int soa, int a_rm, int x_rm) {
+    constexpr int WORDS = (int)sizeof(T) / 4;
+    constexpr int G = sub_group(N, XC, WORDS);
+    constexpr int NC = N + XC;
+    constexpr int LC = sub_lc(N, XC, G);
+    const int lane_g = (G == 1) ? 0 : (int)(threadIdx.x % G);
+    const int c0 = lane_g * LC;                               // first augmented column of this lane
+    int64_t s = ((int64_t)blockIdx.x * kSubThreads + threadIdx.x) / G;
+    const bool valid = s < B;
+    if (!valid) s = B - 1;                                    // keep every lane alive for the shuffles
+
+    const BatchAddr<T> atA(s, N * N, soa != 0);
+    const BatchAddr<T> atX(s, N * (XC > 0 ? XC : 1), soa != 0);
+
+    // ---- load the local block -------------------------------------------------------------
+    T a[N][LC];
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int j = 0; j < LC; ++j) {
+            const int c = c0 + j;
+            T v = (T)0;
+            if (c < N) {
+                v = A[atA(a_rm ? N * r + c : N * c + r)];
+            } else if (c < NC) {
+                if (MODE == MODE_SOLVE) v = Bm[atX(x_rm ? XC * r + (c - N) : N * (c - N) + r)];
+                if (MODE == MODE_INV) v = (r == c - N) ? (T)1 : (T)0;     // identity; rows exchanged below
+            }
+            a[r][j] = v;
+        }
+
+    uint8_t perm[N];
+    if (MODE == MODE_DECOMP) {
+#pragma unroll
+        for (int r = 0; r < N; ++r) perm[r] = (uint8_t)r;
+    }
+    int degenerate = 0;
+    bool parity = false;
+
+    // ---- elimination ----------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) {
+        const int owner = i / LC;          // static
+        const int k = i % LC;              // static local column of the pivot column in the owner lane
+        // pivot search on local column k (meaningful in the owner lane only)
+        T biggest = abs_(a[i][k]);
+        bool gt[N];
+#pragma unroll
+        for (int p = i + 1; p < N; ++p) {
+            const T v = abs_(a[p][k]);
+            gt[p] = v > biggest;
+            biggest = gt[p] ? v : biggest;
+        }
+        unsigned info = 0;
+        bool later = false;
+#pragma unroll
+        for (int p = N - 1; p > i; --p) {
+            info |= (gt[p] && !later) ? (1u << p) : 0u;
+            later = later || gt[p];
+        }
+        info |= (biggest == (T)0) ? 0x80000000u : 0u;
+        info = shfl_u<G>(info, owner);
+        const bool dead = (info & 0x80000000u) != 0;
+        degenerate += dead ? 1 : 0;
+        parity = parity != ((info & 0x7fffffffu) != 0);
+        // exchange rows i <-> pvt in the local columns
+#pragma unroll
+        for (int p = i + 1; p < N; ++p) {
+            const bool sw = ((info >> p) & 1u) != 0;
+#pragma unroll
+            for (int j = 0; j < LC; ++j) {
+                const T t = a[i][j];
+                a[i][j] = sw ? a[p][j] : t;
+                a[p][j] = sw ? t : a[p][j];
+            }
+            if (MODE == MODE_DECOMP) {
+                const uint8_t t = perm[i];
+                perm[i] = sw ? perm[p] : t;
+                perm[p] = sw ? t : perm[p];
+            }
+        }
+        // multipliers from the owner lane, then the rank-1 update of the local columns
+        const T piv = a[i][k];
+        const bool mine = (G == 1) || (lane_g == owner);
+#pragma unroll
+        for (int r = i + 1; r < N; ++r) {
+            T b = div_rn(a[r][k], piv);
+            b = shfl_t<G>(b, owner);
+            const bool upd = !dead && (b != (T)0);
+            if (mine) a[r][k] = dead ? a[r][k] : b;             // L(r,i)
+#pragma unroll
+            for (int j = 0; j < LC; ++j) {
+                if ((G - 1) * LC + j > i) {                       // static: some lane's column at j is right of i
+                    const int c = c0 + j;
+                    const bool is_rider = XC > 0 && c >= N;
+                    const bool go = (c > i) && (is_rider || upd);
+                    const T v = fma_rn(-b, a[i][j], a[r][j]);
+                    a[r][j] = go ? v : a[r][j];
+                }
+            }
+        }
+    }
+
+    const bool good = degenerate == 0;
+
+    // ---- outputs that need no backward sweep ------------------------------------------------
+    if (MODE == MODE_DECOMP || (MODE == MODE_SOLVE && LU != nullptr)) {
+        T* dst = (MODE == MODE_DECOMP) ? const_cast<T*>(A) : LU;
+        if (valid) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < LC; ++j) {
+                    const int c = c0 + j;
+                    if (c < N) dst[atA(a_rm ? N * r + c : N * c + r)] = a[r][j];
+                }
+        }
+    }
+    if (MODE == MODE_DECOMP) {
+        if (valid && lane_g == 0) {
+            if (perm_out) {
+#pragma unroll
+                for (int r = 0; r < N; ++r) perm_out[s * N + r] = perm[r];
+            }
+            if (parity_out) parity_out[s] = parity ? 1 : 0;
+            if (degen_out) degen_out[s] = (uint8_t)degenerate;
+        }
+        return;
+    }
+
+    // ---- backward sweep on the riders (column-oriented) -------------------------------------
+    if (XC > 0) {
+#pragma unroll
+        for (int c = N - 1; c >= 0; --c) {
+            const int owner = c / LC;
+            const int k = c % LC;
+            const bool solve_row = c >= skip;
+            // u(r, c) for r <= c lives in the owner lane's local column k
+            const T ucc = shfl_t<G>(a[c][k], owner);
+#pragma unroll
+            for (int j = 0; j < LC; ++j) {
+                if (sub_any_rider(N, XC, G, j)) {                 // static
+                    const bool is_rider = (c0 + j >= N);
+                    const T q = div_rn(a[c][j], ucc);
+                    a[c][j] = (is_rider && solve_row) ? q : a[c][j];
+                }
+            }
+#pragma unroll
+            for (int r = c - 1; r >= 0; --r) {
+                const T urc = shfl_t<G>(a[r][k], owner);
+                const bool row_on = r >= skip;
+#pragma unroll
+                for (int j = 0; j < LC; ++j) {
+                    if (sub_any_rider(N, XC, G, j)) {             // static
+                        const bool is_rider = (c0 + j >= N);
+                        const T v = fma_rn(-a[c][j], urc, a[r][j]);
+                        a[r][j] = (is_rider && row_on) ? v : a[r][j];
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- store riders -----------------------------------------------------------------------
+    if (valid) {
+        if (MODE == MODE_SOLVE) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < LC; ++j) {
+                    const int c = c0 + j;
+                    if (c >= N && c < NC) {
+                        const int64_t off = atX(x_rm ? XC * r + (c - N) : N * (c - N) + r);
+                        X[off] = good ? a[r][j] : Bm[off];              // x untouched on failure (:391-393)
+                    }
+                }
+        }
+        if (MODE == MODE_INV && good) {                                  // out untouched on failure
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < LC; ++j) {
+                    const int c = c0 + j;
+                    if (c >= N && c < NC) X[atA(N * r + (c - N))] = a[r][j];   // invNxN writes `out` row-major (:192)
+                }
+        }
+        if (lane_g == 0 && ok_out) ok_out[s] = good ? 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+template <typename T, int N, int XC, int MODE>
+static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t* perm, uint8_t* parity, uint8_t* degen,
+                      int skip, int64_t B, int layout, int a_rm, int x_rm, cudaStream_t st) {
+    constexpr int G = sub_group(N, XC, (int)sizeof(T) / 4);
+    const int64_t threads = B * G;
+    const unsigned grid = (unsigned)ceil_div(threads, kSubThreads);
+    if (grid == 0) return GMB_OK;
+    k_sub_plu<T, N, XC, MODE><<<grid, kSubThreads, 0, st>>>(A, Bm, X, LU, ok, perm, parity, degen, skip, B,
+                                                           layout == GMB_LAYOUT_SOA ? 1 : 0, a_rm, x_rm);
+    return after_launch();
+}
+
+template <typename T>
+int subwarp_plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout,
+                      int rm, cudaStream_t st) {
+    if (m != 1) return GMB_ERR_UNSUPPORTED;
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        rc = launch_sub<T, N.value, 1, MODE_SOLVE>(A, Bm, X, LU, ok, nullptr, nullptr, nullptr, skip, B, layout, rm, rm, st);
+    });
+    return rc;
+}
+
+template <typename T>
+int subwarp_decomp(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
+                   cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        rc = launch_sub<T, N.value, 0, MODE_DECOMP>(A, nullptr, nullptr, nullptr, nullptr, perm, parity, degen, 0, B, layout,
+                                                    rm, rm, st);
+    });
+    return rc;
+}
+
+// inv for n >= 5 (MatrixInv.h:243-249 + 219-231): the working copy has the DESTINATION's layout and
+// is then treated as row-major, i.e. the kernel reads A with a_rm = (src layout == dst layout)
+// and writes the result flat row-major into the destination buffer.
+template <typename T>
+int subwarp_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    const int a_rm = ((src_rm != 0) == (dst_rm != 0)) ? 1 : 0;
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        rc = launch_sub<T, N.value, N.value, MODE_INV>(A, nullptr, Ainv, nullptr, ok, nullptr, nullptr, nullptr, 0, B,
+                                                       layout, a_rm, 1, st);
+    });
+    return rc;
+}
+
 template <typename T>
 int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t) {
-    return GMB_ERR_UNSUPPORTED;
+    return GMB_ERR_UNSUPPORTED;      // n >= 5 Cholesky runs on the generic kernel (gmb_generic.cu)
 }
 
 #define INSTANTIATE(T)                                                                                              \
