@@ -48,7 +48,9 @@ _TYPED = {
 
 # every symbol include/geomc_b200.h declares (tests/test_abi.py checks the header against this)
 UNTYPED = ["gmb_version", "gmb_error_string", "gmb_device_count", "gmb_soa_tile_width", "gmb_soa_elems",
-           "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count"]
+           "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count", "gmb_set_device",
+           "gmb_device_alloc", "gmb_device_free", "gmb_memcpy_h2d", "gmb_memcpy_d2h", "gmb_memset_device",
+           "gmb_stream_synchronize"]
 EXPORTS = UNTYPED + [f"{k}_{s}" for k in _TYPED for s in ("f32", "f64")]
 
 

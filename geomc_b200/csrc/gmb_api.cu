@@ -336,6 +336,29 @@ void gmb_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int gmb_set_device(int device) { return (int)cudaSetDevice(device); }
+void* gmb_device_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void gmb_device_free(void* p) {
+    if (p) cudaFree(p);
+}
+int gmb_memcpy_h2d(void* dst, const void* src, size_t bytes, void* stream) {
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, as_stream(stream));
+}
+int gmb_memcpy_d2h(void* dst, const void* src, size_t bytes, void* stream) {
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream));
+}
+int gmb_memset_device(void* dst, int value, size_t bytes, void* stream) {
+    return (int)cudaMemsetAsync(dst, value, bytes, as_stream(stream));
+}
+int gmb_stream_synchronize(void* stream) { return (int)cudaStreamSynchronize(as_stream(stream)); }
+
 #define GMB_DEFINE(SUF, T)                                                                                            \
     int gmb_aos_to_soa_##SUF(int E, int64_t B, const T* aos, T* soa, void* stream) {                                  \
         if (B < 0 || E < 1 || (B > 0 && (!aos || !soa))) return GMB_ERR_INVALID_ARG;                                  \

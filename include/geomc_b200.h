@@ -186,6 +186,16 @@ int gmb_host_plu_decomp_f32(int rows, int cols, int64_t B, float* A_inout, uint8
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t gmb_launch_count(void);
 
+/* ---- device memory and streams for hosts that do not link the CUDA runtime themselves --------
+ * (include/geomc_b200/batch.hpp builds with a plain C++ compiler on top of these). */
+int gmb_set_device(int device);
+void* gmb_device_alloc(size_t bytes);                 /* NULL on failure */
+void gmb_device_free(void* p);
+int gmb_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream);
+int gmb_memcpy_d2h(void* dst_host, const void* src_device, size_t bytes, void* stream);
+int gmb_memset_device(void* dst_device, int value, size_t bytes, void* stream);
+int gmb_stream_synchronize(void* stream);             /* NULL = the default stream */
+
 #ifdef __cplusplus
 }
 #endif

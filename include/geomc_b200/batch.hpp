@@ -1,0 +1,340 @@
+// geomc_b200/batch.hpp -- C++ host side of the drop-in: the reference's geomc/linalg factor /
+// solve / inverse functions, one call per BATCH, same names, argument meaning and error behaviour
+// (bool / degenerate-count results per system, inputs destroyed where the reference destroys
+// them, outputs untouched where the reference leaves them untouched).
+//
+// Builds with a plain C++17 compiler; links libgeomc_b200.so (the C ABI of ../geomc_b200.h).
+// There is no CPU fallback: every call ends in a CUDA kernel launch or returns an error.
+//
+//   namespace geom::batch
+//     BatchSoA<T>                      the SoA-interleaved batch container (replaces T[B][E] of objects)
+//     decomp_plu / decomp_lup          LUDecomp.h:188 / :102
+//     backsolve_lu / backsolve_plu     LUDecomp.h:332 / :271
+//     linear_solve (pointer form)      LUDecomp.h:388
+//     linear_solve (Vec form)          LUDecomp.h:417
+//     cholesky                         Cholesky.h:37 / :83
+//     cholesky_solve                   (new; the reference has no Cholesky solve)
+//     inv                              Matrix.h:717 -> MatrixInv.h:49-337
+//
+// Three forms of every function:
+//   (1) device form  -- DeviceBatch / BatchSoA arguments already resident in HBM, asynchronous;
+//   (2) host form    -- raw host arrays `T a[B][n*n]` exactly as a loop over the reference's
+//                       pointer functions would see them; copies in, solves, copies out;
+//   (3) object form  -- arrays of the reference's own objects (geom::SimpleMatrix<T,N,N,Lyt>,
+//                       geom::Vec<T,N>), duck-typed so this header does not include geomc.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../geomc_b200.h"
+
+namespace geom {
+namespace batch {
+
+using index_t = std::ptrdiff_t;          // geomc_defs.h:85
+
+enum class Layout : int { AoS = GMB_LAYOUT_AOS, SoA = GMB_LAYOUT_SOA };
+
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const char* what) : std::runtime_error(std::string(what) + ": " + gmb_error_string(c)), code(c) {}
+};
+inline void check(int rc, const char* what) {
+    if (rc != GMB_OK) throw Error(rc, what);
+}
+
+// ---------------------------------------------------------------- type -> C ABI entry points
+template <typename T> struct Abi;
+#define GMB_ABI(T, S)                                                                                       \
+    template <> struct Abi<T> {                                                                             \
+        static constexpr auto aos_to_soa = gmb_aos_to_soa_##S;                                              \
+        static constexpr auto soa_to_aos = gmb_soa_to_aos_##S;                                              \
+        static constexpr auto plu_decomp = gmb_plu_decomp_##S;                                              \
+        static constexpr auto lup_decomp = gmb_lup_decomp_##S;                                              \
+        static constexpr auto lu_backsolve = gmb_lu_backsolve_##S;                                          \
+        static constexpr auto plu_backsolve = gmb_plu_backsolve_##S;                                        \
+        static constexpr auto apply_permutation = gmb_apply_permutation_##S;                                \
+        static constexpr auto plu_solve = gmb_plu_solve_##S;                                                \
+        static constexpr auto linear_solve_vec = gmb_linear_solve_vec_##S;                                  \
+        static constexpr auto cholesky = gmb_cholesky_##S;                                                  \
+        static constexpr auto cholesky_solve = gmb_cholesky_solve_##S;                                      \
+        static constexpr auto inv = gmb_inv_##S;                                                            \
+        static constexpr auto host_plu_solve = gmb_host_plu_solve_##S;                                      \
+        static constexpr auto host_inv = gmb_host_inv_##S;                                                  \
+        static constexpr auto host_cholesky_solve = gmb_host_cholesky_solve_##S;                            \
+        static constexpr auto host_plu_decomp = gmb_host_plu_decomp_##S;                                    \
+    };
+GMB_ABI(float, f32)
+GMB_ABI(double, f64)
+#undef GMB_ABI
+
+// ---------------------------------------------------------------- device memory (RAII over the C ABI)
+template <typename T>
+class DeviceArray {
+public:
+    DeviceArray() = default;
+    explicit DeviceArray(std::size_t n) : n_(n) {
+        p_ = static_cast<T*>(gmb_device_alloc(n * sizeof(T)));
+        if (!p_) throw Error(GMB_ERR_ALLOC, "gmb_device_alloc");
+    }
+    DeviceArray(DeviceArray&& o) noexcept : p_(o.p_), n_(o.n_) { o.p_ = nullptr; o.n_ = 0; }
+    DeviceArray& operator=(DeviceArray&& o) noexcept {
+        if (this != &o) { gmb_device_free(p_); p_ = o.p_; n_ = o.n_; o.p_ = nullptr; o.n_ = 0; }
+        return *this;
+    }
+    DeviceArray(const DeviceArray&) = delete;
+    DeviceArray& operator=(const DeviceArray&) = delete;
+    ~DeviceArray() { gmb_device_free(p_); }
+    T* get() const { return p_; }
+    std::size_t size() const { return n_; }
+    void upload(const T* host, std::size_t n, void* stream = nullptr) { check(gmb_memcpy_h2d(p_, host, n * sizeof(T), stream), "h2d"); }
+    void download(T* host, std::size_t n, void* stream = nullptr) const { check(gmb_memcpy_d2h(host, p_, n * sizeof(T), stream), "d2h"); }
+private:
+    T* p_ = nullptr;
+    std::size_t n_ = 0;
+};
+
+// A batch of B records of E elements resident in HBM, in either layout.
+template <typename T>
+class DeviceBatch {
+public:
+    DeviceBatch(index_t B, int E, Layout layout)
+        : B_(B), E_(E), layout_(layout),
+          data_(layout == Layout::SoA ? (std::size_t)gmb_soa_elems(B, E, (int)sizeof(T)) : (std::size_t)(B * E)) {}
+    index_t size() const { return B_; }
+    int elems() const { return E_; }
+    Layout layout() const { return layout_; }
+    T* data() const { return data_.get(); }
+    // AoS host array <-> this batch (coalesced AoS->SoA ingest kernel when the layout is SoA)
+    void upload_aos(const T* host, void* stream = nullptr) {
+        if (layout_ == Layout::AoS) { data_.upload(host, (std::size_t)(B_ * E_), stream); return; }
+        DeviceArray<T> tmp((std::size_t)(B_ * E_));
+        tmp.upload(host, (std::size_t)(B_ * E_), stream);
+        check(Abi<T>::aos_to_soa(E_, B_, tmp.get(), data_.get(), stream), "aos_to_soa");
+        check(gmb_stream_synchronize(stream), "sync");
+    }
+    void download_aos(T* host, void* stream = nullptr) const {
+        if (layout_ == Layout::AoS) { data_.download(host, (std::size_t)(B_ * E_), stream); check(gmb_stream_synchronize(stream), "sync"); return; }
+        DeviceArray<T> tmp((std::size_t)(B_ * E_));
+        check(Abi<T>::soa_to_aos(E_, B_, data_.get(), tmp.get(), stream), "soa_to_aos");
+        tmp.download(host, (std::size_t)(B_ * E_), stream);
+        check(gmb_stream_synchronize(stream), "sync");
+    }
+private:
+    index_t B_;
+    int E_;
+    Layout layout_;
+    DeviceArray<T> data_;
+};
+
+// The SoA-interleaved batch container: tiles of W = 512/sizeof(T) systems, element e of system s at
+// data[((s / W) * E + e) * W + s % W].
+template <typename T>
+class BatchSoA : public DeviceBatch<T> {
+public:
+    static constexpr int W = 512 / (int)sizeof(T);
+    BatchSoA(index_t B, int E) : DeviceBatch<T>(B, E, Layout::SoA) {}
+    static std::size_t index(index_t s, int e, int E) { return (std::size_t)(((s / W) * E + e) * W + s % W); }
+};
+
+// ================================================================= (1) device forms (asynchronous)
+// Results per system: ok / parity / degenerate are uint8[B] device arrays, reorder is uint8[B][rows].
+
+// decomp_plu<T,RowMajor>(m, rows, cols, reorder, parity) -> degenerate_ct      LUDecomp.h:188
+template <typename T, bool RowMajor = true>
+void decomp_plu(DeviceBatch<T>& m, index_t rows, index_t cols, std::uint8_t* reorder, std::uint8_t* parity,
+                std::uint8_t* degenerate_ct, void* stream = nullptr) {
+    check(Abi<T>::plu_decomp((int)rows, (int)cols, m.size(), m.data(), reorder, parity, degenerate_ct, (int)m.layout(),
+                             RowMajor ? 1 : 0, stream), "decomp_plu");
+}
+// decomp_lup                                                                     LUDecomp.h:102
+template <typename T, bool RowMajor = true>
+void decomp_lup(DeviceBatch<T>& m, index_t rows, index_t cols, std::uint8_t* reorder, std::uint8_t* parity,
+                std::uint8_t* degenerate_ct, void* stream = nullptr) {
+    check(Abi<T>::lup_decomp((int)rows, (int)cols, m.size(), m.data(), reorder, parity, degenerate_ct, (int)m.layout(),
+                             RowMajor ? 1 : 0, stream), "decomp_lup");
+}
+// backsolve_lu<T,RowMajor>(lu, n, m, x, skip)                                    LUDecomp.h:332
+template <typename T, bool RowMajor = true>
+void backsolve_lu(const DeviceBatch<T>& lu, index_t n, index_t m, DeviceBatch<T>& x, index_t skip = 0, void* stream = nullptr) {
+    check(Abi<T>::lu_backsolve((int)n, (int)m, lu.size(), lu.data(), x.data(), (int)skip, (int)lu.layout(), RowMajor ? 1 : 0,
+                               stream), "backsolve_lu");
+}
+// backsolve_plu<T,RowMajor>(plu, p, n, m, x, b, skip)                            LUDecomp.h:271
+template <typename T, bool RowMajor = true>
+void backsolve_plu(const DeviceBatch<T>& plu, const std::uint8_t* p, index_t n, index_t m, DeviceBatch<T>& x,
+                   const DeviceBatch<T>& b, index_t skip = 0, void* stream = nullptr) {
+    check(Abi<T>::plu_backsolve((int)n, (int)m, plu.size(), plu.data(), p, x.data(), b.data(), (int)skip, (int)plu.layout(),
+                                RowMajor ? 1 : 0, stream), "backsolve_plu");
+}
+// linear_solve<T,RowMajor>(a, n, m, x, skip) -> bool                              LUDecomp.h:388
+// x holds b on entry and the solution on exit (untouched where ok == 0).  `a` is NOT destroyed
+// unless lu_out aliases it.
+template <typename T, bool RowMajor = true>
+void linear_solve(const DeviceBatch<T>& a, index_t n, index_t m, DeviceBatch<T>& x, std::uint8_t* ok, index_t skip = 0,
+                  void* stream = nullptr, DeviceBatch<T>* lu_out = nullptr) {
+    check(Abi<T>::plu_solve((int)n, (int)m, a.size(), a.data(), x.data(), x.data(), ok, lu_out ? lu_out->data() : nullptr,
+                            (int)skip, (int)a.layout(), RowMajor ? 1 : 0, stream), "linear_solve");
+}
+// cholesky<T,RowMajor>(m, n) -> bool                                              Cholesky.h:37
+template <typename T, bool RowMajor = true>
+void cholesky(DeviceBatch<T>& m, index_t n, std::uint8_t* ok, void* stream = nullptr) {
+    check(Abi<T>::cholesky((int)n, m.size(), m.data(), ok, (int)m.layout(), RowMajor ? 1 : 0, stream), "cholesky");
+}
+// fused Cholesky factor + solve (new)
+template <typename T, bool RowMajor = true>
+void cholesky_solve(const DeviceBatch<T>& a, index_t n, index_t m, DeviceBatch<T>& x, std::uint8_t* ok, void* stream = nullptr) {
+    check(Abi<T>::cholesky_solve((int)n, (int)m, a.size(), a.data(), x.data(), x.data(), ok, nullptr, (int)a.layout(),
+                                 RowMajor ? 1 : 0, stream), "cholesky_solve");
+}
+// inv(into, src) -> bool                                                          Matrix.h:717
+template <typename T>
+void inv(DeviceBatch<T>& into, const DeviceBatch<T>& src, index_t n, std::uint8_t* ok, bool src_row_major = true,
+         bool dst_row_major = true, void* stream = nullptr) {
+    check(Abi<T>::inv((int)n, src.size(), src.data(), into.data(), ok, (int)src.layout(), src_row_major ? 1 : 0,
+                      dst_row_major ? 1 : 0, stream), "inv");
+}
+
+// ================================================================= (2) host forms (synchronous)
+// Raw host arrays exactly as a loop over the reference's pointer functions sees them.
+// `ok` receives the reference's bool per system (nullptr allowed).  Returns the number of systems
+// for which the reference would have returned false.
+namespace detail {
+inline index_t count_false(const std::uint8_t* ok, index_t B) {
+    index_t n = 0;
+    for (index_t i = 0; i < B; ++i) n += ok[i] ? 0 : 1;
+    return n;
+}
+}  // namespace detail
+
+// for (s < B) ok[s] = geom::linear_solve<T,RowMajor>(a + s*n*n, n, m, x + s*n*m, skip);
+// Difference from the reference: `a` is left intact (the reference leaves the LU factors in it).
+template <typename T, bool RowMajor = true>
+index_t linear_solve(const T* a, index_t n, index_t m, T* x, index_t B, bool* ok = nullptr, index_t skip = 0, int device = 0) {
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    check(Abi<T>::host_plu_solve((int)n, (int)m, B, a, x, x, okb.data(), (int)skip, RowMajor ? 1 : 0, device), "linear_solve");
+    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
+    return detail::count_false(okb.data(), B);
+}
+
+// for (s < B) degenerate[s] = geom::decomp_plu<T,RowMajor>(m + s*rows*cols, rows, cols, reorder + s*rows, parity + s);
+template <typename T, bool RowMajor = true>
+void decomp_plu(T* m, index_t rows, index_t cols, index_t B, index_t* reorder, bool* parity, index_t* degenerate_ct, int device = 0) {
+    std::vector<std::uint8_t> p((std::size_t)(B * rows)), par((std::size_t)B), deg((std::size_t)B);
+    check(Abi<T>::host_plu_decomp((int)rows, (int)cols, B, m, p.data(), par.data(), deg.data(), RowMajor ? 1 : 0, device),
+          "decomp_plu");
+    if (reorder) for (index_t i = 0; i < B * rows; ++i) reorder[i] = (index_t)p[(std::size_t)i];
+    if (parity) for (index_t i = 0; i < B; ++i) parity[i] = par[(std::size_t)i] != 0;
+    if (degenerate_ct) for (index_t i = 0; i < B; ++i) degenerate_ct[i] = (index_t)deg[(std::size_t)i];
+}
+
+// for (s < B) ok[s] = geom::cholesky<T,RowMajor>(...) followed by the L L^T solve of x (new).
+template <typename T, bool RowMajor = true>
+index_t cholesky_solve(const T* a, index_t n, index_t m, T* x, index_t B, bool* ok = nullptr, int device = 0) {
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    check(Abi<T>::host_cholesky_solve((int)n, (int)m, B, a, x, x, okb.data(), RowMajor ? 1 : 0, device), "cholesky_solve");
+    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
+    return detail::count_false(okb.data(), B);
+}
+
+// for (s < B) ok[s] = inv2x2/3x3/4x4/invNxN on flat arrays; `out` untouched where ok == false.
+template <typename T>
+index_t inv(T* out, const T* src, index_t n, index_t B, bool* ok = nullptr, bool src_row_major = true,
+            bool dst_row_major = true, int device = 0) {
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    check(Abi<T>::host_inv((int)n, B, src, out, okb.data(), src_row_major ? 1 : 0, dst_row_major ? 1 : 0, device), "inv");
+    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
+    return detail::count_false(okb.data(), B);
+}
+
+// ================================================================= (3) object forms
+// Arrays of the reference's own objects, duck-typed: Mx needs `elem_t`, static `ROWDIM`, `COLDIM`,
+// `Layout` (0 = ROW_MAJOR, 1 = COL_MAJOR: LinalgTypes.h:36-39) and `data_begin()`; Vec needs
+// `begin()`.  Objects whose size is not N*N*sizeof(T) (SimpleMatrix<float,3,3> is 40 bytes) are
+// packed into a temporary.
+namespace detail {
+template <typename Mx> using elem_of = typename Mx::elem_t;
+template <typename Mx>
+std::vector<elem_of<Mx>> pack(const Mx* m, index_t B, int E) {
+    std::vector<elem_of<Mx>> v((std::size_t)(B * E));
+    for (index_t s = 0; s < B; ++s) std::memcpy(v.data() + s * E, m[s].data_begin(), sizeof(elem_of<Mx>) * (std::size_t)E);
+    return v;
+}
+template <typename Mx>
+void unpack(Mx* m, const std::vector<elem_of<Mx>>& v, index_t B, int E, const std::uint8_t* only_where) {
+    for (index_t s = 0; s < B; ++s)
+        if (!only_where || only_where[s]) std::memcpy(m[s].data_begin(), v.data() + s * E, sizeof(elem_of<Mx>) * (std::size_t)E);
+}
+}  // namespace detail
+
+// for (s < B) ok[s] = geom::inv(&into[s], src[s]);          Matrix.h:717 (static N = 2..16)
+template <typename Md, typename Mx>
+index_t inv(Md* into, const Mx* src, index_t B, bool* ok = nullptr, int device = 0) {
+    using T = detail::elem_of<Mx>;
+    constexpr int N = (int)(Mx::ROWDIM > Mx::COLDIM ? Mx::ROWDIM : Mx::COLDIM);
+    static_assert(N >= 2 && N <= GMB_MAX_N, "static dimension 2..16 required");
+    static_assert(std::is_same<T, detail::elem_of<Md>>::value, "element types must agree");
+    auto a = detail::pack(src, B, N * N);
+    auto o = detail::pack(into, B, N * N);                  // current contents: "untouched on failure"
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    check(Abi<T>::host_inv(N, B, a.data(), o.data(), okb.data(), (int)Mx::Layout == 0 ? 1 : 0, (int)Md::Layout == 0 ? 1 : 0, device), "inv");
+    detail::unpack(into, o, B, N * N, okb.data());
+    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
+    return detail::count_false(okb.data(), B);
+}
+
+// for (s < B) ok[s] = geom::cholesky(&m[s]);                Cholesky.h:83 (row-major arithmetic on begin())
+template <typename Mx>
+index_t cholesky(Mx* m, index_t B, bool* ok = nullptr, int device = 0) {
+    using T = detail::elem_of<Mx>;
+    constexpr int N = (int)Mx::ROWDIM;
+    static_assert(Mx::ROWDIM == Mx::COLDIM && N >= 2 && N <= GMB_MAX_N, "square static dimension 2..16 required");
+    // Cholesky.h:87 runs cholesky<T,true> on m->begin(), the ROW-MAJOR iterator: logical (r,c) order
+    // whatever the storage layout; a symmetric input makes the two coincide for reading, and the
+    // factor is written to logical (r,c).
+    const bool rm = (int)Mx::Layout == 0;
+    auto a = detail::pack(m, B, N * N);
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    DeviceBatch<T> d(B, N * N, Layout::AoS);
+    DeviceArray<std::uint8_t> dok((std::size_t)B);
+    check(gmb_set_device(device), "set_device");
+    d.upload_aos(a.data());
+    check(Abi<T>::cholesky(N, B, d.data(), dok.get(), GMB_LAYOUT_AOS, rm ? 1 : 0, nullptr), "cholesky");
+    d.download_aos(a.data());
+    dok.download(okb.data(), (std::size_t)B);
+    check(gmb_stream_synchronize(nullptr), "sync");
+    detail::unpack(m, a, B, N * N, nullptr);
+    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
+    return detail::count_false(okb.data(), B);
+}
+
+// for (s < B) ok[s] = geom::linear_solve<T,N>(bases[s], 1, &x[s], skip);      LUDecomp.h:417
+// bases: B arrays of N column vectors (Vec<T,N>[N], contiguous N*N); x: B vectors (b in, x out).
+// N < 5 is inverse-then-multiply exactly like the reference; `bases` is left intact.
+template <typename V>
+index_t linear_solve_vec(const V* bases, V* x, index_t N, index_t B, bool* ok = nullptr, index_t skip = 0, int device = 0) {
+    using T = typename std::remove_cv<typename std::remove_reference<decltype(*std::declval<V&>().begin())>::type>::type;
+    static_assert(sizeof(V) % sizeof(T) == 0, "packed vectors expected (VecBase.h:112)");
+    check(gmb_set_device(device), "set_device");
+    DeviceBatch<T> dA(B, (int)(N * N), Layout::AoS), dX(B, (int)N, Layout::AoS);
+    DeviceArray<std::uint8_t> dok((std::size_t)B);
+    dA.upload_aos(reinterpret_cast<const T*>(bases));
+    dX.upload_aos(reinterpret_cast<const T*>(x));
+    check(Abi<T>::linear_solve_vec((int)N, 1, B, dA.data(), dX.data(), dX.data(), dok.get(), (int)skip, GMB_LAYOUT_AOS, nullptr),
+          "linear_solve(Vec)");
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    dX.download_aos(reinterpret_cast<T*>(x));
+    dok.download(okb.data(), (std::size_t)B);
+    check(gmb_stream_synchronize(nullptr), "sync");
+    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
+    return detail::count_false(okb.data(), B);
+}
+
+}  // namespace batch
+}  // namespace geom

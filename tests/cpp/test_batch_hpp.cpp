@@ -1,0 +1,205 @@
+// Exercises include/geomc_b200/batch.hpp the way a geomc user would after switching:
+// the reference's call shapes (linear_solve(T*,n,m,T*), inv(&into, src), cholesky(&m),
+// linear_solve(Vec[N],...), decomp_plu(...)), one call per batch.
+//
+//   g++ -std=c++17 -O2 -I include tests/cpp/test_batch_hpp.cpp -L geomc_b200 -lgeomc_b200 -Wl,-rpath,$PWD/geomc_b200
+//   add -DWITH_GEOMC -std=c++23 -include oracle/shim/prelude.h -I oracle/shim -I /root/reference
+//   to run the object forms on the reference's real SimpleMatrix / Vec types.
+// `--compile-only` semantics: the not-gpu suite only compiles this file; the gpu suite runs it.
+#ifdef WITH_GEOMC
+#include <geomc/linalg/Matrix.h>
+#include <geomc/linalg/Vec.h>
+#endif
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include <geomc_b200/batch.hpp>
+
+namespace gb = geom::batch;
+
+#ifndef WITH_GEOMC
+// Minimal stand-ins with the members batch.hpp's object forms rely on (same names as the reference).
+namespace geom {
+enum MatrixLayout { ROW_MAJOR, COL_MAJOR };
+template <typename T, long M, long N, MatrixLayout L = ROW_MAJOR>
+struct SimpleMatrix {
+    typedef T elem_t;
+    static constexpr long ROWDIM = M, COLDIM = N;
+    static constexpr MatrixLayout Layout = L;
+    T data[M * N];
+    SimpleMatrix() { for (long i = 0; i < M * N; ++i) data[i] = (i / N == i % N) ? 1 : 0; }
+    T* data_begin() { return data; }
+    const T* data_begin() const { return data; }
+    T& operator()(long r, long c) { return data[L == ROW_MAJOR ? N * r + c : M * c + r]; }
+    T operator()(long r, long c) const { return data[L == ROW_MAJOR ? N * r + c : M * c + r]; }
+};
+template <typename T, long N>
+struct Vec {
+    T v[N];
+    T* begin() { return v; }
+    const T* begin() const { return v; }
+    T& operator[](long i) { return v[i]; }
+    T operator[](long i) const { return v[i]; }
+};
+}  // namespace geom
+#endif
+
+static int failures = 0;
+#define EXPECT(cond, ...) do { if (!(cond)) { ++failures; std::printf("FAIL %s:%d: ", __FILE__, __LINE__); std::printf(__VA_ARGS__); std::printf("\n"); } } while (0)
+
+template <typename T>
+static void test_pointer_linear_solve(long n, long B) {
+    std::mt19937_64 rng(17 + n);
+    std::normal_distribution<double> g(0, 1);
+    std::vector<T> a(B * n * n), b(B * n), x;
+    for (auto& v : a) v = (T)g(rng);
+    for (auto& v : b) v = (T)g(rng);
+    for (long c = 0; c < n; ++c) a[7 * n * n + c * n] = 0;       // system 7: zero first column -> false
+    x = b;
+    std::vector<char> okc(B);
+    bool* ok = reinterpret_cast<bool*>(okc.data());
+    long nfalse = gb::linear_solve<T, true>(a.data(), n, 1, x.data(), B, ok);
+    EXPECT(nfalse == 1 && !ok[7], "expected exactly system 7 to be degenerate (got %ld)", nfalse);
+    for (long r = 0; r < n; ++r) EXPECT(x[7 * n + r] == b[7 * n + r], "x must be untouched on failure");
+    double worst = 0;
+    for (long s = 0; s < B; ++s) {
+        if (!ok[s]) continue;
+        double xm = 1;
+        for (long r = 0; r < n; ++r) xm = std::fmax(xm, std::fabs((double)x[s * n + r]));
+        for (long r = 0; r < n; ++r) {
+            double acc = -(double)b[s * n + r];
+            for (long c = 0; c < n; ++c) acc += (double)a[s * n * n + r * n + c] * (double)x[s * n + c];
+            worst = std::fmax(worst, std::fabs(acc) / xm);
+        }
+    }
+    EXPECT(worst < (sizeof(T) == 4 ? 2e-2 : 1e-8), "residual %g too large (n=%ld)", worst, n);
+}
+
+template <typename T, long N, geom::MatrixLayout LS, geom::MatrixLayout LD>
+static void test_object_inv(long B) {
+    std::mt19937_64 rng(5 + N);
+    std::normal_distribution<double> g(0, 1);
+    std::vector<geom::SimpleMatrix<T, N, N, LS>> src(B);
+    std::vector<geom::SimpleMatrix<T, N, N, LD>> dst(B);
+    for (auto& m : src) for (long r = 0; r < N; ++r) for (long c = 0; c < N; ++c) m(r, c) = (T)g(rng);
+    for (long r = 0; r < N; ++r) for (long c = 0; c < N; ++c) src[3](r, c) = 0;      // singular
+    std::vector<char> okc(B);
+    bool* ok = reinterpret_cast<bool*>(okc.data());
+    long nfalse = gb::inv(dst.data(), src.data(), B, ok);
+    EXPECT(nfalse == 1 && !ok[3], "expected exactly system 3 to be singular");
+    for (long r = 0; r < N; ++r) for (long c = 0; c < N; ++c)
+        EXPECT(dst[3](r, c) == (r == c ? 1 : 0), "destination must keep its (identity) contents on failure");
+    double worst = 0;
+    for (long s = 0; s < B; ++s) {
+        if (!ok[s]) continue;
+        for (long r = 0; r < N; ++r) for (long c = 0; c < N; ++c) {
+            double acc = 0;
+            for (long k = 0; k < N; ++k) acc += (double)src[s](r, k) * (double)dst[s](k, c);
+            worst = std::fmax(worst, std::fabs(acc - (r == c ? 1.0 : 0.0)));
+        }
+    }
+    EXPECT(worst < (sizeof(T) == 4 ? 0.5 : 1e-6), "M * M^-1 deviates from I by %g (N=%ld)", worst, N);
+}
+
+template <typename T, long N>
+static void test_vec_linear_solve(long B) {
+    std::mt19937_64 rng(9 + N);
+    std::normal_distribution<double> g(0, 1);
+    std::vector<geom::Vec<T, N>> bases(B * N), x(B), b;
+    for (auto& v : bases) for (long i = 0; i < N; ++i) v[i] = (T)g(rng);
+    for (auto& v : x) for (long i = 0; i < N; ++i) v[i] = (T)g(rng);
+    b = x;
+    long nfalse = gb::linear_solve_vec(bases.data(), x.data(), N, B);
+    EXPECT(nfalse == 0, "random bases should be regular");
+    double worst = 0;
+    for (long s = 0; s < B; ++s)
+        for (long r = 0; r < N; ++r) {                  // sum_i x[i] * basis_i == b   (linear_solve.cpp:46-52)
+            double acc = -(double)b[s][r];
+            for (long i = 0; i < N; ++i) acc += (double)x[s][i] * (double)bases[s * N + i][r];
+            worst = std::fmax(worst, std::fabs(acc));
+        }
+    EXPECT(worst < 1e-5, "Vec-form residual %g (N=%ld)", worst, N);
+}
+
+static void test_decomp_and_cholesky(long B) {
+    const long n = 6;
+    std::mt19937_64 rng(3);
+    std::normal_distribution<double> g(0, 1);
+    std::vector<double> m(B * n * n), lu;
+    for (auto& v : m) v = g(rng);
+    lu = m;
+    std::vector<gb::index_t> p(B * n), deg(B);
+    std::vector<char> par(B);
+    gb::decomp_plu<double, true>(lu.data(), n, n, B, p.data(), reinterpret_cast<bool*>(par.data()), deg.data());
+    double worst = 0;
+    for (long s = 0; s < B; ++s)
+        for (long r = 0; r < n; ++r) for (long c = 0; c < n; ++c) {       // L U == P M   (linear_solve.cpp:86-99)
+            double acc = 0;
+            for (long k = 0; k <= std::min(r, c); ++k) acc += (k == r ? 1.0 : lu[s * 36 + r * n + k]) * lu[s * 36 + k * n + c];
+            worst = std::fmax(worst, std::fabs(acc - m[s * 36 + p[s * n + r] * n + c]));
+        }
+    EXPECT(worst < 1e-5, "L U != P M (%g)", worst);
+    // SPD 3x3 double: cholesky object form + fused cholesky_solve host form
+    std::vector<geom::SimpleMatrix<double, 3, 3>> S(B);
+    std::vector<double> flat(B * 9), rhs(B * 3), x;
+    for (long s = 0; s < B; ++s) {
+        double R[9];
+        for (auto& v : R) v = g(rng);
+        for (long r = 0; r < 3; ++r) for (long c = 0; c < 3; ++c) {
+            double acc = r == c ? 1 : 0;
+            for (long k = 0; k < 3; ++k) acc += R[r * 3 + k] * R[c * 3 + k];
+            S[s](r, c) = acc;
+            flat[s * 9 + r * 3 + c] = acc;
+        }
+        for (long r = 0; r < 3; ++r) rhs[s * 3 + r] = g(rng);
+    }
+    x = rhs;
+    const long not_spd = gb::cholesky_solve<double, true>(flat.data(), 3, 1, x.data(), B);
+    EXPECT(not_spd == 0, "SPD systems must factor");
+    EXPECT(gb::cholesky(S.data(), B) == 0, "SPD matrices must factor");
+    worst = 0;
+    for (long s = 0; s < B; ++s)
+        for (long r = 0; r < 3; ++r) {
+            double acc = -rhs[s * 3 + r];
+            for (long c = 0; c < 3; ++c) acc += flat[s * 9 + r * 3 + c] * x[s * 3 + c];
+            worst = std::fmax(worst, std::fabs(acc));
+            for (long c = 0; c < 3; ++c) {
+                double ll = 0;
+                for (long k = 0; k < 3; ++k) ll += S[s](r, k) * S[s](c, k);
+                worst = std::fmax(worst, std::fabs(ll - flat[s * 9 + r * 3 + c]));
+            }
+        }
+    EXPECT(worst < 1e-9, "cholesky / cholesky_solve residual %g", worst);
+}
+
+int main() {
+    if (gmb_device_count() == 0) {
+        // no CPU fallback: the call must fail loudly
+        float a[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, x[4] = {1, 2, 3, 4};
+        try {
+            gb::linear_solve<float, true>(a, 4, 1, x, 1);
+            std::printf("FAIL: computed without a GPU\n");
+            return 1;
+        } catch (const gb::Error& e) {
+            std::printf("no GPU: %s (expected)\n", e.what());
+            return e.code == GMB_ERR_NO_DEVICE ? 0 : 1;
+        }
+    }
+    for (long n : {2L, 3L, 4L, 5L, 8L, 16L}) {
+        test_pointer_linear_solve<float>(n, 3001);
+        test_pointer_linear_solve<double>(n, 1777);
+    }
+    test_object_inv<float, 4, geom::ROW_MAJOR, geom::ROW_MAJOR>(2049);
+    test_object_inv<double, 4, geom::ROW_MAJOR, geom::COL_MAJOR>(1000);
+    test_object_inv<float, 3, geom::COL_MAJOR, geom::ROW_MAJOR>(1000);     // 40-byte objects: packed path
+    test_object_inv<double, 6, geom::ROW_MAJOR, geom::ROW_MAJOR>(500);
+    test_vec_linear_solve<double, 3>(1000);
+    test_vec_linear_solve<double, 4>(1000);
+    test_vec_linear_solve<double, 7>(1000);
+    test_decomp_and_cholesky(999);
+    std::printf(failures ? "FAILED (%d)\n" : "batch.hpp OK (%d failures)\n", failures);
+    return failures ? 1 : 0;
+}
