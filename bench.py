@@ -103,12 +103,22 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads(lib):
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 for its workers; the
+    CPU reference arm is meant to use every core, so the OpenMP team size is set explicitly."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if lib.kind == "reference":
+        lib.set_threads(n)
+        return n
+    return 1
+
+
 def cpu_reference_rate(seconds_budget=12.0, sample_log2=21):
     """The reference's own linear_solve<float,true> on an AoS sample, OpenMP over all host threads."""
     import numpy as np
     from oracle import pyoracle as po
     lib = po.best()
-    threads = lib.max_threads()
+    threads = host_threads(lib)
     Bs = 1 << sample_log2
     rng = np.random.default_rng(123)
     A0 = po.exact_grid(rng, (Bs, 16), np.float32)
@@ -136,7 +146,7 @@ def run_reference(args, rank, world):
     import numpy as np
     from oracle import pyoracle as po
     lib = po.best()
-    threads = lib.max_threads()
+    threads = host_threads(lib)
     Bs = 1 << 21
     rng = np.random.default_rng(123)
     A0 = po.exact_grid(rng, (Bs, 16), np.float32)
@@ -218,6 +228,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     B = 1 << args.log2_batch

@@ -28,6 +28,9 @@
 namespace gmb {
 
 constexpr int kSubThreads = 128;
+#ifndef GMB_SUB_MIN_BLOCKS
+#define GMB_SUB_MIN_BLOCKS 3      // cap at 128 registers: occupancy matters more than a few spills here (ncu: 12% -> 25%)
+#endif
 constexpr int kRegBudgetWords = 100;      // register words for the local block
 
 constexpr int MODE_SOLVE = 0;   // A, Bm -> X, ok (, LU)
@@ -82,7 +85,7 @@ struct BatchAddr {          // element e of system s: p[s_base + e * e_stride]
 };
 
 template <typename T, int N, int XC, int MODE>
-__global__ void __launch_bounds__(kSubThreads)
+__global__ void __launch_bounds__(kSubThreads, GMB_SUB_MIN_BLOCKS)
 k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ perm_out,
           uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B, int soa, int a_rm, int x_rm) {
     constexpr int WORDS = (int)sizeof(T) / 4;
@@ -180,8 +183,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
                     const int c = c0 + j;
                     const bool is_rider = XC > 0 && c >= N;
                     const bool go = (c > i) && (is_rider || upd);
-                    const T v = fma_rn(-b, a[i][j], a[r][j]);
-                    a[r][j] = go ? v : a[r][j];
+                    if (go) a[r][j] = fma_rn(-b, a[i][j], a[r][j]);     // predicated FMA, no select
                 }
             }
         }

@@ -1,0 +1,69 @@
+"""Small driver for ncu captures of the secondary kernels (one launch of each after a warm-up).
+
+    python profiles/prof_cases.py [case ...]      cases: c2 c3aos c3soa c4n4 c4n8 c5 c1aos
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+
+import geomc_b200 as gm
+
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(7)
+
+
+def grid(shape, dt):
+    return (torch.randint(-(1 << 19), 1 << 19, shape, device=dev, generator=g).to(dt) * 2.0 ** -17)
+
+
+def run(case):
+    f32, f64 = torch.float32, torch.float64
+    if case == "c2":
+        B = 1 << 23
+        R = torch.randint(-128, 128, (B, 3, 3), device=dev, generator=g).double() * 2.0 ** -5
+        S = (R @ R.transpose(1, 2) + torch.eye(3, device=dev, dtype=f64)).reshape(B, 9).contiguous()
+        Ss, bs = gm.BatchSoA.from_aos(S), gm.BatchSoA.from_aos(grid((B, 3), f64))
+        xs, ok = bs.empty_like(), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.cholesky_solve(Ss, bs, 3, x_out=xs, ok_out=ok)
+    if case in ("c3aos", "c3soa", "c1aos"):
+        B = 1 << 23
+        A, b = grid((B, 16), f32), grid((B, 4), f32)
+        ok = torch.zeros(B, dtype=torch.uint8, device=dev)
+        if case == "c1aos":
+            x = torch.empty_like(b)
+            return lambda: gm.linear_solve(A, b, 4, x_out=x, ok_out=ok)
+        if case == "c3soa":
+            A = gm.BatchSoA.from_aos(A)
+        out = A.empty_like() if case == "c3soa" else torch.empty_like(A)
+        return lambda: gm.inv(A, 4, out=out, ok_out=ok)
+    if case.startswith("c4n"):
+        n = int(case[3:])
+        B = 1 << 21
+        M = gm.BatchSoA(B, n * n, f64, dev)
+        M.data.copy_(grid(M.data.shape, f64))
+        return lambda: gm.decomp_plu(M, n, inplace=True)
+    if case == "c5":
+        B = 1 << 19
+        A, b = grid((B, 256), f32), grid((B, 16), f32)
+        x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
+    if case == "c5soa":
+        B = 1 << 19
+        A, b = gm.BatchSoA.from_aos(grid((B, 256), f32)), gm.BatchSoA.from_aos(grid((B, 16), f32))
+        x, ok = b.empty_like(), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
+    raise SystemExit(f"unknown case {case}")
+
+
+ONCE = "--once" in sys.argv           # under ncu: a single launch per case
+for case in ([a for a in sys.argv[1:] if not a.startswith("--")] or ["c2", "c3aos", "c3soa", "c4n4", "c4n8", "c5"]):
+    fn = run(case)
+    for _ in range(0 if ONCE else 3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); e1.synchronize()
+    print(f"{case}: {e0.elapsed_time(e1):.4f} ms")
