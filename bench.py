@@ -380,20 +380,25 @@ def main():
         bs = torch.randint(-(1 << 19), 1 << 19, (B, 3), device=dev, generator=g).double() * 2.0 ** -17
         Ss, bss = gm.BatchSoA.from_aos(S), gm.BatchSoA.from_aos(bs)
         xs = bss.empty_like()
-        sides.append(side_config(gm, torch, "C2: 3x3 f64 SPD cholesky + solve, SoA",
-                                 lambda: gm.cholesky_solve(Ss, bss, 3, x_out=xs, ok_out=ok), 120, B, peak))
+        # algorithmic bytes: the factorization reads only the LOWER triangle (Cholesky.h:42-44), so the SoA
+        # kernel never touches the 3 upper-triangle planes: 48 + 24 read, 24 written = 96 B (the survey's
+        # 120 B counts the full 72-byte matrix, which the AoS path does pull in sector-wise).
+        sides.append(side_config(gm, torch, "C2: 3x3 f64 SPD cholesky + solve, SoA (96 B/system: lower triangle only)",
+                                 lambda: gm.cholesky_solve(Ss, bss, 3, x_out=xs, ok_out=ok), 96, B, peak))
         xs_a = torch.empty_like(bs)
-        sides.append(side_config(gm, torch, "C2: 3x3 f64 SPD cholesky + solve, AoS",
+        sides.append(side_config(gm, torch, "C2: 3x3 f64 SPD cholesky + solve, AoS (120 B/system: whole records)",
                                  lambda: gm.cholesky_solve(S, bs, 3, x_out=xs_a, ok_out=ok), 120, B, peak))
         del R, S, bs, Ss, bss, xs, xs_a
-        # C4: f64 PLU decompose N = 2..8 (one homogeneous sub-batch per N), 2^22 systems each
-        Bc = 1 << 22
+        # C4: f64 PLU decompose N = 2..8 (one homogeneous sub-batch per N; working set >> L2 for every N)
         for nn in range(2, 9):
+            Bc = 1 << (23 if nn <= 4 else 22)
             M = gm.BatchSoA(Bc, nn * nn, f64, dev)
             M.data.copy_(torch.randint(-(1 << 19), 1 << 19, M.data.shape, device=dev, generator=g).double() * 2.0 ** -17)
-            sides.append(side_config(gm, torch, f"C4: {nn}x{nn} f64 PLU decompose (in place), SoA",
-                                     lambda: gm.decomp_plu(M, nn, inplace=True), 16 * nn * nn + nn + 2, Bc, peak, reps=3))
-            del M
+            outs = (torch.empty((Bc, nn), dtype=torch.uint8, device=dev), torch.empty(Bc, dtype=torch.uint8, device=dev),
+                    torch.empty(Bc, dtype=torch.uint8, device=dev))
+            sides.append(side_config(gm, torch, f"C4: {nn}x{nn} f64 PLU decompose (in place), SoA, 2^{23 if nn <= 4 else 22} systems",
+                                     lambda: gm.decomp_plu(M, nn, inplace=True, out=outs), 16 * nn * nn + nn + 2, Bc, peak, reps=3))
+            del M, outs
         # C5: 16x16 f32 PLU solve, 2^21 systems
         B5 = 1 << 21
         A16 = torch.randint(-(1 << 19), 1 << 19, (B5, 256), device=dev, generator=g).float() * 2.0 ** -17

@@ -136,6 +136,107 @@ __device__ __forceinline__ void aos_store(T* __restrict__ base, int64_t s, const
     }
 }
 
+// ---- AoS access staged through shared memory (warp-private transpose) -----------------------
+// A warp owns 32 consecutive records of R = E*sizeof(T) bytes: one contiguous, 16-byte aligned
+// range of 32*R bytes.  Instead of every thread fetching its own record (R-byte stride between
+// lanes: half-used sectors, 16-32 L1 wavefronts per instruction), the warp moves the range with
+// fully coalesced 128-bit accesses (512 contiguous bytes per instruction) through a warp-private
+// shared-memory buffer, and each lane then reads/writes its record there.  For power-of-two
+// records of 32 / 64 / 128 bytes the 16-byte chunks are XOR-swizzled so that both sides are
+// bank-conflict free; other record sizes (36, 48, 72, 96 bytes) are conflict free (or 2-way at
+// worst) in linear order.  Records under 32 bytes are already coalesced per thread and are not staged.
+template <int R>
+struct StageCfg {
+    static constexpr bool vec16 = (R % 16 == 0);
+    static constexpr int CH = R / 16;                        // 16-byte chunks per record (if vec16)
+    static constexpr bool swz = vec16 && (CH == 2 || CH == 4 || CH == 8);
+    static constexpr bool use = R >= 32;
+    static constexpr int warp_bytes = 32 * R;
+    __device__ static __forceinline__ int chunk(int t, int j) {           // position of chunk j of record t
+        if constexpr (swz) return t * CH + (j ^ ((t / (8 / CH)) & (CH - 1)));
+        else return t * CH + j;
+    }
+};
+
+template <typename T, int E>
+__device__ __forceinline__ unsigned char* stage_buffer() {
+    constexpr int R = E * (int)sizeof(T);
+    __shared__ __align__(16) unsigned char buf[4][StageCfg<R>::warp_bytes];
+    return buf[(threadIdx.x >> 5) & 3];
+}
+
+// all 32 lanes of the warp call this; record t = lane; `full` = all 32 records exist
+template <typename T, int E>
+__device__ __forceinline__ void aos_load_staged(const T* __restrict__ base, int64_t s_warp0, int lane, T (&q)[E]) {
+    constexpr int R = E * (int)sizeof(T);
+    using Cfg = StageCfg<R>;
+    unsigned char* sm = stage_buffer<T, E>();
+    const uint4* g = reinterpret_cast<const uint4*>(base + s_warp0 * (int64_t)E);
+    constexpr int NCH = 2 * R;                               // 32 * R / 16
+#pragma unroll
+    for (int c0 = 0; c0 < NCH; c0 += 32) {
+        const int c = c0 + lane;
+        if (NCH % 32 == 0 || c < NCH) {
+            uint4 v;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g + c));
+            int pos = c;
+            if constexpr (Cfg::swz) pos = Cfg::chunk(c / Cfg::CH, c % Cfg::CH);
+            *reinterpret_cast<uint4*>(sm + pos * 16) = v;
+        }
+    }
+    __syncwarp();
+    if constexpr (Cfg::vec16) {
+        using VT = typename VecOf<T>::type;
+        constexpr int V = soa_v<T>();
+#pragma unroll
+        for (int j = 0; j < Cfg::CH; ++j) {
+            T t[V];
+            unpack(*reinterpret_cast<const VT*>(sm + Cfg::chunk(lane, j) * 16), t);
+#pragma unroll
+            for (int v = 0; v < V; ++v) q[j * V + v] = t[v];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) q[e] = *reinterpret_cast<const T*>(sm + lane * R + e * (int)sizeof(T));
+    }
+    __syncwarp();                                            // the buffer may be reused right away
+}
+
+template <typename T, int E>
+__device__ __forceinline__ void aos_store_staged(T* __restrict__ base, int64_t s_warp0, int lane, const T (&q)[E]) {
+    constexpr int R = E * (int)sizeof(T);
+    using Cfg = StageCfg<R>;
+    unsigned char* sm = stage_buffer<T, E>();
+    if constexpr (Cfg::vec16) {
+        using VT = typename VecOf<T>::type;
+        constexpr int V = soa_v<T>();
+#pragma unroll
+        for (int j = 0; j < Cfg::CH; ++j) {
+            T t[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) t[v] = q[j * V + v];
+            *reinterpret_cast<VT*>(sm + Cfg::chunk(lane, j) * 16) = pack(t);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) *reinterpret_cast<T*>(sm + lane * R + e * (int)sizeof(T)) = q[e];
+    }
+    __syncwarp();
+    uint4* g = reinterpret_cast<uint4*>(base + s_warp0 * (int64_t)E);
+    constexpr int NCH = 2 * R;
+#pragma unroll
+    for (int c0 = 0; c0 < NCH; c0 += 32) {
+        const int c = c0 + lane;
+        if (NCH % 32 == 0 || c < NCH) {
+            int pos = c;
+            if constexpr (Cfg::swz) pos = Cfg::chunk(c / Cfg::CH, c % Cfg::CH);
+            g[c] = *reinterpret_cast<const uint4*>(sm + pos * 16);
+        }
+    }
+    __syncwarp();
+}
+
 // flat element index of logical (r, c): MxWrap, MatrixGlue.h:28-58
 template <int R, int C>
 __device__ __forceinline__ constexpr int flat(bool row_major, int r, int c) {

@@ -2,8 +2,9 @@
 //
 // SoA-interleaved batches: a warp owns one tile (W = 32*V systems); lane l holds the V = 16/sizeof(T)
 // consecutive systems l*V.. and moves every element plane with one 128-bit access.
-// AoS batches (the reference's per-object storage): one system per thread, widest vector access
-// the record size allows (the TMA-staged ingest for 64-byte records lives in gmb_tma.cu).
+// AoS batches (the reference's per-object storage): one system per thread; records of 32 bytes or
+// more are written (and, for the inverse, read) through a warp-private shared-memory transpose so
+// that every global access is a fully coalesced 128-bit access (gmb_io.cuh, aos_*_staged).
 //
 // No tensor cores: these are independent tiny systems (<= 0.6 flop/byte), bound by HBM; the
 // kernels are plain FFMA/DFMA + IEEE division on the CUDA cores.
@@ -27,10 +28,12 @@ struct Work {
             s0 = unit * W + lane * V;
             return unit * W < B;
         } else {
-            lane = 0;
+            // warp-uniform exit: a warp stays whole while any of its 32 systems exists (the staged
+            // AoS transposes are warp-cooperative); lanes past the end compute on zeros and store nothing
+            lane = threadIdx.x & 31;
             unit = (int64_t)blockIdx.x * kThreads + threadIdx.x;
             s0 = unit;
-            return unit < B;
+            return unit - lane < B;
         }
     }
     static int64_t grid(int64_t B) {
@@ -38,15 +41,41 @@ struct Work {
     }
 };
 
-template <typename T, int E, bool SOA>
-__device__ __forceinline__ void load_elems(const T* base, int64_t unit, int lane, T (&q)[Work<T, SOA>::V][E]) {
-    if constexpr (SOA) soa_load<T, E>(base, unit, lane, q);
-    else aos_load<T, E>(base, unit, q[0]);
+// B = batch size (AoS only: guards the ragged last warp)
+// Measured on B200 (profiles/): staging pays for STORES of >= 32-byte records (a per-thread store
+// leaves every 128-byte line partially written by four separate instructions: 4x4 float inverse
+// 0.80 -> 0.97 of the HBM peak), while per-thread LOADS are served well by L1 sector reuse and the
+// extra shared-memory round trip costs more than it saves (fused solve 0.94 -> 0.78 when staged).
+// The inverse kernel (64 bytes in, 64 bytes out, no other traffic) is the exception: staging both
+// sides gives 0.97 against 0.93 with staged stores only, so it passes STAGE_LOAD = true.
+template <typename T, int E, bool SOA, bool STAGE_LOAD = false>
+__device__ __forceinline__ void load_elems(const T* base, int64_t unit, int lane, int64_t B, T (&q)[Work<T, SOA>::V][E]) {
+    if constexpr (SOA) {
+        soa_load<T, E>(base, unit, lane, q);
+    } else {
+        const int64_t s_warp0 = unit - lane;
+        if (STAGE_LOAD && StageCfg<E * (int)sizeof(T)>::use && s_warp0 + 32 <= B) {      // warp-uniform
+            aos_load_staged<T, E>(base, s_warp0, lane, q[0]);
+        } else if (unit < B) {
+            aos_load<T, E>(base, unit, q[0]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) q[0][e] = (T)0;
+        }
+    }
 }
 template <typename T, int E, bool SOA>
-__device__ __forceinline__ void store_elems(T* base, int64_t unit, int lane, const T (&q)[Work<T, SOA>::V][E]) {
-    if constexpr (SOA) soa_store<T, E>(base, unit, lane, q);
-    else aos_store<T, E>(base, unit, q[0]);
+__device__ __forceinline__ void store_elems(T* base, int64_t unit, int lane, int64_t B, const T (&q)[Work<T, SOA>::V][E]) {
+    if constexpr (SOA) {
+        soa_store<T, E>(base, unit, lane, q);
+    } else {
+        const int64_t s_warp0 = unit - lane;
+        if (StageCfg<E * (int)sizeof(T)>::use && s_warp0 + 32 <= B) {
+            aos_store_staged<T, E>(base, s_warp0, lane, q[0]);
+        } else if (unit < B) {
+            aos_store<T, E>(base, unit, q[0]);
+        }
+    }
 }
 
 // K bytes per system, V systems per thread, AoS byte array [B][K]
@@ -113,8 +142,8 @@ k_plu_solve(const T* __restrict__ A, const T* Bm, T* X, uint8_t* __restrict__ ok
     int lane;
     if (!Wk::locate(B, unit, lane, s0)) return;
     T qa[V][N * N], qb[V][N * M];
-    load_elems<T, N * N, SOA>(A, unit, lane, qa);
-    load_elems<T, N * M, SOA>(Bm, unit, lane, qb);
+    load_elems<T, N * N, SOA>(A, unit, lane, B, qa);
+    load_elems<T, N * M, SOA>(Bm, unit, lane, B, qb);
     uint8_t okv[V][1];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -133,8 +162,8 @@ k_plu_solve(const T* __restrict__ A, const T* Bm, T* X, uint8_t* __restrict__ ok
         for (int e = 0; e < N * M; ++e) qb[v][e] = good ? qx[e] : qb[v][e];   // x untouched on failure
         if (LU != nullptr) flatten<T, N, N, RM>(a, qa[v]);
     }
-    store_elems<T, N * M, SOA>(X, unit, lane, qb);
-    if (LU != nullptr) store_elems<T, N * N, SOA>(LU, unit, lane, qa);
+    store_elems<T, N * M, SOA>(X, unit, lane, B, qb);
+    if (LU != nullptr) store_elems<T, N * N, SOA>(LU, unit, lane, B, qa);
     store_bytes<V, 1>(ok, s0, B, okv);
 }
 
@@ -150,7 +179,7 @@ k_decomp(T* __restrict__ A, uint8_t* __restrict__ perm_out, uint8_t* __restrict_
     int lane;
     if (!Wk::locate(B, unit, lane, s0)) return;
     T qa[V][R * C];
-    load_elems<T, R * C, SOA>(A, unit, lane, qa);
+    load_elems<T, R * C, SOA>(A, unit, lane, B, qa);
     uint8_t pv[V][NP], par[V][1], deg[V][1];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -168,7 +197,7 @@ k_decomp(T* __restrict__ A, uint8_t* __restrict__ perm_out, uint8_t* __restrict_
         deg[v][0] = (uint8_t)d;
         flatten<T, R, C, RM>(a, qa[v]);
     }
-    store_elems<T, R * C, SOA>(A, unit, lane, qa);
+    store_elems<T, R * C, SOA>(A, unit, lane, B, qa);
     store_bytes<V, NP>(perm_out, s0, B, pv);
     store_bytes<V, 1>(parity_out, s0, B, par);
     store_bytes<V, 1>(degen_out, s0, B, deg);
@@ -186,8 +215,8 @@ k_backsolve(const T* __restrict__ LU, const uint8_t* __restrict__ perm, const T*
     int lane;
     if (!Wk::locate(B, unit, lane, s0)) return;
     T qa[V][N * N], qb[V][N * M];
-    if (MODE != 2) load_elems<T, N * N, SOA>(LU, unit, lane, qa);
-    load_elems<T, N * M, SOA>(Bm, unit, lane, qb);
+    if (MODE != 2) load_elems<T, N * N, SOA>(LU, unit, lane, B, qa);
+    load_elems<T, N * M, SOA>(Bm, unit, lane, B, qb);
     uint8_t pv[V][N];
     if (MODE != 0) load_bytes<V, N>(perm, s0, B, pv);
 #pragma unroll
@@ -217,7 +246,7 @@ k_backsolve(const T* __restrict__ LU, const uint8_t* __restrict__ perm, const T*
         }
         flatten<T, N, M, RM>(x, qb[v]);
     }
-    store_elems<T, N * M, SOA>(X, unit, lane, qb);
+    store_elems<T, N * M, SOA>(X, unit, lane, B, qb);
 }
 
 // ============================================================ a8: cholesky, and fused cholesky + solve
@@ -230,8 +259,8 @@ k_cholesky(const T* A, const T* __restrict__ Bm, T* X, uint8_t* __restrict__ ok,
     int lane;
     if (!Wk::locate(B, unit, lane, s0)) return;
     T qa[V][N * N], qb[V][SOLVE ? N * M : 1];
-    load_elems<T, N * N, SOA>(A, unit, lane, qa);
-    if constexpr (SOLVE) load_elems<T, N * M, SOA>(Bm, unit, lane, qb);
+    load_elems<T, N * N, SOA>(A, unit, lane, B, qa);
+    if constexpr (SOLVE) load_elems<T, N * M, SOA>(Bm, unit, lane, B, qb);
     uint8_t okv[V][1];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -246,8 +275,8 @@ k_cholesky(const T* A, const T* __restrict__ Bm, T* X, uint8_t* __restrict__ ok,
         }
         flatten<T, N, N, RM>(a, qa[v]);
     }
-    if constexpr (SOLVE) store_elems<T, N * M, SOA>(X, unit, lane, qb);
-    if (L_out != nullptr) store_elems<T, N * N, SOA>(L_out, unit, lane, qa);
+    if constexpr (SOLVE) store_elems<T, N * M, SOA>(X, unit, lane, B, qb);
+    if (L_out != nullptr) store_elems<T, N * N, SOA>(L_out, unit, lane, B, qa);
     store_bytes<V, 1>(ok, s0, B, okv);
 }
 
@@ -264,7 +293,7 @@ k_inv_small(const T* A, T* Ainv, uint8_t* __restrict__ ok, int64_t B) {
     int lane;
     if (!Wk::locate(B, unit, lane, s0)) return;
     T qa[V][N * N], qo[V][N * N];
-    load_elems<T, N * N, SOA>(A, unit, lane, qa);
+    load_elems<T, N * N, SOA, true>(A, unit, lane, B, qa);
     uint8_t okv[V][1];
     bool all_ok = true;
 #pragma unroll
@@ -280,16 +309,16 @@ k_inv_small(const T* A, T* Ainv, uint8_t* __restrict__ ok, int64_t B) {
 #pragma unroll
             for (int c = 0; c < N; ++c) qo[v][N * r + c] = out[TRANSPOSE_OUT ? N * c + r : N * r + c];
     }
-    if (!all_ok) {
+    if (__any_sync(0xffffffffu, !all_ok)) {                  // warp-uniform: the staged AoS load is cooperative
         // "out is unchanged" for singular systems (MatrixInv.h:45-46): re-read the destination.
         T qd[V][N * N];
-        load_elems<T, N * N, SOA>(Ainv, unit, lane, qd);
+        load_elems<T, N * N, SOA>(Ainv, unit, lane, B, qd);
 #pragma unroll
         for (int v = 0; v < V; ++v)
 #pragma unroll
             for (int e = 0; e < N * N; ++e) qo[v][e] = okv[v][0] ? qo[v][e] : qd[v][e];
     }
-    store_elems<T, N * N, SOA>(Ainv, unit, lane, qo);
+    store_elems<T, N * N, SOA>(Ainv, unit, lane, B, qo);
     store_bytes<V, 1>(ok, s0, B, okv);
 }
 
@@ -306,8 +335,8 @@ k_solve_vec_small(const T* __restrict__ bases, const T* Bv, T* X, uint8_t* __res
     int lane;
     if (!Wk::locate(B, unit, lane, s0)) return;
     T qa[V][N * N], qb[V][N * M];
-    load_elems<T, N * N, SOA>(bases, unit, lane, qa);
-    load_elems<T, N * M, SOA>(Bv, unit, lane, qb);
+    load_elems<T, N * N, SOA>(bases, unit, lane, B, qa);
+    load_elems<T, N * M, SOA>(Bv, unit, lane, B, qb);
     uint8_t okv[V][1];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
@@ -330,7 +359,7 @@ k_solve_vec_small(const T* __restrict__ bases, const T* Bv, T* X, uint8_t* __res
 #pragma unroll
         for (int e = 0; e < N * M; ++e) qb[v][e] = good ? out[e] : qb[v][e];
     }
-    store_elems<T, N * M, SOA>(X, unit, lane, qb);
+    store_elems<T, N * M, SOA>(X, unit, lane, B, qb);
     store_bytes<V, 1>(ok, s0, B, okv);
 }
 

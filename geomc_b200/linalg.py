@@ -108,16 +108,23 @@ def _ptr(a: Optional[Batch]) -> Optional[int]:
 
 
 def _u8(B: int, k: int, device) -> torch.Tensor:
-    return torch.zeros((B, k) if k > 1 else (B,), dtype=torch.uint8, device=device)
+    # every entry is written by the kernels, so no fill kernel is launched
+    return torch.empty((B, k) if k > 1 else (B,), dtype=torch.uint8, device=device)
 
 
-def decomp_plu(m: Batch, rows: int, cols: Optional[int] = None, row_major: bool = True, inplace: bool = False):
-    """LU = P M with row pivoting.  -> (lu, reorder uint8[B,rows], parity uint8[B], degenerate_ct uint8[B])."""
+def decomp_plu(m: Batch, rows: int, cols: Optional[int] = None, row_major: bool = True, inplace: bool = False,
+               out: Optional[Tuple[torch.Tensor, torch.Tensor, torch.Tensor]] = None):
+    """LU = P M with row pivoting.  -> (lu, reorder uint8[B,rows], parity uint8[B], degenerate_ct uint8[B]).
+
+    `out` = preallocated (reorder, parity, degenerate_ct) uint8 tensors to write into."""
     cols = rows if cols is None else cols
     layout, B, E, dt, dev, _ = _info(m)
     assert E == rows * cols
     lu = m if inplace else _clone(m)
-    perm, parity, degen = _u8(B, rows, dev).reshape(B, rows), _u8(B, 1, dev), _u8(B, 1, dev)
+    if out is not None:
+        perm, parity, degen = out
+    else:
+        perm, parity, degen = _u8(B, rows, dev).reshape(B, rows), _u8(B, 1, dev), _u8(B, 1, dev)
     _lib.call("gmb_plu_decomp", _SUF[dt], rows, cols, B, _ptr(lu), perm.data_ptr(), parity.data_ptr(), degen.data_ptr(),
               layout, int(row_major), _stream_ptr(dev))
     return lu, perm, parity, degen
