@@ -1,4 +1,5 @@
-// gmb_subwarp.cu -- sub-warp cooperative PLU kernels for n = 5..16.
+// gmb_subwarp.cuh -- sub-warp cooperative PLU kernels for n = 5..16 (instantiated per element type
+// and mode in gmb_subwarp_{solve,decomp,inv}_{f32,f64}.cu so that the translation units build in parallel).
 //
 // A group of G lanes (G = 1, 2, 4, 8 -- the smallest that keeps the working set in registers)
 // owns one system.  The augmented matrix [A | riders] (N rows, N + XC columns) is split into
@@ -21,6 +22,7 @@
 //
 // No tensor cores: the systems are independent, 16x16 at most, and the pivot search is
 // sequential in i; this is FFMA/DFMA + IEEE division + SHFL.
+#pragma once
 #include "gmb_common.cuh"
 #include "gmb_io.cuh"
 #include "gmb_math.cuh"
@@ -67,27 +69,22 @@ __device__ __forceinline__ double shfl_t(double v, int src_in_group) {
     else return __shfl_sync(0xffffffffu, v, src_in_group, G);
 }
 
-template <typename T>
-struct BatchAddr {          // element e of system s: p[s_base + e * e_stride]
-    int64_t s_base;
-    int64_t e_stride;
-    __device__ __forceinline__ BatchAddr(int64_t s, int E, bool soa) {
+// element e of system s lives at p[base(s) + e * STRIDE]; STRIDE is a compile-time constant so every
+// element offset folds into the load/store instruction's immediate
+template <typename T, bool SOA>
+struct BatchAddr {
+    static constexpr int STRIDE = SOA ? soa_w<T>() : 1;
+    __device__ static __forceinline__ int64_t base(int64_t s, int E) {
         constexpr int W = soa_w<T>();
-        if (soa) {
-            s_base = (s / W) * (int64_t)E * W + (s % W);
-            e_stride = W;
-        } else {
-            s_base = s * (int64_t)E;
-            e_stride = 1;
-        }
+        return SOA ? (s / W) * (int64_t)E * W + (s % W) : s * (int64_t)E;
     }
-    __device__ __forceinline__ int64_t operator()(int e) const { return s_base + e * e_stride; }
 };
 
-template <typename T, int N, int XC, int MODE>
+template <typename T, int N, int XC, int MODE, bool SOA, bool A_RM, bool X_RM>
 __global__ void __launch_bounds__(kSubThreads, GMB_SUB_MIN_BLOCKS)
 k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ perm_out,
-          uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B, int soa, int a_rm, int x_rm) {
+          uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B) {
+    constexpr int ST = BatchAddr<T, SOA>::STRIDE;
     constexpr int WORDS = (int)sizeof(T) / 4;
     constexpr int G = sub_group(N, XC, WORDS);
     constexpr int NC = N + XC;
@@ -98,8 +95,9 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     const bool valid = s < B;
     if (!valid) s = B - 1;                                    // keep every lane alive for the shuffles
 
-    const BatchAddr<T> atA(s, N * N, soa != 0);
-    const BatchAddr<T> atX(s, N * (XC > 0 ? XC : 1), soa != 0);
+    const int64_t baseA = BatchAddr<T, SOA>::base(s, N * N);
+    const int64_t baseX = BatchAddr<T, SOA>::base(s, N * (XC > 0 ? XC : 1));
+    const T* Ap = A + baseA + (int64_t)c0 * (A_RM ? ST : N * ST);          // this lane's first column of A
 
     // ---- load the local block -------------------------------------------------------------
     T a[N][LC];
@@ -110,9 +108,9 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
             const int c = c0 + j;
             T v = (T)0;
             if (c < N) {
-                v = A[atA(a_rm ? N * r + c : N * c + r)];
+                v = Ap[(A_RM ? N * r + j : N * j + r) * ST];
             } else if (c < NC) {
-                if (MODE == MODE_SOLVE) v = Bm[atX(x_rm ? XC * r + (c - N) : N * (c - N) + r)];
+                if (MODE == MODE_SOLVE) v = Bm[baseX + (int64_t)(X_RM ? XC * r + (c - N) : N * (c - N) + r) * ST];
                 if (MODE == MODE_INV) v = (r == c - N) ? (T)1 : (T)0;     // identity; rows exchanged below
             }
             a[r][j] = v;
@@ -193,14 +191,14 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
 
     // ---- outputs that need no backward sweep ------------------------------------------------
     if (MODE == MODE_DECOMP || (MODE == MODE_SOLVE && LU != nullptr)) {
-        T* dst = (MODE == MODE_DECOMP) ? const_cast<T*>(A) : LU;
+        T* dst = ((MODE == MODE_DECOMP) ? const_cast<T*>(A) : LU) + baseA + (int64_t)c0 * (A_RM ? ST : N * ST);
         if (valid) {
 #pragma unroll
             for (int r = 0; r < N; ++r)
 #pragma unroll
                 for (int j = 0; j < LC; ++j) {
                     const int c = c0 + j;
-                    if (c < N) dst[atA(a_rm ? N * r + c : N * c + r)] = a[r][j];
+                    if (c < N) dst[(A_RM ? N * r + j : N * j + r) * ST] = a[r][j];
                 }
         }
     }
@@ -258,7 +256,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
                 for (int j = 0; j < LC; ++j) {
                     const int c = c0 + j;
                     if (c >= N && c < NC) {
-                        const int64_t off = atX(x_rm ? XC * r + (c - N) : N * (c - N) + r);
+                        const int64_t off = baseX + (int64_t)(X_RM ? XC * r + (c - N) : N * (c - N) + r) * ST;
                         X[off] = good ? a[r][j] : Bm[off];              // x untouched on failure (:391-393)
                     }
                 }
@@ -269,7 +267,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
 #pragma unroll
                 for (int j = 0; j < LC; ++j) {
                     const int c = c0 + j;
-                    if (c >= N && c < NC) X[atA(N * r + (c - N))] = a[r][j];   // invNxN writes `out` row-major (:192)
+                    if (c >= N && c < NC) X[baseA + (int64_t)(N * r + (c - N)) * ST] = a[r][j];   // invNxN writes `out` row-major (:192)
                 }
         }
         if (lane_g == 0 && ok_out) ok_out[s] = good ? 1 : 0;
@@ -284,14 +282,21 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
     const int64_t threads = B * G;
     const unsigned grid = (unsigned)ceil_div(threads, kSubThreads);
     if (grid == 0) return GMB_OK;
-    k_sub_plu<T, N, XC, MODE><<<grid, kSubThreads, 0, st>>>(A, Bm, X, LU, ok, perm, parity, degen, skip, B,
-                                                           layout == GMB_LAYOUT_SOA ? 1 : 0, a_rm, x_rm);
+    dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+        dispatch_bool(a_rm != 0, [&](auto ARM) {
+            // riders: linear_solve uses the matrix' own layout flag; invNxN always writes row-major
+            constexpr bool XRM = (MODE == MODE_INV) ? true : ARM.value;
+            (void)x_rm;
+            k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM><<<grid, kSubThreads, 0, st>>>(A, Bm, X, LU, ok, perm, parity,
+                                                                                           degen, skip, B);
+        });
+    });
     return after_launch();
 }
 
 template <typename T>
-int subwarp_plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout,
-                      int rm, cudaStream_t st) {
+int subwarp_plu_solve_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout,
+                           int rm, cudaStream_t st) {
     if (m != 1) return GMB_ERR_UNSUPPORTED;
     int rc = GMB_ERR_UNSUPPORTED;
     dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
@@ -301,8 +306,8 @@ int subwarp_plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, ui
 }
 
 template <typename T>
-int subwarp_decomp(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
-                   cudaStream_t st) {
+int subwarp_decomp_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
+                        cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
         rc = launch_sub<T, N.value, 0, MODE_DECOMP>(A, nullptr, nullptr, nullptr, nullptr, perm, parity, degen, 0, B, layout,
@@ -315,7 +320,8 @@ int subwarp_decomp(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8
 // is then treated as row-major, i.e. the kernel reads A with a_rm = (src layout == dst layout)
 // and writes the result flat row-major into the destination buffer.
 template <typename T>
-int subwarp_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm, cudaStream_t st) {
+int subwarp_inv_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm,
+                     cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     const int a_rm = ((src_rm != 0) == (dst_rm != 0)) ? 1 : 0;
     dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
@@ -324,20 +330,5 @@ int subwarp_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, 
     });
     return rc;
 }
-
-template <typename T>
-int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t) {
-    return GMB_ERR_UNSUPPORTED;      // n >= 5 Cholesky runs on the generic kernel (gmb_generic.cu)
-}
-
-#define INSTANTIATE(T)                                                                                              \
-    template int subwarp_plu_solve<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int,       \
-                                      cudaStream_t);                                                                \
-    template int subwarp_decomp<T>(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);         \
-    template int subwarp_inv<T>(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);                 \
-    template int subwarp_cholesky<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool,       \
-                                     cudaStream_t);
-INSTANTIATE(float)
-INSTANTIATE(double)
 
 }  // namespace gmb
