@@ -2,6 +2,7 @@
 // the register (n <= 4), sub-warp cooperative (n = 5..16) and generic kernels, plus the
 // host-buffer pipelines.  No CPU fallback anywhere: every entry point ends in a kernel launch.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -25,6 +26,8 @@ template <typename T> int subwarp_plu_solve(int, int, int64_t, const T*, const T
 template <typename T> int subwarp_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int subwarp_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
+// gmb_rowplu_*.cu
+template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 // gmb_generic.cu
 template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
 template <typename T> int generic_solve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
@@ -34,7 +37,31 @@ template <typename T> int residual_stats(int, int64_t, const T*, const T*, const
 template <typename T> int transpose_batch(bool, int, int64_t, const T*, T*, cudaStream_t);
 int checksum_bytes(const void*, int64_t, int64_t, uint64_t*, cudaStream_t);
 
+// Which fused-solve kernel serves (T, n)?  Measured on B200 (2^20 systems, AoS, CUDA events;
+// profiles/r1d_row_vs_column.md): the row-distributed kernel wins for float n in {12, 14, 15, 16}
+// and for double n >= 12 (n = 16: 2.7x); the column-distributed kernel wins or ties elsewhere.
+// GMB_ROWPLU_MIN_N=<n> in the environment overrides the table (17 disables the row kernel, 9 forces it).
+template <typename T>
+static bool use_row_kernel(int n) {
+    static const int forced = [] {
+        const char* e = std::getenv("GMB_ROWPLU_MIN_N");
+        return e ? std::atoi(e) : -1;
+    }();
+    if (forced >= 0) return n >= forced;
+    if (sizeof(T) == 4) return n == 12 || n >= 14;
+    return n >= 12;
+}
+
 static bool bad_layout(int layout) { return layout != GMB_LAYOUT_AOS && layout != GMB_LAYOUT_SOA; }
+
+// The register and sub-warp kernels use 128-bit accesses and need 16-byte aligned batches (any
+// cudaMalloc / torch allocation is).  An AoS batch that starts at an odd offset inside a larger
+// buffer (the reference's objects are only 4- or 8-byte aligned) is routed to the generic kernels,
+// which use element-wise accesses; a SoA container is aligned by construction.
+template <typename... P>
+static bool all_aligned16(P... ptrs) {
+    return ((reinterpret_cast<uintptr_t>(ptrs) % 16 == 0) && ...);
+}
 
 // ------------------------------------------------------------------ typed implementations
 template <typename T>
@@ -43,11 +70,13 @@ int plu_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* pari
     if (B < 0 || rows < 1 || cols < 1 || bad_layout(layout) || (B > 0 && A == nullptr)) return GMB_ERR_INVALID_ARG;
     if (rows > GMB_MAX_N || cols > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (cols <= 4 && cols >= 2 && (rows == cols || rows == cols - 1)) {
+    const bool fast = all_aligned16(A);
+    if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (fast && cols <= 4 && cols >= 2 && (rows == cols || rows == cols - 1)) {
         int rc = small_decomp<T>(rows, cols, B, A, perm, parity, degen, layout, rm, colpiv, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
-    if (!colpiv && rows == cols && rows >= 5) {
+    if (fast && !colpiv && rows == cols && rows >= 5) {
         int rc = subwarp_decomp<T>(rows, B, A, perm, parity, degen, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
@@ -62,7 +91,9 @@ int lu_backsolve(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* 
         return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (n >= 2 && n <= 4 && m <= 4) {
+    const bool fast = all_aligned16(LU, Bm, X);
+    if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (fast && n >= 2 && n <= 4 && m <= 4) {
         int rc = small_backsolve<T>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
@@ -76,11 +107,17 @@ int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* o
     if (B > 0 && (A == nullptr || Bm == nullptr || X == nullptr)) return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (n >= 2 && n <= 4 && m <= 4) {
+    const bool fast = all_aligned16(A, Bm, X, LU);
+    if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (fast && n >= 2 && n <= 4 && m <= 4) {
         int rc = small_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
-    if (n >= 5) {
+    if (fast && m == 1 && n >= 9 && use_row_kernel<T>(n)) {
+        int rc = rowplu_solve<T>(n, B, A, Bm, X, ok, LU, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    if (fast && n >= 5) {
         int rc = subwarp_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
@@ -96,7 +133,7 @@ int linear_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X,
     cudaStream_t st = as_stream(stream);
     if (n < 5) {
         // inverse-then-multiply: LUDecomp.h:419-426 (skip is ignored on this path, as in the reference)
-        if (n >= 2 && m <= 4) return small_solve_vec<T>(n, m, B, bases, Bv, X, ok, layout, st);
+        if (n >= 2 && m <= 4 && all_aligned16(bases, Bv, X)) return small_solve_vec<T>(n, m, B, bases, Bv, X, ok, layout, st);
         return GMB_ERR_UNSUPPORTED;
     }
     // n >= 5: column-major PLU + permutation + column-major back-substitution (:428-439)
@@ -110,7 +147,9 @@ int cholesky(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok
     if (solve && (m < 1 || (B > 0 && (Bm == nullptr || X == nullptr)))) return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (n >= 2 && n <= 4 && (!solve || m <= 4)) {
+    const bool fast = all_aligned16(A, Bm, X, L_out);
+    if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (fast && n >= 2 && n <= 4 && (!solve || m <= 4)) {
         int rc = small_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
@@ -126,9 +165,15 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
     if (B < 0 || n < 1 || bad_layout(layout) || (B > 0 && (A == nullptr || Ainv == nullptr))) return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
     cudaStream_t st = as_stream(stream);
-    if (n >= 2 && n <= 4) return small_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
-    if (n >= 5) {
-        if (A == Ainv) return GMB_ERR_INVALID_ARG;       // invNxN: m must not alias out (MatrixInv.h:174)
+    const bool fast = all_aligned16(A, Ainv);
+    if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (n >= 5 && A == Ainv) return GMB_ERR_INVALID_ARG;   // invNxN: m must not alias out (MatrixInv.h:174)
+    if (n >= 2 && n <= 4) {
+        // adjugate path only exists in the register kernels (the generic kernel is PLU-based and would
+        // change the arithmetic): an unaligned AoS batch is rejected rather than computed differently
+        return fast ? small_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st) : GMB_ERR_INVALID_ARG;
+    }
+    if (fast && n >= 5) {
         int rc = subwarp_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }

@@ -1,0 +1,274 @@
+// gmb_rowplu.cuh -- row-distributed cooperative fused PLU solve (linear_solve, LUDecomp.h:388) for
+// the upper end of the fixed-size range (n = 9..16, one right-hand side).
+//
+// The column-distributed kernel (gmb_subwarp.cuh) keeps whole columns in a lane, so a row exchange
+// costs two selects per (candidate row, local column) -- for n = 16 that alone is ~1200 selects per
+// lane, and the pivot search and the multipliers are computed redundantly by every lane of the
+// group.  Here the ROWS are distributed: row p of [A | b] lives in lane p % G, register slot p / G
+// (RL = ceil(n / G) slots of n + 1 registers).  Consequences, per elimination step i:
+//   * pivot search: each lane scans its own slots (position order = slot order, strict `>`), then a
+//     log2(G)-round shuffle reduction with "larger value, then lower position" -- exactly the
+//     reference's first strict maximum (LUDecomp.h:205-213); NaN keys are mapped so that a NaN
+//     diagonal is never displaced and a NaN candidate never wins;
+//   * row exchange i <-> pvt (whole rows, L part and rider included, :222): the two rows travel
+//     through a 2-row shared-memory bounce buffer private to the group.  Row i sits in a static
+//     (lane, slot); row pvt is addressed with lane/slot predicates on 128-bit shared accesses, so no
+//     register is ever indexed dynamically and there are no select chains;
+//   * every lane reads the pivot row from the bounce buffer (broadcast), computes the multipliers of
+//     ITS OWN rows only (one IEEE division per live row, no redundancy) and updates them:
+//     a(r,c) = fma(-b, a(i,c), a(r,c)), skipped when b == 0 (:235-241); the rider column is updated
+//     unconditionally (= backsolve_lu's forward sweep, :345-353);
+//   * slots whose rows are all above the diagonal are skipped statically.
+// Backward sweep: column-oriented (x(c) /= u(c,c); x(r) = fma(-x(c), u(r,c), x(r)) for r < c), rows
+// are in position order so everything is statically indexed; one shuffle per column.
+#pragma once
+#include "gmb_common.cuh"
+#include "gmb_io.cuh"
+#include "gmb_math.cuh"
+
+namespace gmb {
+
+constexpr int kRowThreads = 128;
+#ifndef GMB_ROW_MIN_BLOCKS
+#define GMB_ROW_MIN_BLOCKS 4
+#endif
+
+constexpr int row_rl(int n, int g) { return (n + g - 1) / g; }
+constexpr int row_group(int n, int words) {
+    for (int g = 1; g <= 16; g *= 2)
+        if (row_rl(n, g) * (n + 1) * words <= 72) return g;
+    return 16;
+}
+
+template <typename T> struct InfOf;
+template <> struct InfOf<float>  { __device__ static __forceinline__ float get()  { return __int_as_float(0x7f800000); } };
+template <> struct InfOf<double> { __device__ static __forceinline__ double get() { return __longlong_as_double(0x7ff0000000000000LL); } };
+
+template <typename T, int N, bool SOA, bool RM>
+__global__ void __launch_bounds__(kRowThreads, GMB_ROW_MIN_BLOCKS)
+k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out, int skip, int64_t B) {
+    constexpr int WORDS = (int)sizeof(T) / 4;
+    constexpr int G = row_group(N, WORDS);
+    constexpr int RL = row_rl(N, G);
+    constexpr int NC = N + 1;                                  // augmented row: n columns + the rider
+    constexpr int V = soa_v<T>();                              // elements per 128-bit access
+    constexpr int NCP = (NC + V - 1) / V * V;                  // padded row length in the bounce buffer
+    constexpr int NCH = NCP / V;                               // 16-byte chunks per row
+    constexpr int GS_RAW = 2 * NCP * WORDS;                    // words per group (two rows)
+    constexpr int GS = ((GS_RAW / 4) % 2 == 1) ? GS_RAW : GS_RAW + 4;   // odd number of 16-byte units: conflict-free across groups
+    constexpr int ST = SOA ? soa_w<T>() : 1;
+    using VT = typename VecOf<T>::type;
+
+    __shared__ __align__(16) uint32_t bounce[(kRowThreads / G) * GS];
+
+    const int lane_g = (G == 1) ? 0 : (int)(threadIdx.x % G);
+    const int group = (int)(threadIdx.x / G);
+    int64_t s = ((int64_t)blockIdx.x * kRowThreads + threadIdx.x) / G;
+    const bool valid = s < B;
+    if (!valid) s = B - 1;                                     // keep all lanes for the shuffles / syncwarp
+    T* buf0 = reinterpret_cast<T*>(bounce + group * GS);       // row i
+    T* buf1 = buf0 + NCP;                                      // row pvt
+
+    constexpr int W = soa_w<T>();
+    const int64_t baseA = SOA ? (s / W) * (int64_t)(N * N) * W + (s % W) : s * (int64_t)(N * N);
+    const int64_t baseX = SOA ? (s / W) * (int64_t)N * W + (s % W) : s * (int64_t)N;
+
+    // ---- load: slot k holds row p = k*G + lane_g ----------------------------------------------
+    T a[RL][NC];
+#pragma unroll
+    for (int k = 0; k < RL; ++k) {
+        const int p = k * G + lane_g;
+        const bool live = p < N;
+        const int pr = live ? p : 0;
+        if constexpr (!SOA && RM && (N * (int)sizeof(T)) % 16 == 0) {
+            const VT* src = reinterpret_cast<const VT*>(A + baseA + (int64_t)pr * N);
+#pragma unroll
+            for (int q = 0; q < N / V; ++q) {
+                T t[V];
+                unpack(ldg_stream(src + q), t);
+#pragma unroll
+                for (int v = 0; v < V; ++v) a[k][q * V + v] = t[v];
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < N; ++c) a[k][c] = A[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
+        }
+        a[k][N] = Bm[baseX + (int64_t)pr * ST];                // m = 1: same address in both layouts
+    }
+
+    int degenerate = 0;
+
+    // ---- elimination ----------------------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) {
+        const int oi_lane = i % G;                             // static
+        const int oi_slot = i / G;                             // static
+
+        // pivot search in column i over positions >= i
+        T best_v = (T)-2;
+        int best_p = 1 << 20;
+#pragma unroll
+        for (int k = oi_slot; k < RL; ++k) {
+            const int p = k * G + lane_g;
+            const bool cand = (p >= i) && (p < N);
+            T v = abs_(a[k][i]);
+            if (v != v) v = (p == i) ? InfOf<T>::get() : (T)-1;     // NaN: diagonal keeps the pivot, others never win
+            const bool take = cand && (v > best_v);
+            best_v = take ? v : best_v;
+            best_p = take ? p : best_p;
+        }
+#pragma unroll
+        for (int off = G / 2; off >= 1; off >>= 1) {
+            const T ov = __shfl_xor_sync(0xffffffffu, best_v, off, G);
+            const int op = __shfl_xor_sync(0xffffffffu, best_p, off, G);
+            const bool take = (ov > best_v) || (ov == best_v && op < best_p);
+            best_v = take ? ov : best_v;
+            best_p = take ? op : best_p;
+        }
+        const int pvt = best_p;
+        const bool dead = (best_v == (T)0);                    // :215
+        degenerate += dead ? 1 : 0;
+        const bool do_swap = pvt != i;
+        const int pl = pvt % G, ps = pvt / G;
+
+        // rows i and pvt -> bounce buffer (row i always: it is also the broadcast copy of the pivot row)
+        if (lane_g == oi_lane) {
+#pragma unroll
+            for (int q = 0; q < NCH; ++q) {
+                T t[V];
+#pragma unroll
+                for (int v = 0; v < V; ++v) t[v] = (q * V + v < NC) ? a[oi_slot][q * V + v] : (T)0;
+                reinterpret_cast<VT*>(buf0)[q] = pack(t);
+            }
+        }
+#pragma unroll
+        for (int k = oi_slot; k < RL; ++k) {
+            if (do_swap && lane_g == pl && ps == k) {
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    T t[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) t[v] = (q * V + v < NC) ? a[k][q * V + v] : (T)0;
+                    reinterpret_cast<VT*>(buf1)[q] = pack(t);
+                }
+            }
+        }
+        __syncwarp();
+        // pivot row (after the exchange) for everybody; the two owners also take their new rows
+        const T* prow = do_swap ? buf1 : buf0;
+        T piv[NC];
+#pragma unroll
+        for (int q = 0; q < NCH; ++q) {
+            T t[V];
+            unpack(reinterpret_cast<const VT*>(prow)[q], t);
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                if (q * V + v < NC) piv[q * V + v] = t[v];
+        }
+        if (do_swap && lane_g == oi_lane) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) a[oi_slot][c] = piv[c];
+        }
+#pragma unroll
+        for (int k = oi_slot; k < RL; ++k) {
+            if (do_swap && lane_g == pl && ps == k) {
+#pragma unroll
+                for (int q = 0; q < NCH; ++q) {
+                    T t[V];
+                    unpack(reinterpret_cast<const VT*>(buf0)[q], t);
+#pragma unroll
+                    for (int v = 0; v < V; ++v)
+                        if (q * V + v < NC) a[k][q * V + v] = t[v];
+                }
+            }
+        }
+        __syncwarp();
+
+        // multipliers and rank-1 update of this lane's own rows below the pivot
+        const T pv = piv[i];
+#pragma unroll
+        for (int k = oi_slot; k < RL; ++k) {
+            const int p = k * G + lane_g;
+            const bool below = (p > i) && (p < N);
+            const T b = div_rn(a[k][i], pv);                   // :234
+            const bool upd = below && !dead && (b != (T)0);    // :235
+            if (below && !dead) a[k][i] = b;                   // :245
+#pragma unroll
+            for (int c = i + 1; c < N; ++c) {
+                const T v = fma_rn(-b, piv[c], a[k][c]);       // :241
+                a[k][c] = upd ? v : a[k][c];
+            }
+            {                                                  // rider: forward sweep, never skipped (:350)
+                const T v = fma_rn(-piv[N], b, a[k][N]);
+                a[k][N] = below ? v : a[k][N];
+            }
+        }
+    }
+
+    const bool good = degenerate == 0;
+
+    // ---- optional: the packed LU the reference leaves in `a` --------------------------------------
+    if (LU != nullptr && valid) {
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+            const int p = k * G + lane_g;
+            if (p < N) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) LU[baseA + (int64_t)(RM ? N * p + c : N * c + p) * ST] = a[k][c];
+            }
+        }
+    }
+
+    // ---- backward sweep, column-oriented (:356-365) -----------------------------------------------
+#pragma unroll
+    for (int c = N - 1; c >= 0; --c) {
+        const int oc_lane = c % G, oc_slot = c / G;            // static
+        const bool on = c >= skip;
+        const T q = div_rn(a[oc_slot][N], a[oc_slot][c]);
+        T xc = (G == 1) ? q : __shfl_sync(0xffffffffu, q, oc_lane, G);
+        if (on && lane_g == oc_lane) a[oc_slot][N] = q;
+#pragma unroll
+        for (int k = 0; k <= oc_slot; ++k) {
+            const int p = k * G + lane_g;
+            const bool row_on = on && (p < c) && (p >= skip);
+            const T v = fma_rn(-xc, a[k][c], a[k][N]);
+            a[k][N] = row_on ? v : a[k][N];
+        }
+    }
+
+    // ---- store ------------------------------------------------------------------------------------
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+            const int p = k * G + lane_g;
+            if (p < N) {
+                const int64_t off = baseX + (int64_t)p * ST;
+                X[off] = good ? a[k][N] : Bm[off];             // x untouched on failure (:391-393)
+            }
+        }
+        if (lane_g == 0 && ok_out) ok_out[s] = good ? 1 : 0;
+    }
+}
+
+template <typename T>
+int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout, int rm,
+                      cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
+        const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
+        if (grid == 0) {
+            rc = GMB_OK;
+            return;
+        }
+        dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+            dispatch_bool(rm != 0, [&](auto RM) {
+                k_row_solve<T, N.value, SOA.value, RM.value><<<grid, kRowThreads, 0, st>>>(A, Bm, X, LU, ok, skip, B);
+            });
+        });
+        rc = after_launch();
+    });
+    return rc;
+}
+
+}  // namespace gmb

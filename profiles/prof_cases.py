@@ -50,6 +50,13 @@ def run(case):
         A, b = grid((B, 256), f32), grid((B, 16), f32)
         x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
+    if case.startswith("solve"):          # solve<f|d><n>: fused PLU solve, AoS, n x n
+        dt = f32 if case[5] == "f" else f64
+        n = int(case[6:])
+        B = 1 << 20
+        A, b = grid((B, n * n), dt), grid((B, n), dt)
+        x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.linear_solve(A, b, n, x_out=x, ok_out=ok)
     if case == "c5soa":
         B = 1 << 19
         A, b = gm.BatchSoA.from_aos(grid((B, 256), f32)), gm.BatchSoA.from_aos(grid((B, 16), f32))

@@ -169,6 +169,31 @@ def test_aos_soa_round_trip(gm, dt, E):
             assert flat[((s // W) * E + e) * W + s % W] == a[s, e]
 
 
+@pytest.mark.parametrize("n", [3, 4, 6, 16])
+def test_unaligned_aos_batches_take_the_elementwise_kernels(gm, port, n):
+    """The reference's objects are only 4/8-byte aligned: an AoS batch at an odd offset must still be
+    solved (generic element-wise kernels), bit-identically."""
+    rng = np.random.default_rng(n)
+    B = 777
+    A = rng.standard_normal((B, n * n)).astype(np.float32)
+    b = rng.standard_normal((B, n)).astype(np.float32)
+    buf_a = torch.zeros(B * n * n + 1, dtype=torch.float32, device="cuda")
+    buf_b = torch.zeros(B * n + 1, dtype=torch.float32, device="cuda")
+    dA = buf_a[1:].view(B, n * n)
+    db = buf_b[1:].view(B, n)
+    dA.copy_(torch.from_numpy(A))
+    db.copy_(torch.from_numpy(b))
+    assert dA.data_ptr() % 16 != 0
+    x, ok = gm.linear_solve(dA, db, n)
+    _, xe, oke = port.linear_solve(A, b, n)
+    check(down(x), xe, f"unaligned linear_solve n={n}")
+    check(down(ok), oke, "unaligned ok")
+    lu, p, par, dg = gm.decomp_plu(dA, n)
+    e = port.decomp_plu(A, n)
+    check(down(lu), e[0], "unaligned decomp lu")
+    check(down(p).astype(np.int64), e[1], "unaligned decomp perm")
+
+
 def test_host_api_matches_device_api(gm, port):
     rng = np.random.default_rng(9)
     B, n = 70001, 4
@@ -239,3 +264,21 @@ def test_full_size_properties(gm):
     good = (ok1 == 1) & (ok2 == 1)
     rel = ((inv2 - A).abs().amax(dim=1) / A.abs().amax(dim=1))[good]
     assert rel.median().item() < 1e-4
+
+
+@pytest.mark.parametrize("force", ["9", "17"])
+def test_both_large_n_solve_kernels(force):
+    """The dispatch table picks one of two fused-solve kernels per (type, n); force each of them for
+    every n = 9..16 (row-distributed with GMB_ROWPLU_MIN_N=9, column-distributed with =17) in a fresh
+    process and rerun the oracle comparison."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GMB_ROWPLU_MIN_N=force)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = " or ".join(f"{n}-" for n in range(9, 17))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
+                        "-k", f"(test_random_vs_oracle or test_golden) and ({sel}) and not both_large"],
+                       env=env, capture_output=True, text=True, cwd=root, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
