@@ -39,7 +39,7 @@ int checksum_bytes(const void*, int64_t, int64_t, uint64_t*, cudaStream_t);
 
 // Which fused-solve kernel serves (T, n)?  Measured on B200 (2^20 systems, AoS, CUDA events;
 // profiles/r1d_row_vs_column.md): the row-distributed kernel wins for float n in {12, 14, 15, 16}
-// and for double n >= 12 (n = 16: 2.7x); the column-distributed kernel wins or ties elsewhere.
+// and for double n = 10 and n >= 12 (n = 16: 3.4x); the column-distributed kernel wins elsewhere.
 // GMB_ROWPLU_MIN_N=<n> in the environment overrides the table (17 disables the row kernel, 9 forces it).
 template <typename T>
 static bool use_row_kernel(int n) {
@@ -49,7 +49,7 @@ static bool use_row_kernel(int n) {
     }();
     if (forced >= 0) return n >= forced;
     if (sizeof(T) == 4) return n == 12 || n >= 14;
-    return n >= 12;
+    return n == 10 || n >= 12;
 }
 
 static bool bad_layout(int layout) { return layout != GMB_LAYOUT_AOS && layout != GMB_LAYOUT_SOA; }
