@@ -399,6 +399,12 @@ def main():
             sides.append(side_config(gm, torch, f"C4: {nn}x{nn} f64 PLU decompose (in place), SoA, 2^{23 if nn <= 4 else 22} systems",
                                      lambda: gm.decomp_plu(M, nn, inplace=True, out=outs), 16 * nn * nn + nn + 2, Bc, peak, reps=3))
             del M, outs
+        # row (f)1: orthogonal<float,3> (cross product) and <float,4> (3x4 PLU + back-substitution), AoS Vec arrays
+        for nn in (3, 4):
+            Vn = torch.randint(-(1 << 19), 1 << 19, (B, (nn - 1) * nn), device=dev, generator=g).float() * 2.0 ** -17
+            sides.append(side_config(gm, torch, f"(f)1: orthogonal<float,{nn}>, AoS Vec arrays", lambda: gm.orthogonal(Vn, nn),
+                                     4 * ((nn - 1) * nn + nn), B, peak, reps=3))
+            del Vn
         # C5: 16x16 f32 PLU solve, 2^21 systems
         B5 = 1 << 21
         A16 = torch.randint(-(1 << 19), 1 << 19, (B5, 256), device=dev, generator=g).float() * 2.0 ** -17

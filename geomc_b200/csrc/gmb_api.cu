@@ -36,6 +36,9 @@ template <typename T> int generic_inv(int, int64_t, const T*, T*, uint8_t*, int,
 template <typename T> int residual_stats(int, int64_t, const T*, const T*, const T*, const uint8_t*, double*, int, int, cudaStream_t);
 template <typename T> int transpose_batch(bool, int, int64_t, const T*, T*, cudaStream_t);
 int checksum_bytes(const void*, int64_t, int64_t, uint64_t*, cudaStream_t);
+template <typename T> int small_orthogonal(int, int64_t, const T*, T*, int, cudaStream_t);
+template <typename T> int generic_orthogonal(int, int64_t, const T*, T*, int, cudaStream_t);
+template <typename T> int generic_nullspace(int, int, int64_t, const T*, T*, uint8_t*, int, cudaStream_t);
 
 // Which fused-solve kernel serves (T, n)?  Measured on B200 (2^20 systems, AoS, CUDA events;
 // profiles/r1d_row_vs_column.md): the row-distributed kernel wins for float n in {12, 14, 15, 16}
@@ -178,6 +181,24 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     return generic_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
+}
+
+template <typename T>
+int orthogonal(int n, int64_t B, const T* V, T* out, int layout, void* stream) {
+    if (B < 0 || n < 2 || bad_layout(layout) || (B > 0 && (V == nullptr || out == nullptr))) return GMB_ERR_INVALID_ARG;
+    if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    const bool fast = all_aligned16(V, out);
+    if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (fast && n <= 4) return small_orthogonal<T>(n, B, V, out, layout, as_stream(stream));
+    return generic_orthogonal<T>(n, B, V, out, layout, as_stream(stream));
+}
+
+template <typename T>
+int nullspace(int N, int nb, int64_t B, const T* bases, T* null, uint8_t* ok, int layout, void* stream) {
+    if (B < 0 || N < 3 || nb < 1 || nb >= N || bad_layout(layout) || (B > 0 && (bases == nullptr || null == nullptr)))
+        return GMB_ERR_INVALID_ARG;
+    if (N > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    return generic_nullspace<T>(N, nb, B, bases, null, ok, layout, as_stream(stream));
 }
 
 // ------------------------------------------------------------------ host-buffer pipelines
@@ -451,6 +472,13 @@ int gmb_stream_synchronize(void* stream) { return (int)cudaStreamSynchronize(as_
     int gmb_inv_##SUF(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_row_major,              \
                       int dst_row_major, void* stream) {                                                              \
         return inv<T>(n, B, A, Ainv, ok, layout, src_row_major, dst_row_major, stream);                               \
+    }                                                                                                                 \
+    int gmb_orthogonal_##SUF(int n, int64_t B, const T* V, T* out, int layout, void* stream) {                        \
+        return orthogonal<T>(n, B, V, out, layout, stream);                                                           \
+    }                                                                                                                 \
+    int gmb_nullspace_##SUF(int N, int nb, int64_t B, const T* bases, T* null_basis, uint8_t* ok, int layout,         \
+                            void* stream) {                                                                           \
+        return nullspace<T>(N, nb, B, bases, null_basis, ok, layout, stream);                                         \
     }                                                                                                                 \
     int gmb_solve_residual_##SUF(int n, int64_t B, const T* A, const T* X, const T* Bm, const uint8_t* ok,            \
                                  double* stats4, int layout, int row_major, void* stream) {                           \

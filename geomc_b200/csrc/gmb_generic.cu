@@ -238,6 +238,85 @@ g_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm
 // linear_solve(Vec) for n >= 5 (LUDecomp.h:428-439) is g_solve<T,3> with rm = 0: the local
 // routines index logical (r, c) and load_local / store_local map the column-major storage.
 
+// orthogonal (Orthogonal.h:73-98, general N; N = 2, 3 follow the specialisations :101-110) and
+// nullspace (Orthogonal.h:136-178).  Vectors are rows of a row-major matrix; nb = number of bases.
+template <typename T>
+__device__ void orthogonal_local(const T* g, Addr<T> atV, int64_t s, int n, T* o) {
+    if (n == 2) {
+        o[0] = -g[atV(s, 1)];
+        o[1] = g[atV(s, 0)];
+        return;
+    }
+    if (n == 3) {
+        const T ax = g[atV(s, 0)], ay = g[atV(s, 1)], az = g[atV(s, 2)];
+        const T bx = g[atV(s, 3)], by = g[atV(s, 4)], bz = g[atV(s, 5)];
+        o[0] = dop(ay, bz, az, by);
+        o[1] = dop(az, bx, ax, bz);
+        o[2] = dop(ax, by, ay, bx);
+        return;
+    }
+    T a[kMaxN * kMaxN];
+    uint8_t p[kMaxN];
+    for (int e = 0; e < n * (n - 1); ++e) a[e] = g[atV(s, e)];
+    for (int e = 0; e < n; ++e) o[e] = (T)0;
+    bool par;
+    if (lu_local<T, false>(a, n - 1, n, p, par) > 0) return;
+    o[n - 1] = (T)1;
+    for (int r = n - 2; r >= 0; --r) {
+        T acc = o[r];
+        for (int c = n - 1; c > r; --c) acc = fma_rn(-o[c], a[n * r + c], acc);
+        o[r] = div_rn(acc, a[n * r + r]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGenThreads)
+g_orthogonal(int n, int64_t B, const T* V, T* out, int layout) {
+    const int64_t s = (int64_t)blockIdx.x * kGenThreads + threadIdx.x;
+    if (s >= B) return;
+    T o[kMaxN];
+    orthogonal_local<T>(V, Addr<T>{layout, n * (n - 1)}, s, n, o);
+    Addr<T> atO{layout, n};
+    for (int e = 0; e < n; ++e) out[atO(s, e)] = o[e];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kGenThreads)
+g_nullspace(int N, int nb, int64_t B, const T* bases, T* null, uint8_t* ok, int layout) {
+    const int64_t s = (int64_t)blockIdx.x * kGenThreads + threadIdx.x;
+    if (s >= B) return;
+    const int nn = N - nb;
+    Addr<T> atB{layout, N * nb}, atN{layout, N * nn};
+    if (nn == 1) {                                          // :138-142
+        T o[kMaxN];
+        orthogonal_local<T>(bases, atB, s, N, o);
+        for (int e = 0; e < N; ++e) null[atN(s, e)] = o[e];
+        if (ok) ok[s] = 1;
+        return;
+    }
+    T a[kMaxN * kMaxN];
+    uint8_t p[kMaxN];
+    for (int e = 0; e < N * nb; ++e) a[e] = bases[atB(s, e)];
+    bool par;
+    const int d = lu_local<T, false>(a, nb, N, p, par);
+    if (ok) ok[s] = d == 0 ? 1 : 0;
+    if (d > 0) {                                            // :161: the zero-filled null basis is returned
+        for (int e = 0; e < N * nn; ++e) null[atN(s, e)] = (T)0;
+        return;
+    }
+    T x[kMaxN];
+    for (int b = 0; b < nn; ++b) {
+        for (int e = 0; e < N; ++e) x[e] = (T)0;
+        x[b + nb] = (T)1;
+        for (int r = nb - 1; r >= 0; --r) {
+            T xi = -a[N * r + (nb + b)];
+            for (int c = r + 1; c < nb; ++c) xi = fma_rn(-a[N * r + c], x[c], xi);   // :171
+            x[r] = div_rn(xi, a[N * r + r]);
+        }
+        for (int e = 0; e < N; ++e) null[atN(s, N * b + e)] = x[e];
+    }
+}
+
 // ---------------------------------------------------------------- residual statistics
 template <typename T>
 __global__ void __launch_bounds__(128)
@@ -421,6 +500,24 @@ int generic_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, 
 }
 
 template <typename T>
+int generic_orthogonal(int n, int64_t B, const T* V, T* out, int layout, cudaStream_t st) {
+    if (n < 2 || n > kMaxN) return GMB_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)ceil_div(B, kGenThreads);
+    if (grid == 0) return GMB_OK;
+    g_orthogonal<T><<<grid, kGenThreads, 0, st>>>(n, B, V, out, layout);
+    return after_launch();
+}
+
+template <typename T>
+int generic_nullspace(int N, int nb, int64_t B, const T* bases, T* null, uint8_t* ok, int layout, cudaStream_t st) {
+    if (N < 3 || N > kMaxN || nb < 1 || nb >= N) return GMB_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)ceil_div(B, kGenThreads);
+    if (grid == 0) return GMB_OK;
+    g_nullspace<T><<<grid, kGenThreads, 0, st>>>(N, nb, B, bases, null, ok, layout);
+    return after_launch();
+}
+
+template <typename T>
 int residual_stats(int n, int64_t B, const T* A, const T* X, const T* Bm, const uint8_t* ok, double* stats, int layout,
                    int rm, cudaStream_t st) {
     if (n < 1 || n > kMaxN) return GMB_ERR_UNSUPPORTED;
@@ -465,7 +562,9 @@ int transpose_batch(bool to_soa, int E, int64_t B, const T* src, T* dst, cudaStr
     template int generic_inv<T>(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);                     \
     template int residual_stats<T>(int, int64_t, const T*, const T*, const T*, const uint8_t*, double*, int, int,       \
                                    cudaStream_t);                                                                       \
-    template int transpose_batch<T>(bool, int, int64_t, const T*, T*, cudaStream_t);
+    template int transpose_batch<T>(bool, int, int64_t, const T*, T*, cudaStream_t);                                     \
+    template int generic_orthogonal<T>(int, int64_t, const T*, T*, int, cudaStream_t);                                  \
+    template int generic_nullspace<T>(int, int, int64_t, const T*, T*, uint8_t*, int, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(double)
 

@@ -363,6 +363,65 @@ k_solve_vec_small(const T* __restrict__ bases, const T* Bv, T* X, uint8_t* __res
     store_bytes<V, 1>(ok, s0, B, okv);
 }
 
+// ============================================================ (f)1: orthogonal, N <= 4
+// Orthogonal.h:73-110: N = 2 left_perpendicular, N = 3 cross product (diff_of_products), N = 4
+// rectangular decomp_plu of the 3 x 4 matrix + back-substitution from o[3] = 1; the zero vector when
+// the decomposition reports a degenerate column.
+template <typename T, int N, bool SOA>
+__global__ void __launch_bounds__(kThreads)
+k_orthogonal_small(const T* __restrict__ Vin, T* __restrict__ Out, int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    int64_t unit, s0;
+    int lane;
+    if (!Wk::locate(B, unit, lane, s0)) return;
+    T qv[V][(N - 1) * N], qo[V][N];
+    load_elems<T, (N - 1) * N, SOA>(Vin, unit, lane, B, qv);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        if constexpr (N == 2) {
+            qo[v][0] = -qv[v][1];
+            qo[v][1] = qv[v][0];
+        } else if constexpr (N == 3) {
+            const T ax = qv[v][0], ay = qv[v][1], az = qv[v][2], bx = qv[v][3], by = qv[v][4], bz = qv[v][5];
+            qo[v][0] = dop(ay, bz, az, by);                  // Vec3.h:207-219
+            qo[v][1] = dop(az, bx, ax, bz);
+            qo[v][2] = dop(ax, by, ay, bx);
+        } else {
+            T a[N - 1][N], dummy[N - 1][1];
+            unflatten<T, N - 1, N, true>(qv[v], a);
+            uint8_t perm[N - 1];
+            bool parity;
+            const int degenerate = plu_rows<T, N - 1, N, 0, false>(a, dummy, perm, parity);
+            T o[N];
+            o[N - 1] = (T)1;
+#pragma unroll
+            for (int r = N - 2; r >= 0; --r) {
+                T acc = (T)0;
+#pragma unroll
+                for (int c = N - 1; c > r; --c) acc = fma_rn(-o[c], a[r][c], acc);     // :93
+                o[r] = div_rn(acc, a[r][r]);
+            }
+#pragma unroll
+            for (int e = 0; e < N; ++e) qo[v][e] = degenerate > 0 ? (T)0 : o[e];
+        }
+    }
+    store_elems<T, N, SOA>(Out, unit, lane, B, qo);
+}
+
+template <typename T>
+int small_orthogonal(int n, int64_t B, const T* V, T* out, int layout, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+            if (Work<T, SOA.value>::grid(B) > 0)
+                k_orthogonal_small<T, N.value, SOA.value><<<(unsigned)Work<T, SOA.value>::grid(B), kThreads, 0, st>>>(V, out, B);
+            rc = after_launch();
+        });
+    });
+    return rc;
+}
+
 // ============================================================ launchers (called from gmb_api.cu)
 #define GMB_LAUNCH(kernel, grid, stream, ...)                                   \
     do {                                                                        \
@@ -489,7 +548,8 @@ int small_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X, 
     template int small_cholesky<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool,            \
                                    cudaStream_t);                                                                      \
     template int small_inv<T>(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);                      \
-    template int small_solve_vec<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, cudaStream_t);
+    template int small_solve_vec<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, cudaStream_t);          \
+    template int small_orthogonal<T>(int, int64_t, const T*, T*, int, cudaStream_t);
 
 INSTANTIATE(float)
 INSTANTIATE(double)

@@ -234,6 +234,25 @@ def inv(a: Batch, n: int, src_row_major: bool = True, dst_row_major: bool = True
     return out, ok
 
 
+def orthogonal(v: Batch, n: int) -> Batch:
+    """geom::orthogonal: v = n-1 vectors of n per system, shape (B, (n-1)*n) -> (B, n)."""
+    layout, B, E, dt, dev, _ = _info(v)
+    assert E == (n - 1) * n
+    out = _new_like(v, n)
+    _lib.call("gmb_orthogonal", _SUF[dt], n, B, _ptr(v), _ptr(out), layout, _stream_ptr(dev))
+    return out
+
+
+def nullspace(bases: Batch, N: int, nb: int):
+    """geom::nullspace: bases = nb vectors of N per system -> (null basis (B, (N-nb)*N), ok uint8[B])."""
+    layout, B, E, dt, dev, _ = _info(bases)
+    assert E == nb * N and 1 <= nb < N
+    null = _new_like(bases, (N - nb) * N)
+    ok = _u8(B, 1, dev)
+    _lib.call("gmb_nullspace", _SUF[dt], N, nb, B, _ptr(bases), _ptr(null), ok.data_ptr(), layout, _stream_ptr(dev))
+    return null, ok
+
+
 def solve_residual(a: Batch, x: Batch, b: Batch, ok: Optional[torch.Tensor], n: int, row_major: bool = True) -> torch.Tensor:
     """Device-side batch statistics: [sum of per-system max|Ax-b|, max, #ok==0, #non-finite] (float64[4])."""
     layout, B, E, dt, dev, _ = _info(a)

@@ -145,6 +145,20 @@ int gmb_inv_f32(int n, int64_t B, const float* A, float* Ainv, uint8_t* ok, int 
 int gmb_inv_f64(int n, int64_t B, const double* A, double* Ainv, uint8_t* ok, int layout, int src_row_major,
                 int dst_row_major, void* stream);
 
+/* ---- "next" row (f)1: orthogonal / nullspace  (Orthogonal.h:73-110 / 136-178) ---------------
+ * gmb_orthogonal: V holds n-1 vectors of n per system (row-major (n-1) x n); out receives the vector
+ * orthogonal to all of them (n = 2: left_perpendicular, n = 3: cross product, n >= 4: rectangular
+ * decomp_plu + back-substitution from o[n-1] = 1; the zero vector if a degenerate column is found).
+ * gmb_nullspace: bases holds nb vectors of N (1 <= nb < N), null_basis receives N - nb vectors of N
+ * whose dot products with the bases vanish; ok = 0 (and a zero-filled null basis) when the bases are
+ * linearly dependent.  nb == N - 1 delegates to orthogonal, as the reference does. */
+int gmb_orthogonal_f32(int n, int64_t B, const float* V, float* out, int layout, void* stream);
+int gmb_orthogonal_f64(int n, int64_t B, const double* V, double* out, int layout, void* stream);
+int gmb_nullspace_f32(int N, int nb, int64_t B, const float* bases, float* null_basis, uint8_t* ok, int layout,
+                      void* stream);
+int gmb_nullspace_f64(int N, int nb, int64_t B, const double* bases, double* null_basis, uint8_t* ok, int layout,
+                      void* stream);
+
 /* ---- batch statistics (what the reference's tests assert, reduced on the device) ------------
  * stats[0] = sum over systems of max_i |(A x - b)_i| (only systems with ok != 0),
  * stats[1] = max of the same, stats[2] = number of systems with ok == 0,

@@ -69,6 +69,8 @@ template <typename T> struct Abi;
         static constexpr auto host_inv = gmb_host_inv_##S;                                                  \
         static constexpr auto host_cholesky_solve = gmb_host_cholesky_solve_##S;                            \
         static constexpr auto host_plu_decomp = gmb_host_plu_decomp_##S;                                    \
+        static constexpr auto orthogonal = gmb_orthogonal_##S;                                              \
+        static constexpr auto nullspace = gmb_nullspace_##S;                                                \
     };
 GMB_ABI(float, f32)
 GMB_ABI(double, f64)
@@ -330,6 +332,40 @@ index_t linear_solve_vec(const V* bases, V* x, index_t N, index_t B, bool* ok = 
           "linear_solve(Vec)");
     std::vector<std::uint8_t> okb((std::size_t)B);
     dX.download_aos(reinterpret_cast<T*>(x));
+    dok.download(okb.data(), (std::size_t)B);
+    check(gmb_stream_synchronize(nullptr), "sync");
+    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
+    return detail::count_false(okb.data(), B);
+}
+
+// ---- row (f)1 of the scope table: orthogonal / nullspace (Orthogonal.h:73-178) --------------------
+namespace detail {
+template <typename V>
+using vec_elem = typename std::remove_cv<typename std::remove_reference<decltype(*std::declval<V&>().begin())>::type>::type;
+}
+
+// for (s < B) out[s] = geom::orthogonal(v + s*(N-1));        v: B groups of N-1 packed Vec<T,N>
+template <typename V>
+void orthogonal(const V* v, V* out, index_t N, index_t B, int device = 0) {
+    using T = detail::vec_elem<V>;
+    check(gmb_set_device(device), "set_device");
+    DeviceBatch<T> dV(B, (int)((N - 1) * N), Layout::AoS), dO(B, (int)N, Layout::AoS);
+    dV.upload_aos(reinterpret_cast<const T*>(v));
+    check(Abi<T>::orthogonal((int)N, B, dV.data(), dO.data(), GMB_LAYOUT_AOS, nullptr), "orthogonal");
+    dO.download_aos(reinterpret_cast<T*>(out));
+}
+
+// for (s < B) ok[s] = geom::nullspace<T,N>(bases + s*n, n, null_basis + s*(N-n));      1 <= n < N
+template <typename V>
+index_t nullspace(const V* bases, index_t n, V* null_basis, index_t N, index_t B, bool* ok = nullptr, int device = 0) {
+    using T = detail::vec_elem<V>;
+    check(gmb_set_device(device), "set_device");
+    DeviceBatch<T> dB(B, (int)(n * N), Layout::AoS), dN(B, (int)((N - n) * N), Layout::AoS);
+    DeviceArray<std::uint8_t> dok((std::size_t)B);
+    dB.upload_aos(reinterpret_cast<const T*>(bases));
+    check(Abi<T>::nullspace((int)N, (int)n, B, dB.data(), dN.data(), dok.get(), GMB_LAYOUT_AOS, nullptr), "nullspace");
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    dN.download_aos(reinterpret_cast<T*>(null_basis));
     dok.download(okb.data(), (std::size_t)B);
     check(gmb_stream_synchronize(nullptr), "sync");
     if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;

@@ -201,6 +201,27 @@ class CpuLinalg:
         assert rc == 0
         return dst, ok
 
+    def orthogonal(self, v, n):
+        """geom::orthogonal<T,N> (Orthogonal.h:73): v = (B, (n-1)*n) -> (B, n)."""
+        v = self._prep(v)
+        B = v.shape[0]
+        assert v.shape[1] == (n - 1) * n
+        out = np.zeros((B, n), v.dtype)
+        rc = self._fn("orthogonal", v.dtype)(C.c_int(n), C.c_int64(B), _ptr(v), _ptr(out))
+        assert rc == 0
+        return out
+
+    def nullspace(self, bases, N, nb):
+        """geom::nullspace<T,N>(bases, nb, null_basis) (Orthogonal.h:136): (B, nb*N) -> ((B, (N-nb)*N), ok[B])."""
+        bases = self._prep(bases)
+        B = bases.shape[0]
+        assert bases.shape[1] == nb * N and nb < N
+        null = np.zeros((B, (N - nb) * N), bases.dtype)
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("nullspace", bases.dtype)(C.c_int(N), C.c_int(nb), C.c_int64(B), _ptr(bases), _ptr(null), _ptr(ok))
+        assert rc == 0
+        return null, ok
+
     # in-place, zero-copy variants used only by bench.py's CPU baseline timing loop
     def linear_solve_inplace(self, a, x, ok, n, m=1, skip=0, row_major=True):
         rc = self._fn("linear_solve", a.dtype)(C.c_int(n), C.c_int(m), C.c_int64(a.shape[0]), _ptr(a), _ptr(x),

@@ -19,12 +19,15 @@
 //   ref_cholesky_mtx_*    geom::cholesky(SimpleMatrix*)         Cholesky.h:83
 //   ref_inv_*             geom::inv(Md*, const Mx&)             Matrix.h:717 (static N = 2..16)
 //   ref_inv_raw_*         geom::inv2x2/inv3x3/inv4x4 / invNxN(T*,T*,n)   MatrixInv.h:49/75/117/186
+//   ref_orthogonal_*      geom::orthogonal<T,N>(const Vec<T,N>[N-1])    Orthogonal.h:73 (+ N=2,3 overloads :101,:107)
+//   ref_nullspace_*       geom::nullspace<T,N>(bases, n, null_basis)    Orthogonal.h:136
 //
 // Build: see oracle/Makefile (g++ -std=c++23 -O3 -mavx2 -mfma -ffp-contract=fast
 //        --param=avoid-fma-max-bits=0 -fno-tree-loop-vectorize -fopenmp; the Makefile explains each flag).
 #include <geomc/linalg/Matrix.h>
 #include <geomc/linalg/LUDecomp.h>
 #include <geomc/linalg/Cholesky.h>
+#include <geomc/linalg/Orthogonal.h>
 #include <geomc/linalg/Vec.h>
 
 #include <cstdint>
@@ -179,6 +182,29 @@ void inv_raw_batch(int n, int64_t B, T* src_destroyed, T* dst, uint8_t* ok) {
     }
 }
 
+template <typename T, index_t N>
+void orthogonal_batch(int64_t B, const T* v, T* out) {
+    static_assert(sizeof(geom::Vec<T, N>) == sizeof(T) * N);
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        const auto* vs = reinterpret_cast<const geom::Vec<T, N>*>(v + s * N * (N - 1));
+        geom::Vec<T, N> o = geom::orthogonal(vs);
+        std::memcpy(out + s * N, o.begin(), sizeof(T) * N);
+    }
+}
+
+template <typename T, index_t N>
+void nullspace_batch(int n, int64_t B, const T* bases, T* null_basis, uint8_t* ok) {
+    const int64_t nn = N - n;
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        const auto* bs = reinterpret_cast<const geom::Vec<T, N>*>(bases + s * N * n);
+        auto* ns = reinterpret_cast<geom::Vec<T, N>*>(null_basis + s * N * (nn > 0 ? nn : 0));
+        bool r = geom::nullspace<T, N>(bs, n, ns);
+        if (ok) ok[s] = r ? 1 : 0;
+    }
+}
+
 #define FOR_N_2_16(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
 template <typename T>
@@ -186,6 +212,26 @@ int linear_solve_vec_dispatch(int n, int m, int64_t B, T* bases, T* x, int skip,
     switch (n) {
 #define CASE(N) case N: linear_solve_vec_batch<T, N>(m, B, bases, x, skip, ok); return 0;
         FOR_N_2_16(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+
+template <typename T>
+int orthogonal_dispatch(int n, int64_t B, const T* v, T* out) {
+    switch (n) {
+#define CASE(N) case N: orthogonal_batch<T, N>(B, v, out); return 0;
+        FOR_N_2_16(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+
+template <typename T>
+int nullspace_dispatch(int N_, int n, int64_t B, const T* bases, T* null_basis, uint8_t* ok) {
+    switch (N_) {
+#define CASE(N) case N: nullspace_batch<T, N>(n, B, bases, null_basis, ok); return 0;
+        CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(15) CASE(16)
 #undef CASE
         default: return -1;
     }
@@ -262,6 +308,12 @@ int inv_dispatch(int n, int64_t B, const T* src, T* dst, uint8_t* ok, int srm, i
     extern "C" int ref_inv_##SUF(int n, int64_t B, const T* src, T* dst, uint8_t* ok, int src_row_major,          \
                                  int dst_row_major) {                                                             \
         return inv_dispatch<T>(n, B, src, dst, ok, src_row_major, dst_row_major);                                 \
+    }                                                                                                             \
+    extern "C" int ref_orthogonal_##SUF(int n, int64_t B, const T* v, T* out) {                                   \
+        return orthogonal_dispatch<T>(n, B, v, out);                                                              \
+    }                                                                                                             \
+    extern "C" int ref_nullspace_##SUF(int N_, int n, int64_t B, const T* bases, T* null_basis, uint8_t* ok) {    \
+        return nullspace_dispatch<T>(N_, n, B, bases, null_basis, ok);                                            \
     }                                                                                                             \
     extern "C" int ref_inv_raw_##SUF(int n, int64_t B, T* src_destroyed, T* dst, uint8_t* ok) {                   \
         inv_raw_batch<T>(n, B, src_destroyed, dst, ok);                                                           \

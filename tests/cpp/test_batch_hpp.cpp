@@ -175,6 +175,38 @@ static void test_decomp_and_cholesky(long B) {
     EXPECT(worst < 1e-9, "cholesky / cholesky_solve residual %g", worst);
 }
 
+template <typename T, long N>
+static void test_orthogonal_nullspace(long B) {
+    std::mt19937_64 rng(21 + N);
+    std::normal_distribution<double> g(0, 1);
+    std::vector<geom::Vec<T, N>> v(B * (N - 1)), o(B);
+    for (auto& x : v) for (long i = 0; i < N; ++i) x[i] = (T)g(rng);
+    gb::orthogonal(v.data(), o.data(), N, B);
+    double worst = 0;
+    for (long s = 0; s < B; ++s)
+        for (long k = 0; k < N - 1; ++k) {
+            double d = 0, nv = 0, no = 0;
+            for (long i = 0; i < N; ++i) { d += (double)v[s * (N - 1) + k][i] * (double)o[s][i]; nv += (double)v[s * (N - 1) + k][i] * v[s * (N - 1) + k][i]; no += (double)o[s][i] * o[s][i]; }
+            worst = std::fmax(worst, std::fabs(d) / std::sqrt(nv * no + 1e-300));
+        }
+    EXPECT(worst < (sizeof(T) == 4 ? 1e-3 : 1e-9), "orthogonal: cosine %g (N=%ld)", worst, N);
+    if (N >= 4) {
+        const long nb = 2;
+        std::vector<geom::Vec<T, N>> bs(B * nb), ns(B * (N - nb));
+        for (auto& x : bs) for (long i = 0; i < N; ++i) x[i] = (T)g(rng);
+        long bad = gb::nullspace(bs.data(), nb, ns.data(), N, B);
+        EXPECT(bad == 0, "random bases are independent");
+        worst = 0;
+        for (long s = 0; s < B; ++s)
+            for (long j = 0; j < nb; ++j) for (long k = 0; k < N - nb; ++k) {   // linear_solve.cpp:141-147
+                double d = 0;
+                for (long i = 0; i < N; ++i) d += (double)bs[s * nb + j][i] * (double)ns[s * (N - nb) + k][i];
+                worst = std::fmax(worst, std::fabs(d));
+            }
+        EXPECT(worst < (sizeof(T) == 4 ? 1e-2 : 1e-5), "nullspace: dot %g (N=%ld)", worst, N);
+    }
+}
+
 int main() {
     if (gmb_device_count() == 0) {
         // no CPU fallback: the call must fail loudly
@@ -200,6 +232,10 @@ int main() {
     test_vec_linear_solve<double, 4>(1000);
     test_vec_linear_solve<double, 7>(1000);
     test_decomp_and_cholesky(999);
+    test_orthogonal_nullspace<double, 3>(500);
+    test_orthogonal_nullspace<double, 4>(500);
+    test_orthogonal_nullspace<float, 4>(500);
+    test_orthogonal_nullspace<double, 7>(300);
     std::printf(failures ? "FAILED (%d)\n" : "batch.hpp OK (%d failures)\n", failures);
     return failures ? 1 : 0;
 }
