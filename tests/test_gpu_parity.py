@@ -282,3 +282,31 @@ def test_both_large_n_solve_kernels(force):
                        env=env, capture_output=True, text=True, cwd=root, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [2, 4, 6, 9, 12, 16])
+def test_skip_rows_single_rhs(gm, port, dt, n, soa):
+    """`skip` > 0 with ONE right-hand side goes through the register / column / row kernels (the m = 3
+    cases above take the generic path): rows < skip keep their forward-substituted values
+    (LUDecomp.h:356), bit for bit, in both layouts and both matrix orders."""
+    rng = np.random.default_rng(31 * n + np.dtype(dt).itemsize)
+    B = 513
+    A = rng.standard_normal((B, n * n)).astype(dt)
+    A[::101] = 0
+    b = rng.standard_normal((B, n)).astype(dt)
+    for skip in sorted({1, 2, n - 1, n} - {0}):
+        if skip > n:
+            continue
+        for rm in (True, False):
+            x, ok = gm.linear_solve(up(gm, A, soa), up(gm, b, soa), n, 1, skip, rm)
+            _, xe, oke = port.linear_solve(A, b, n, 1, skip, rm)
+            check(down(x), xe, f"skip={skip} n={n} rm={rm} soa={soa}")
+            check(down(ok), oke, f"skip={skip} ok")
+    # and through the Vec-form entry point for n >= 5 (column-major PLU, LUDecomp.h:428-439)
+    if n >= 5:
+        xv, okv = gm.linear_solve_vec(up(gm, A, soa), up(gm, b, soa), n, 1, 1)
+        _, xe, oke = port.linear_solve_vec(A, b, n, 1, 1)
+        check(down(xv), xe, f"Vec-form skip=1 n={n}")
+        check(down(okv), oke, "Vec-form ok")
