@@ -28,6 +28,7 @@ template <typename T> int subwarp_inv(int, int64_t, const T*, T*, uint8_t*, int,
 template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
 // gmb_rowplu_*.cu
 template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
+template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 // gmb_generic.cu
 template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
 template <typename T> int generic_solve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
@@ -66,6 +67,18 @@ static bool all_aligned16(P... ptrs) {
     return ((reinterpret_cast<uintptr_t>(ptrs) % 16 == 0) && ...);
 }
 
+// Same question for decomp_plu (GMB_ROWDECOMP_MIN_N overrides).  Measured (2^21 systems, SoA, in place):
+// the row kernel wins for float n >= 9 (n = 16: 1.35x) and double n >= 10 (n = 16: 2.3x); ties below.
+template <typename T>
+static bool use_row_decomp(int n) {
+    static const int forced = [] {
+        const char* e = std::getenv("GMB_ROWDECOMP_MIN_N");
+        return e ? std::atoi(e) : -1;
+    }();
+    if (forced >= 0) return n >= forced;
+    return sizeof(T) == 4 ? n >= 9 : n >= 10;
+}
+
 // ------------------------------------------------------------------ typed implementations
 template <typename T>
 int plu_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
@@ -77,6 +90,10 @@ int plu_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* pari
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && cols <= 4 && cols >= 2 && (rows == cols || rows == cols - 1)) {
         int rc = small_decomp<T>(rows, cols, B, A, perm, parity, degen, layout, rm, colpiv, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    if (fast && !colpiv && rows == cols && rows >= 7 && use_row_decomp<T>(rows)) {
+        int rc = rowplu_decomp<T>(rows, B, A, perm, parity, degen, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     if (fast && !colpiv && rows == cols && rows >= 5) {

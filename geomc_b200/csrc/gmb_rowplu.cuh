@@ -47,9 +47,15 @@ template <typename T> struct InfOf;
 template <> struct InfOf<float>  { __device__ static __forceinline__ float get()  { return __int_as_float(0x7f800000); } };
 template <> struct InfOf<double> { __device__ static __forceinline__ double get() { return __longlong_as_double(0x7ff0000000000000LL); } };
 
-template <typename T, int N, bool SOA, bool RM>
+// DECOMP = false: fused linear_solve (rider = right-hand side).
+// DECOMP = true : decomp_plu in place (LUDecomp.h:188): the rider carries the row's ORIGINAL index,
+//                 so after the exchanges slot p holds reorder[p]; no rider arithmetic, no backward sweep.
+//                 (A is then read and written through `LU`; perm / parity / degenerate counts are stored.)
+template <typename T, int N, bool SOA, bool RM, bool DECOMP>
 __global__ void __launch_bounds__(kRowThreads, GMB_ROW_MIN_BLOCKS)
-k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out, int skip, int64_t B) {
+k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
+            uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
+            int64_t B) {
     constexpr int WORDS = (int)sizeof(T) / 4;
     constexpr int G = row_group(N, WORDS);
     constexpr int RL = row_rl(N, G);
@@ -96,10 +102,12 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
 #pragma unroll
             for (int c = 0; c < N; ++c) a[k][c] = A[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
         }
-        a[k][N] = Bm[baseX + (int64_t)pr * ST];                // m = 1: same address in both layouts
+        if (DECOMP) a[k][N] = (T)pr;                           // the row's source index rides along
+        else a[k][N] = Bm[baseX + (int64_t)pr * ST];           // m = 1: same address in both layouts
     }
 
     int degenerate = 0;
+    bool parity = false;
 
     // ---- elimination ----------------------------------------------------------------------------
 #pragma unroll
@@ -132,6 +140,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         const bool dead = (best_v == (T)0);                    // :215
         degenerate += dead ? 1 : 0;
         const bool do_swap = pvt != i;
+        parity = parity != do_swap;
         const int pl = pvt % G, ps = pvt / G;
 
         // rows i and pvt -> bounce buffer (row i always: it is also the broadcast copy of the pivot row)
@@ -201,7 +210,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
                 const T v = fma_rn(-b, piv[c], a[k][c]);       // :241
                 a[k][c] = upd ? v : a[k][c];
             }
-            {                                                  // rider: forward sweep, never skipped (:350)
+            if (!DECOMP) {                                     // rider: forward sweep, never skipped (:350)
                 const T v = fma_rn(-piv[N], b, a[k][N]);
                 a[k][N] = below ? v : a[k][N];
             }
@@ -222,6 +231,19 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         }
     }
 
+    if constexpr (DECOMP) {
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < RL; ++k) {
+                const int p = k * G + lane_g;
+                if (p < N && perm_out) perm_out[s * N + p] = (uint8_t)(int)a[k][N];
+            }
+            if (lane_g == 0) {
+                if (parity_out) parity_out[s] = parity ? 1 : 0;
+                if (degen_out) degen_out[s] = (uint8_t)degenerate;
+            }
+        }
+    } else {
     // ---- backward sweep, column-oriented (:356-365) -----------------------------------------------
 #pragma unroll
     for (int c = N - 1; c >= 0; --c) {
@@ -251,6 +273,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         }
         if (lane_g == 0 && ok_out) ok_out[s] = good ? 1 : 0;
     }
+    }   // !DECOMP
 }
 
 template <typename T>
@@ -266,7 +289,30 @@ int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* 
         }
         dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
             dispatch_bool(rm != 0, [&](auto RM) {
-                k_row_solve<T, N.value, SOA.value, RM.value><<<grid, kRowThreads, 0, st>>>(A, Bm, X, LU, ok, skip, B);
+                k_row_solve<T, N.value, SOA.value, RM.value, false><<<grid, kRowThreads, 0, st>>>(A, Bm, X, LU, ok, nullptr,
+                                                                                                  nullptr, nullptr, skip, B);
+            });
+        });
+        rc = after_launch();
+    });
+    return rc;
+}
+
+template <typename T>
+int rowplu_decomp_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
+                       cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
+        const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
+        if (grid == 0) {
+            rc = GMB_OK;
+            return;
+        }
+        dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+            dispatch_bool(rm != 0, [&](auto RM) {
+                k_row_solve<T, N.value, SOA.value, RM.value, true><<<grid, kRowThreads, 0, st>>>(A, nullptr, nullptr, A, nullptr,
+                                                                                                 perm, parity, degen, 0, B);
             });
         });
         rc = after_launch();

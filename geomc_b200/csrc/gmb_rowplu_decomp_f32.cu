@@ -1,0 +1,9 @@
+// explicit instantiation unit: row-distributed PLU decomposition, float
+#include "gmb_rowplu.cuh"
+namespace gmb {
+template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
+template <> int rowplu_decomp<float>(int n, int64_t B, float* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
+                                   cudaStream_t st) {
+    return rowplu_decomp_impl<float>(n, B, A, perm, parity, degen, layout, rm, st);
+}
+}  // namespace gmb

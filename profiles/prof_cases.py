@@ -50,6 +50,15 @@ def run(case):
         A, b = grid((B, 256), f32), grid((B, 16), f32)
         x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
+    if case.startswith("dec"):            # dec<f|d><n>: PLU decomposition in place, SoA
+        dt = f32 if case[3] == "f" else f64
+        n = int(case[4:])
+        B = 1 << 21
+        M = gm.BatchSoA(B, n * n, dt, dev)
+        M.data.copy_(grid(M.data.shape, dt))
+        outs = (torch.empty((B, n), dtype=torch.uint8, device=dev), torch.empty(B, dtype=torch.uint8, device=dev),
+                torch.empty(B, dtype=torch.uint8, device=dev))
+        return lambda: gm.decomp_plu(M, n, inplace=True, out=outs)
     if case.startswith("solve"):          # solve<f|d><n>: fused PLU solve, AoS, n x n
         dt = f32 if case[5] == "f" else f64
         n = int(case[6:])

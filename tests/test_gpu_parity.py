@@ -310,3 +310,20 @@ def test_skip_rows_single_rhs(gm, port, dt, n, soa):
         _, xe, oke = port.linear_solve_vec(A, b, n, 1, 1)
         check(down(xv), xe, f"Vec-form skip=1 n={n}")
         check(down(okv), oke, "Vec-form ok")
+
+
+@pytest.mark.parametrize("force", ["7", "17"])
+def test_both_large_n_decomp_kernels(force):
+    """decomp_plu has the same two kernel families; force each for every n it serves and recheck
+    factors, permutation, parity and degenerate counts against the oracle."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GMB_ROWDECOMP_MIN_N=force)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = " or ".join(f"{n}-" for n in range(7, 17))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
+                        "-k", f"(test_random_vs_oracle or test_golden) and ({sel}) and not both_large"],
+                       env=env, capture_output=True, text=True, cwd=root, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
