@@ -327,3 +327,58 @@ def test_both_large_n_decomp_kernels(force):
                        env=env, capture_output=True, text=True, cwd=root, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 9, 12, 16])
+def test_no_out_of_bounds_writes(gm, dt, n, soa):
+    """(compute-sanitizer is closed on this pool.)  Every output buffer sits inside a larger allocation
+    filled with a sentinel; after running each kernel family on a ragged batch the guard bands on both
+    sides must be untouched."""
+    tdt = getattr(torch, TDT[np.dtype(dt)])
+    B = 257 + n
+    GUARD = 4096                       # elements / bytes on each side, keeps 16-byte alignment
+    SENT = -12345.0
+
+    def guarded(nelem, dtype):
+        buf = torch.full((nelem + 2 * GUARD,), SENT if dtype != torch.uint8 else 0xAB, dtype=dtype, device="cuda")
+        return buf, buf[GUARD:GUARD + nelem]
+
+    def intact(buf, nelem):
+        s = SENT if buf.dtype != torch.uint8 else 0xAB
+        return bool((buf[:GUARD] == s).all()) and bool((buf[GUARD + nelem:] == s).all())
+
+    def batch(E, fill=None):
+        nelem = gm.lib().gmb_soa_elems(B, E, np.dtype(dt).itemsize) if soa else B * E
+        buf, view = guarded(nelem, tdt)
+        if fill is not None:
+            src = torch.from_numpy(fill).cuda()
+            if soa:
+                tmp = gm.BatchSoA.from_aos(src)
+                view.copy_(tmp.data)
+            else:
+                view.copy_(src.reshape(-1))
+        obj = gm.BatchSoA(B, E, tdt, "cuda", view) if soa else view.view(B, E)
+        return buf, nelem, obj
+
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((B, n * n)).astype(dt)
+    b = rng.standard_normal((B, n)).astype(dt)
+    bufA, neA, dA = batch(n * n, A)
+    bufb, neb, db = batch(n, b)
+    bufx, nex, dx = batch(n)
+    bufo, neo, dout = batch(n * n)
+    bufok, ok = guarded(B, torch.uint8)
+    bufp, perm = guarded(B * n, torch.uint8)
+    bufpar, par = guarded(B, torch.uint8)
+    bufdg, dg = guarded(B, torch.uint8)
+    gm.linear_solve(dA, db, n, x_out=dx, ok_out=ok)
+    gm.inv(dA, n, out=dout, ok_out=ok)
+    gm.cholesky_solve(dA, db, n, x_out=dx, ok_out=ok)
+    gm.decomp_plu(dA, n, inplace=True, out=(perm.view(B, n), par, dg))
+    gm.cholesky(dA, n, inplace=True)
+    torch.cuda.synchronize()
+    for name, buf, ne in (("A", bufA, neA), ("b", bufb, neb), ("x", bufx, nex), ("inv", bufo, neo), ("ok", bufok, B),
+                          ("perm", bufp, B * n), ("parity", bufpar, B), ("degenerate", bufdg, B)):
+        assert intact(buf, ne), f"guard band of {name} was overwritten (n={n}, soa={soa})"
