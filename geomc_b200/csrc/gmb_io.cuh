@@ -237,41 +237,4 @@ __device__ __forceinline__ void aos_store_staged(T* __restrict__ base, int64_t s
     __syncwarp();
 }
 
-// flat element index of logical (r, c): MxWrap, MatrixGlue.h:28-58
-template <int R, int C>
-__device__ __forceinline__ constexpr int flat(bool row_major, int r, int c) {
-    return row_major ? (C * r + c) : (R * c + r);
-}
-
-// flat -> logical register matrix (uniform branch on the runtime layout flag; all indices static)
-template <typename T, int R, int C>
-__device__ __forceinline__ void to_logical(const T (&q)[R * C], T (&a)[R][C], bool row_major) {
-    if (row_major) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c) a[r][c] = q[C * r + c];
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c) a[r][c] = q[R * c + r];
-    }
-}
-
-template <typename T, int R, int C>
-__device__ __forceinline__ void from_logical(const T (&a)[R][C], T (&q)[R * C], bool row_major) {
-    if (row_major) {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c) q[C * r + c] = a[r][c];
-    } else {
-#pragma unroll
-        for (int r = 0; r < R; ++r)
-#pragma unroll
-            for (int c = 0; c < C; ++c) q[R * c + r] = a[r][c];
-    }
-}
-
 }  // namespace gmb
