@@ -6,8 +6,4 @@ template <> int subwarp_decomp<float>(int n, int64_t B, float* A, uint8_t* perm,
                                     cudaStream_t st) {
     return subwarp_decomp_impl<float>(n, B, A, perm, parity, degen, layout, rm, st);
 }
-template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
-template <> int subwarp_cholesky<float>(int, int, int64_t, const float*, const float*, float*, uint8_t*, float*, int, int, bool, cudaStream_t) {
-    return GMB_ERR_UNSUPPORTED;      // n >= 5 Cholesky runs on the generic kernel (gmb_generic.cu)
-}
 }  // namespace gmb

@@ -6,8 +6,4 @@ template <> int subwarp_decomp<double>(int n, int64_t B, double* A, uint8_t* per
                                     cudaStream_t st) {
     return subwarp_decomp_impl<double>(n, B, A, perm, parity, degen, layout, rm, st);
 }
-template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
-template <> int subwarp_cholesky<double>(int, int, int64_t, const double*, const double*, double*, uint8_t*, double*, int, int, bool, cudaStream_t) {
-    return GMB_ERR_UNSUPPORTED;      // n >= 5 Cholesky runs on the generic kernel (gmb_generic.cu)
-}
 }  // namespace gmb

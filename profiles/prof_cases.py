@@ -50,6 +50,15 @@ def run(case):
         A, b = grid((B, 256), f32), grid((B, 16), f32)
         x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
+    if case.startswith("chol"):           # chol<f|d><n>: fused Cholesky + solve, SoA, SPD inputs
+        dt = f32 if case[4] == "f" else f64
+        n = int(case[5:])
+        B = 1 << 20
+        R = torch.randint(-128, 128, (B, n, n), device=dev, generator=g).to(dt) * 2.0 ** -5
+        S = gm.BatchSoA.from_aos((R @ R.transpose(1, 2) + torch.eye(n, device=dev, dtype=dt)).reshape(B, n * n).contiguous())
+        b = gm.BatchSoA.from_aos(grid((B, n), dt))
+        x, ok = b.empty_like(), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.cholesky_solve(S, b, n, x_out=x, ok_out=ok)
     if case.startswith("dec"):            # dec<f|d><n>: PLU decomposition in place, SoA
         dt = f32 if case[3] == "f" else f64
         n = int(case[4:])
