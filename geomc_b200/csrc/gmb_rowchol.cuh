@@ -1,0 +1,162 @@
+// gmb_rowchol.cuh -- row-distributed cooperative Cholesky (and fused Cholesky + solve), n = 5..16.
+//
+// cholesky<T,RowMajor> (Cholesky.h:37-58) sweeps rows: s = A(r,c) - sum_{k<c} L(r,k) L(c,k), k
+// ascending; diagonal: ok &= s > 0, L(r,r) = sqrt(s); off-diagonal: L(r,c) = s / L(c,c); the strict
+// upper triangle is zeroed and only the lower triangle of the input is read.  The right-looking order
+// used here applies, for k = 0..n-1, a(r,c) = fma(-L(r,k), L(c,k), a(r,c)) to every r >= c > k: each
+// element receives the reference's terms in the reference's order (k ascending) -> bit-identical.
+//
+// Rows are distributed like in gmb_rowplu.cuh: row p of [A | b] lives in lane p % G, slot p / G, so
+// every lane divides and updates only its own rows (no redundant divisions); there is no pivoting,
+// hence no row exchange and no shared memory.  Per step k: the owner of row k broadcasts
+// d = sqrt(a(k,k)); every lane forms L(r,k) = a(r,k) / d for its rows; column k of L is then
+// broadcast with n-1-k shuffles (static source lane and register) and each lane updates the part of
+// its rows inside the lower triangle.
+//
+// Fused solve (framework-defined, same as the n <= 4 kernel and oracle.c): forward L y = b during
+// the factorization (y(k) = b(k) / L(k,k); b(r) = fma(-y(k), L(r,k), b(r))), backward L^T x = y column
+// by column: x(c) = y(c) / L(c,c), then y(r) = fma(-x(c), L(c,r), y(r)) for r < c, where L(c,r) comes
+// from the owner of row c by shuffle and is consumed by the (static) owner of row r.
+#pragma once
+#include "gmb_rowplu.cuh"
+
+namespace gmb {
+
+template <typename T, int N, bool SOLVE, bool SOA, bool RM>
+__global__ void __launch_bounds__(kRowThreads, GMB_ROW_MIN_BLOCKS)
+k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out, int64_t B) {
+    constexpr int WORDS = (int)sizeof(T) / 4;
+    constexpr int G = row_group(N, WORDS);
+    constexpr int RL = row_rl(N, G);
+    constexpr int ST = SOA ? soa_w<T>() : 1;
+    constexpr int W = soa_w<T>();
+    const int lane_g = (G == 1) ? 0 : (int)(threadIdx.x % G);
+    int64_t s = ((int64_t)blockIdx.x * kRowThreads + threadIdx.x) / G;
+    const bool valid = s < B;
+    if (!valid) s = B - 1;
+    const int64_t baseA = SOA ? (s / W) * (int64_t)(N * N) * W + (s % W) : s * (int64_t)(N * N);
+    const int64_t baseX = SOA ? (s / W) * (int64_t)N * W + (s % W) : s * (int64_t)N;
+
+    // ---- load the lower triangle of this lane's rows (and b) ------------------------------------
+    T a[RL][N];
+    T y[RL];
+#pragma unroll
+    for (int k = 0; k < RL; ++k) {
+        const int p = k * G + lane_g;
+        const int pr = p < N ? p : 0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) {
+            a[k][c] = (T)0;
+            if (c <= k * G + (G - 1)) {                        // static: some lane's row in this slot reaches column c
+                if (c <= pr) a[k][c] = A[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
+            }
+        }
+        y[k] = SOLVE ? Bm[baseX + (int64_t)pr * ST] : (T)0;
+    }
+
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int ok_lane = k % G, ok_slot = k / G;            // static owner of row k
+        // diagonal (Cholesky.h:46-48)
+        const T sdiag = (G == 1) ? a[ok_slot][k] : __shfl_sync(0xffffffffu, a[ok_slot][k], ok_lane, G);
+        ok = ok && (sdiag > (T)0);
+        const T d = sqrt_rn(sdiag);
+        if (lane_g == ok_lane) a[ok_slot][k] = d;
+        // column k of L for this lane's rows below k (Cholesky.h:50)
+#pragma unroll
+        for (int sl = ok_slot; sl < RL; ++sl) {
+            const int p = sl * G + lane_g;
+            const T v = div_rn(a[sl][k], d);
+            if (p > k && p < N) a[sl][k] = v;
+        }
+        if (SOLVE) {
+            // forward substitution: y(k) = b(k) / L(k,k), then b(r) -= y(k) L(r,k) for r > k
+            const T ykq = div_rn(y[ok_slot], d);
+            const T yk = (G == 1) ? ykq : __shfl_sync(0xffffffffu, ykq, ok_lane, G);
+            if (lane_g == ok_lane) y[ok_slot] = yk;
+#pragma unroll
+            for (int sl = ok_slot; sl < RL; ++sl) {
+                const int p = sl * G + lane_g;
+                const T v = fma_rn(-yk, a[sl][k], y[sl]);
+                if (p > k && p < N) y[sl] = v;
+            }
+        }
+        // trailing update: a(r,c) -= L(r,k) L(c,k) for k < c <= r
+#pragma unroll
+        for (int c = k + 1; c < N; ++c) {
+            const T lck = (G == 1) ? a[c / G][k] : __shfl_sync(0xffffffffu, a[c / G][k], c % G, G);   // L(c,k), static source
+#pragma unroll
+            for (int sl = c / G; sl < RL; ++sl) {              // slots below c / G hold rows < c: skipped statically
+                const int p = sl * G + lane_g;
+                const T v = fma_rn(-a[sl][k], lck, a[sl][c]);
+                if (p >= c && p < N) a[sl][c] = v;
+            }
+        }
+    }
+
+    // ---- L with the strict upper triangle zeroed (Cholesky.h:52) ---------------------------------
+    if (L_out != nullptr && valid) {
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+            const int p = k * G + lane_g;
+            if (p < N) {
+#pragma unroll
+                for (int c = 0; c < N; ++c)
+                    L_out[baseA + (int64_t)(RM ? N * p + c : N * c + p) * ST] = (c <= p) ? a[k][c] : (T)0;
+            }
+        }
+    }
+
+    // ---- backward sweep L^T x = y -----------------------------------------------------------------
+    if (SOLVE) {
+#pragma unroll
+        for (int c = N - 1; c >= 0; --c) {
+            const int oc_lane = c % G, oc_slot = c / G;        // static
+            const T q = div_rn(y[oc_slot], a[oc_slot][c]);
+            const T xc = (G == 1) ? q : __shfl_sync(0xffffffffu, q, oc_lane, G);
+            if (lane_g == oc_lane) y[oc_slot] = xc;
+#pragma unroll
+            for (int r = c - 1; r >= 0; --r) {
+                // L(c, r) sits in the owner of row c; the (static) owner of row r consumes it
+                const T lcr = (G == 1) ? a[oc_slot][r] : __shfl_sync(0xffffffffu, a[oc_slot][r], oc_lane, G);
+                const T v = fma_rn(-xc, lcr, y[r / G]);
+                if (lane_g == r % G) y[r / G] = v;
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < RL; ++k) {
+                const int p = k * G + lane_g;
+                if (p < N) X[baseX + (int64_t)p * ST] = y[k];
+            }
+        }
+    }
+    if (valid && lane_g == 0 && ok_out) ok_out[s] = ok ? 1 : 0;
+}
+
+template <typename T>
+int rowchol_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* L_out, int layout, int rm, bool solve,
+                 cudaStream_t st) {
+    if (solve && m != 1) return GMB_ERR_UNSUPPORTED;
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
+        const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
+        if (grid == 0) {
+            rc = GMB_OK;
+            return;
+        }
+        dispatch_bool(solve, [&](auto SOLVE) {
+            dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                dispatch_bool(rm != 0, [&](auto RM) {
+                    k_row_chol<T, N.value, SOLVE.value, SOA.value, RM.value><<<grid, kRowThreads, 0, st>>>(A, Bm, X, L_out, ok, B);
+                });
+            });
+        });
+        rc = after_launch();
+    });
+    return rc;
+}
+
+}  // namespace gmb
