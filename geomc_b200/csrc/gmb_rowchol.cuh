@@ -65,10 +65,12 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
         if (lane_g == ok_lane) a[ok_slot][k] = d;
         // column k of L for this lane's rows below k (Cholesky.h:50)
 #pragma unroll
-        for (int sl = ok_slot; sl < RL; ++sl) {
-            const int p = sl * G + lane_g;
-            const T v = div_rn(a[sl][k], d);
-            if (p > k && p < N) a[sl][k] = v;
+        for (int sl = 0; sl < RL; ++sl) {
+            if (sl >= ok_slot) {                               // static
+                const int p = sl * G + lane_g;
+                const T v = div_rn(a[sl][k], d);
+                if (p > k && p < N) a[sl][k] = v;
+            }
         }
         if (SOLVE) {
             // forward substitution: y(k) = b(k) / L(k,k), then b(r) -= y(k) L(r,k) for r > k
@@ -76,21 +78,27 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
             const T yk = (G == 1) ? ykq : __shfl_sync(0xffffffffu, ykq, ok_lane, G);
             if (lane_g == ok_lane) y[ok_slot] = yk;
 #pragma unroll
-            for (int sl = ok_slot; sl < RL; ++sl) {
-                const int p = sl * G + lane_g;
-                const T v = fma_rn(-yk, a[sl][k], y[sl]);
-                if (p > k && p < N) y[sl] = v;
+            for (int sl = 0; sl < RL; ++sl) {
+                if (sl >= ok_slot) {                           // static
+                    const int p = sl * G + lane_g;
+                    const T v = fma_rn(-yk, a[sl][k], y[sl]);
+                    if (p > k && p < N) y[sl] = v;
+                }
             }
         }
         // trailing update: a(r,c) -= L(r,k) L(c,k) for k < c <= r
 #pragma unroll
-        for (int c = k + 1; c < N; ++c) {
-            const T lck = (G == 1) ? a[c / G][k] : __shfl_sync(0xffffffffu, a[c / G][k], c % G, G);   // L(c,k), static source
+        for (int c = 0; c < N; ++c) {
+            if (c > k) {                                       // static
+                const T lck = (G == 1) ? a[c / G][k] : __shfl_sync(0xffffffffu, a[c / G][k], c % G, G);   // L(c,k), static source
 #pragma unroll
-            for (int sl = c / G; sl < RL; ++sl) {              // slots below c / G hold rows < c: skipped statically
-                const int p = sl * G + lane_g;
-                const T v = fma_rn(-a[sl][k], lck, a[sl][c]);
-                if (p >= c && p < N) a[sl][c] = v;
+                for (int sl = 0; sl < RL; ++sl) {
+                    if (sl >= c / G) {                         // static: lower slots hold rows < c
+                        const int p = sl * G + lane_g;
+                        const T v = fma_rn(-a[sl][k], lck, a[sl][c]);
+                        if (p >= c && p < N) a[sl][c] = v;
+                    }
+                }
             }
         }
     }
@@ -117,11 +125,13 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
             const T xc = (G == 1) ? q : __shfl_sync(0xffffffffu, q, oc_lane, G);
             if (lane_g == oc_lane) y[oc_slot] = xc;
 #pragma unroll
-            for (int r = c - 1; r >= 0; --r) {
-                // L(c, r) sits in the owner of row c; the (static) owner of row r consumes it
-                const T lcr = (G == 1) ? a[oc_slot][r] : __shfl_sync(0xffffffffu, a[oc_slot][r], oc_lane, G);
-                const T v = fma_rn(-xc, lcr, y[r / G]);
-                if (lane_g == r % G) y[r / G] = v;
+            for (int r = N - 1; r >= 0; --r) {
+                if (r < c) {                                   // static
+                    // L(c, r) sits in the owner of row c; the (static) owner of row r consumes it
+                    const T lcr = (G == 1) ? a[oc_slot][r] : __shfl_sync(0xffffffffu, a[oc_slot][r], oc_lane, G);
+                    const T v = fma_rn(-xc, lcr, y[r / G]);
+                    if (lane_g == r % G) y[r / G] = v;
+                }
             }
         }
         if (valid) {
