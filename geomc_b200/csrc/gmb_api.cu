@@ -29,6 +29,7 @@ template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*
 // gmb_rowplu_*.cu
 template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
+template <typename T> int row_backsolve(int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
 // gmb_generic.cu
 template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
 template <typename T> int generic_solve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
@@ -115,6 +116,10 @@ int lu_backsolve(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* 
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && n >= 2 && n <= 4 && m <= 4) {
         int rc = small_backsolve<T>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    if (fast && n >= 5 && m == 1 && mode != 2) {
+        int rc = row_backsolve<T>(mode, n, B, LU, perm, Bm, X, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     return generic_solve<T>(mode, n, m, B, LU, perm, Bm, X, nullptr, nullptr, skip, layout, rm, st);

@@ -170,3 +170,102 @@ int rowchol_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t
 }
 
 }  // namespace gmb
+
+namespace gmb {
+
+// ---------------------------------------------------------------------------------------------------
+// backsolve_lu / backsolve_plu (LUDecomp.h:332-366 / 271-312) for n = 5..16, one right-hand side, rows
+// distributed as above.  PLU = true gathers y(r) = b(perm[r]) first (:294).  Forward sweep column by
+// column (c ascending: x(r) = fma(-x(c), lu(r,c), x(r)) for r > c -- for every row the terms arrive in
+// the reference's order), backward sweep as in k_row_solve (c descending, then divide by u(c,c)).
+template <typename T, int N, bool PLU, bool SOA, bool RM>
+__global__ void __launch_bounds__(kRowThreads, GMB_ROW_MIN_BLOCKS)
+k_row_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, const T* Bm, T* X, int skip, int64_t B) {
+    constexpr int WORDS = (int)sizeof(T) / 4;
+    constexpr int G = row_group(N, WORDS);
+    constexpr int RL = row_rl(N, G);
+    constexpr int ST = SOA ? soa_w<T>() : 1;
+    constexpr int W = soa_w<T>();
+    const int lane_g = (G == 1) ? 0 : (int)(threadIdx.x % G);
+    int64_t s = ((int64_t)blockIdx.x * kRowThreads + threadIdx.x) / G;
+    const bool valid = s < B;
+    if (!valid) s = B - 1;
+    const int64_t baseA = SOA ? (s / W) * (int64_t)(N * N) * W + (s % W) : s * (int64_t)(N * N);
+    const int64_t baseX = SOA ? (s / W) * (int64_t)N * W + (s % W) : s * (int64_t)N;
+
+    T a[RL][N];
+    T x[RL];
+#pragma unroll
+    for (int k = 0; k < RL; ++k) {
+        const int p = k * G + lane_g;
+        const int pr = p < N ? p : 0;
+#pragma unroll
+        for (int c = 0; c < N; ++c) a[k][c] = LUm[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
+        const int src = PLU ? (int)perm[s * N + pr] : pr;
+        x[k] = Bm[baseX + (int64_t)src * ST];
+    }
+    // forward: L y = b (unit diagonal)
+#pragma unroll
+    for (int c = 0; c < N - 1; ++c) {
+        const T xc = (G == 1) ? x[c / G] : __shfl_sync(0xffffffffu, x[c / G], c % G, G);
+#pragma unroll
+        for (int sl = 0; sl < RL; ++sl) {
+            if (sl >= c / G) {                                 // static
+                const int p = sl * G + lane_g;
+                const T v = fma_rn(-xc, a[sl][c], x[sl]);
+                if (p > c && p < N) x[sl] = v;
+            }
+        }
+    }
+    // backward: U x = y
+#pragma unroll
+    for (int c = N - 1; c >= 0; --c) {
+        const int oc_lane = c % G, oc_slot = c / G;            // static
+        const bool on = c >= skip;
+        const T q = div_rn(x[oc_slot], a[oc_slot][c]);
+        const T xc = (G == 1) ? q : __shfl_sync(0xffffffffu, q, oc_lane, G);
+        if (on && lane_g == oc_lane) x[oc_slot] = q;
+#pragma unroll
+        for (int sl = 0; sl < RL; ++sl) {
+            if (sl <= oc_slot) {                               // static
+                const int p = sl * G + lane_g;
+                const T v = fma_rn(-xc, a[sl][c], x[sl]);
+                if (on && p < c && p >= skip) x[sl] = v;
+            }
+        }
+    }
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+            const int p = k * G + lane_g;
+            if (p < N) X[baseX + (int64_t)p * ST] = x[k];
+        }
+    }
+}
+
+template <typename T>
+int rowbacksolve_impl(int mode, int n, int64_t B, const T* LU, const uint8_t* perm, const T* Bm, T* X, int skip, int layout,
+                      int rm, cudaStream_t st) {
+    if (mode != 0 && mode != 1) return GMB_ERR_UNSUPPORTED;
+    if (mode == 1 && X == Bm) return GMB_ERR_UNSUPPORTED;        // the gather needs distinct buffers
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
+        const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
+        if (grid == 0) {
+            rc = GMB_OK;
+            return;
+        }
+        dispatch_bool(mode == 1, [&](auto PLU) {
+            dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                dispatch_bool(rm != 0, [&](auto RM) {
+                    k_row_backsolve<T, N.value, PLU.value, SOA.value, RM.value><<<grid, kRowThreads, 0, st>>>(LU, perm, Bm, X, skip, B);
+                });
+            });
+        });
+        rc = after_launch();
+    });
+    return rc;
+}
+
+}  // namespace gmb

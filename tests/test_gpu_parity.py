@@ -382,3 +382,24 @@ def test_no_out_of_bounds_writes(gm, dt, n, soa):
     for name, buf, ne in (("A", bufA, neA), ("b", bufb, neb), ("x", bufx, nex), ("inv", bufo, neo), ("ok", bufok, B),
                           ("perm", bufp, B * n), ("parity", bufpar, B), ("degenerate", bufdg, B)):
         assert intact(buf, ne), f"guard band of {name} was overwritten (n={n}, soa={soa})"
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [3, 5, 6, 9, 12, 16])
+def test_backsolve_single_rhs(gm, port, dt, n, soa):
+    """backsolve_lu / backsolve_plu with ONE right-hand side (n >= 5: the row-distributed kernel; the
+    m = 3 cases in run_all go through the generic path), skip = 0 and skip > 0, both matrix orders."""
+    rng = np.random.default_rng(77 * n + np.dtype(dt).itemsize)
+    B = 300 + n
+    A = rng.standard_normal((B, n * n)).astype(dt)
+    b = rng.standard_normal((B, n)).astype(dt)
+    for rm in (True, False):
+        lu_np, p_np, _, _ = port.decomp_plu(A, n, n, rm)
+        lu, p = up(gm, lu_np, soa), torch.from_numpy(p_np.astype(np.uint8)).cuda()
+        for skip in (0, 1, n - 1):
+            with np.errstate(all="ignore"):
+                check(down(gm.backsolve_lu(lu, up(gm, b, soa), n, 1, skip, rm)), port.backsolve_lu(lu_np, b, n, 1, skip, rm),
+                      f"backsolve_lu n={n} rm={rm} skip={skip} soa={soa}")
+                check(down(gm.backsolve_plu(lu, p, up(gm, b, soa), n, 1, skip, rm)),
+                      port.backsolve_plu(lu_np, p_np, b, n, 1, skip, rm), f"backsolve_plu n={n} rm={rm} skip={skip} soa={soa}")
