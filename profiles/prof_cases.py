@@ -50,6 +50,13 @@ def run(case):
         A, b = grid((B, 256), f32), grid((B, 16), f32)
         x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
+    if case.startswith("inv"):            # inv<f|d><n>: matrix inverse, AoS
+        dt = f32 if case[3] == "f" else f64
+        n = int(case[4:])
+        B = 1 << 20
+        A = grid((B, n * n), dt)
+        out, ok = torch.empty_like(A), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.inv(A, n, out=out, ok_out=ok)
     if case.startswith("chol"):           # chol<f|d><n>: fused Cholesky + solve, SoA, SPD inputs
         dt = f32 if case[4] == "f" else f64
         n = int(case[5:])
