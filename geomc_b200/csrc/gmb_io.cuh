@@ -237,4 +237,53 @@ __device__ __forceinline__ void aos_store_staged(T* __restrict__ base, int64_t s
     __syncwarp();
 }
 
+// ---- warp-cooperative staging of whole systems for the sub-warp / row-distributed kernels ----------
+// A warp that works on NSYS = 32 / G consecutive AoS systems of E elements owns one contiguous,
+// 16-byte aligned range of NSYS * E elements.  Per-lane element loads from it would touch up to 32
+// sectors per instruction (stride E); instead the range is copied with coalesced 128-bit accesses into
+// shared memory, system q at q * (E | 1) elements (odd stride: lanes reading the same element of
+// different systems hit different banks), and the lanes pick their elements there.  The same buffer
+// serves the way back for in-place / matrix outputs.
+template <int E> constexpr int stage_stride() { return E | 1; }
+
+template <typename T, int E, int NSYS>
+__device__ __forceinline__ void warp_stage_in(const T* __restrict__ g, T* sm, int lane) {
+    constexpr int S = stage_stride<E>();
+    constexpr int V = soa_v<T>();
+    constexpr int TOT = NSYS * E;
+    static_assert(TOT % V == 0, "a warp's range must be a whole number of 16-byte chunks");
+    using VT = typename VecOf<T>::type;
+    const VT* gv = reinterpret_cast<const VT*>(g);
+    for (int i = lane; i < TOT / V; i += 32) {
+        T t[V];
+        unpack(ldg_stream(gv + i), t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int idx = i * V + v, q = idx / E;
+            sm[q * S + (idx - q * E)] = t[v];
+        }
+    }
+    __syncwarp();
+}
+
+template <typename T, int E, int NSYS>
+__device__ __forceinline__ void warp_stage_out(T* __restrict__ g, const T* sm, int lane) {
+    constexpr int S = stage_stride<E>();
+    constexpr int V = soa_v<T>();
+    constexpr int TOT = NSYS * E;
+    using VT = typename VecOf<T>::type;
+    VT* gv = reinterpret_cast<VT*>(g);
+    __syncwarp();
+    for (int i = lane; i < TOT / V; i += 32) {
+        T t[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const int idx = i * V + v, q = idx / E;
+            t[v] = sm[q * S + (idx - q * E)];
+        }
+        gv[i] = pack(t);
+    }
+    __syncwarp();
+}
+
 }  // namespace gmb

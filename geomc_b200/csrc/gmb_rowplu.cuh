@@ -220,7 +220,25 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     const bool good = degenerate == 0;
 
     // ---- optional: the packed LU the reference leaves in `a` --------------------------------------
-    if (LU != nullptr && valid) {
+    // AoS: per-lane row stores would write partial sectors at a stride of one system; the warp's 32/G
+    // systems go through a staging buffer instead and leave with coalesced 128-bit stores (gmb_io.cuh)
+    extern __shared__ __align__(16) unsigned char gmb_dyn_smem[];
+    constexpr int NSYS = 32 / G;
+    constexpr int SA = stage_stride<N * N>();
+    const int64_t s_warp0 = ((int64_t)blockIdx.x * kRowThreads + (threadIdx.x & ~31u)) / G;
+    if (!SOA && LU != nullptr && s_warp0 + NSYS <= B) {
+        T* smw = reinterpret_cast<T*>(gmb_dyn_smem) + (threadIdx.x >> 5) * (NSYS * SA);
+        T* smd = smw + ((threadIdx.x & 31) / G) * SA;
+#pragma unroll
+        for (int k = 0; k < RL; ++k) {
+            const int p = k * G + lane_g;
+            if (p < N) {
+#pragma unroll
+                for (int c = 0; c < N; ++c) smd[RM ? N * p + c : N * c + p] = a[k][c];
+            }
+        }
+        warp_stage_out<T, N * N, NSYS>(LU + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
+    } else if (LU != nullptr && valid) {
 #pragma unroll
         for (int k = 0; k < RL; ++k) {
             const int p = k * G + lane_g;
@@ -276,6 +294,12 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     }   // !DECOMP
 }
 
+// dynamic shared memory of the AoS output staging: one buffer of 32/G systems per warp
+template <typename T, int N>
+constexpr size_t row_stage_bytes() {
+    return (size_t)(kRowThreads / 32) * (32 / row_group(N, (int)sizeof(T) / 4)) * stage_stride<N * N>() * sizeof(T);
+}
+
 template <typename T>
 int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout, int rm,
                       cudaStream_t st) {
@@ -289,8 +313,14 @@ int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* 
         }
         dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
             dispatch_bool(rm != 0, [&](auto RM) {
-                k_row_solve<T, N.value, SOA.value, RM.value, false><<<grid, kRowThreads, 0, st>>>(A, Bm, X, LU, ok, nullptr,
-                                                                                                  nullptr, nullptr, skip, B);
+                auto kern = k_row_solve<T, N.value, SOA.value, RM.value, false>;
+                const size_t smem = (SOA.value || LU == nullptr) ? 0 : row_stage_bytes<T, N.value>();
+                if (smem > 0) {   // static + dynamic may exceed the 48 KB default
+                    static bool raised = false;   // per instantiation
+                    if (!raised) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    raised = true;
+                }
+                kern<<<grid, kRowThreads, smem, st>>>(A, Bm, X, LU, ok, nullptr, nullptr, nullptr, skip, B);
             });
         });
         rc = after_launch();
@@ -311,8 +341,14 @@ int rowplu_decomp_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, u
         }
         dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
             dispatch_bool(rm != 0, [&](auto RM) {
-                k_row_solve<T, N.value, SOA.value, RM.value, true><<<grid, kRowThreads, 0, st>>>(A, nullptr, nullptr, A, nullptr,
-                                                                                                 perm, parity, degen, 0, B);
+                auto kern = k_row_solve<T, N.value, SOA.value, RM.value, true>;
+                const size_t smem = SOA.value ? 0 : row_stage_bytes<T, N.value>();
+                if (smem > 0) {   // static + dynamic may exceed the 48 KB default
+                    static bool raised = false;   // per instantiation
+                    if (!raised) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    raised = true;
+                }
+                kern<<<grid, kRowThreads, smem, st>>>(A, nullptr, nullptr, A, nullptr, perm, parity, degen, 0, B);
             });
         });
         rc = after_launch();

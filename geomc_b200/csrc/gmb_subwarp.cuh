@@ -47,6 +47,12 @@ constexpr bool sub_any_rider(int n, int xc, int g, int j) {
         if (l * lc + j >= n && l * lc + j < n + xc) return true;
     return false;
 }
+// which directions of an AoS batch go through the warp's staging buffer (see k_sub_plu)
+template <typename T>
+constexpr bool sub_stage_in(int n, int mode, bool soa) {
+    return !soa && sizeof(T) == 4 && mode != MODE_INV && (n == 8 || n == 9);
+}
+constexpr bool sub_stage_out(int mode, bool soa) { return !soa && mode != MODE_SOLVE; }
 constexpr int sub_group(int n, int xc, int words) {
     for (int g = 1; g <= 16; g *= 2)
         if (n * sub_lc(n, xc, g) * words <= kRegBudgetWords) return g;
@@ -99,6 +105,20 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     const int64_t baseX = BatchAddr<T, SOA>::base(s, N * (XC > 0 ? XC : 1));
     const T* Ap = A + baseA + (int64_t)c0 * (A_RM ? ST : N * ST);          // this lane's first column of A
 
+    // AoS batches: the warp's NSYS systems are staged through shared memory (gmb_io.cuh, warp_stage_in)
+    extern __shared__ __align__(16) unsigned char gmb_dyn_smem[];
+    constexpr int NSYS = 32 / G;
+    constexpr int SA = stage_stride<N * N>();
+    T* smw = reinterpret_cast<T*>(gmb_dyn_smem) + (threadIdx.x >> 5) * (NSYS * SA);
+    const int64_t s_warp0 = ((int64_t)blockIdx.x * kSubThreads + (threadIdx.x & ~31u)) / G;
+    // Measured (profiles/r1e_*): per-lane strided LOADS go through L1 and every fetched line is consumed,
+    // so staging them only pays where the record stride is a power of two (f32 N=8) or nearly so;
+    // per-lane strided STORES write partial sectors, so matrix outputs are always staged.
+    constexpr bool STAGE_IN = sub_stage_in<T>(N, MODE, SOA), STAGE_OUT = sub_stage_out(MODE, SOA);
+    const bool stage = (STAGE_IN || STAGE_OUT) && (s_warp0 + NSYS <= B);   // warp-uniform
+    const T* sms = smw + ((threadIdx.x & 31) / G) * SA + (A_RM ? c0 : N * c0);   // this lane's system, first local column
+    if (STAGE_IN && stage) warp_stage_in<T, N * N, NSYS>(A + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
+
     // ---- load the local block -------------------------------------------------------------
     T a[N][LC];
 #pragma unroll
@@ -108,7 +128,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
             const int c = c0 + j;
             T v = (T)0;
             if (c < N) {
-                v = Ap[(A_RM ? N * r + j : N * j + r) * ST];
+                v = (STAGE_IN && stage) ? sms[A_RM ? N * r + j : N * j + r] : Ap[(A_RM ? N * r + j : N * j + r) * ST];
             } else if (c < NC) {
                 if (MODE == MODE_SOLVE) v = Bm[baseX + (int64_t)(X_RM ? XC * r + (c - N) : N * (c - N) + r) * ST];
                 if (MODE == MODE_INV) v = (r == c - N) ? (T)1 : (T)0;     // identity; rows exchanged below
@@ -191,8 +211,18 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
 
     // ---- outputs that need no backward sweep ------------------------------------------------
     if (MODE == MODE_DECOMP || (MODE == MODE_SOLVE && LU != nullptr)) {
-        T* dst = ((MODE == MODE_DECOMP) ? const_cast<T*>(A) : LU) + baseA + (int64_t)c0 * (A_RM ? ST : N * ST);
-        if (valid) {
+        T* dstb = (MODE == MODE_DECOMP) ? const_cast<T*>(A) : LU;
+        T* dst = dstb + baseA + (int64_t)c0 * (A_RM ? ST : N * ST);
+        if (STAGE_OUT && stage) {
+            __syncwarp();                                              // every lane is done reading the staged input
+            T* smd = smw + ((threadIdx.x & 31) / G) * SA + (A_RM ? c0 : N * c0);
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < LC; ++j)
+                    if (c0 + j < N) smd[A_RM ? N * r + j : N * j + r] = a[r][j];
+            warp_stage_out<T, N * N, NSYS>(dstb + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
+        } else if (valid) {
 #pragma unroll
             for (int r = 0; r < N; ++r)
 #pragma unroll
@@ -248,6 +278,25 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     }
 
     // ---- store riders -----------------------------------------------------------------------
+    // inverse, AoS: when every system of the warp is regular the result goes back through the staging
+    // buffer (coalesced); a warp containing a singular system stores per lane so that the singular
+    // system's destination stays untouched
+    bool inv_staged = false;
+    if (MODE == MODE_INV && STAGE_OUT && stage) {
+        inv_staged = __all_sync(0xffffffffu, good);
+        if (inv_staged) {
+            __syncwarp();
+            T* smd = smw + ((threadIdx.x & 31) / G) * SA;
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < LC; ++j) {
+                    const int c = c0 + j;
+                    if (c >= N && c < NC) smd[N * r + (c - N)] = a[r][j];
+                }
+            warp_stage_out<T, N * N, NSYS>(X + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
+        }
+    }
     if (valid) {
         if (MODE == MODE_SOLVE) {
 #pragma unroll
@@ -261,7 +310,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
                     }
                 }
         }
-        if (MODE == MODE_INV && good) {                                  // out untouched on failure
+        if (MODE == MODE_INV && good && !(stage && inv_staged)) {        // out untouched on failure
 #pragma unroll
             for (int r = 0; r < N; ++r)
 #pragma unroll
@@ -287,8 +336,19 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
             // riders: linear_solve uses the matrix' own layout flag; invNxN always writes row-major
             constexpr bool XRM = (MODE == MODE_INV) ? true : ARM.value;
             (void)x_rm;
-            k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM><<<grid, kSubThreads, 0, st>>>(A, Bm, X, LU, ok, perm, parity,
-                                                                                           degen, skip, B);
+            auto kern = k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM>;
+            // AoS: one staging buffer of 32/G systems per warp (dynamic shared memory)
+            const size_t smem = !(sub_stage_in<T>(N, MODE, SOA.value) || sub_stage_out(MODE, SOA.value))
+                                    ? 0
+                                    : (size_t)(kSubThreads / 32) * (32 / G) * stage_stride<N * N>() * sizeof(T);
+            if (smem > 48 * 1024) {
+                static bool raised = false;       // per instantiation
+                if (!raised) {
+                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    raised = true;
+                }
+            }
+            kern<<<grid, kSubThreads, smem, st>>>(A, Bm, X, LU, ok, perm, parity, degen, skip, B);
         });
     });
     return after_launch();

@@ -1,5 +1,5 @@
 """Sweep every fast-path kernel family over n = 2..16, float and double (AoS resident in HBM), and print
-systems/s and the fraction of the measured HBM peak.   python profiles/sweep.py > gpurun_out/sweep.md
+systems/s and the fraction of the measured HBM peak.   python profiles/sweep.py [nmin nmax] > gpurun_out/sweep.md
 
 Algorithmic bytes per system: solve  E*n*n + 2*E*n (+1);  decomp (in place) 2*E*n*n + n + 2;
 inverse 2*E*n*n (+1);  cholesky+solve E*n*(n+1)/2 (lower triangle) + 2*E*n (+1).   E = sizeof(T).
@@ -35,7 +35,8 @@ def timeit(fn, reps=3):
 
 print("| n | type | solve sys/s (of peak) | decomp_plu | inv | cholesky+solve |")
 print("|---|---|---|---|---|---|")
-for n in range(2, 17):
+NMIN, NMAX = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2, 16)
+for n in range(NMIN, NMAX + 1):
     for dt, name, E in ((torch.float32, "f32", 4), (torch.float64, "f64", 8)):
         B = 1 << (22 if n <= 4 else 20 if n <= 10 else 19)
         A, b = grid((B, n * n), dt), grid((B, n), dt)
