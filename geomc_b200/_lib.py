@@ -42,6 +42,9 @@ _TYPED = {
     "gmb_solve_residual": [_i, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "gmb_orthogonal": [_i, _i64, _vp, _vp, _i, _vp],
     "gmb_nullspace": [_i, _i, _i64, _vp, _vp, _vp, _i, _vp],
+    "gmb_simplex_contains": [_i, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp],
+    "gmb_trace_simplex": [_i, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp],
+    "gmb_simplex_intersect": [_i, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _vp],
     "gmb_host_plu_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _i],
     "gmb_host_inv": [_i, _i64, _vp, _vp, _vp, _i, _i, _i],
     "gmb_host_cholesky_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i],

@@ -40,6 +40,9 @@ template <typename T> int transpose_batch(bool, int, int64_t, const T*, T*, cuda
 int checksum_bytes(const void*, int64_t, int64_t, uint64_t*, cudaStream_t);
 template <typename T> int small_orthogonal(int, int64_t, const T*, T*, int, cudaStream_t);
 template <typename T> int generic_orthogonal(int, int64_t, const T*, T*, int, cudaStream_t);
+template <typename T> int simplex_contains(int, int64_t, const T*, int64_t, const uint8_t*, const T*, uint8_t*, int, cudaStream_t);
+template <typename T> int trace_simplex(int, int64_t, const T*, int64_t, const T*, const T*, int64_t, uint8_t*, T*, T*, int, cudaStream_t);
+template <typename T> int simplex_intersect(int, int64_t, const T*, int64_t, const uint8_t*, const T*, const T*, int64_t, T*, int, cudaStream_t);
 template <typename T> int generic_nullspace(int, int, int64_t, const T*, T*, uint8_t*, int, cudaStream_t);
 
 // Which fused-solve kernel serves (T, n)?  Measured on B200 (2^20 systems, AoS, CUDA events;
@@ -213,6 +216,48 @@ int orthogonal(int n, int64_t B, const T* V, T* out, int layout, void* stream) {
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && n <= 4) return small_orthogonal<T>(n, B, V, out, layout, as_stream(stream));
     return generic_orthogonal<T>(n, B, V, out, layout, as_stream(stream));
+}
+
+// ---- (f)2: simplex queries.  dim = 2..7; strides are in elements, 0 = packed; AoS only (SoA tiles are packed)
+template <typename T>
+int simplex_contains_api(int dim, int64_t B, const T* verts, int64_t vstride, const uint8_t* nverts, const T* p, uint8_t* inside,
+                         int layout, void* stream) {
+    const int64_t E = (int64_t)(dim + 1) * dim;
+    if (B < 0 || dim < 2 || bad_layout(layout) || (vstride != 0 && vstride < E) ||
+        (B > 0 && (verts == nullptr || p == nullptr || inside == nullptr)))
+        return GMB_ERR_INVALID_ARG;
+    if (dim > 7) return GMB_ERR_UNSUPPORTED;
+    if (layout == GMB_LAYOUT_SOA && (vstride != 0 || !all_aligned16(verts, p))) return GMB_ERR_INVALID_ARG;
+    return simplex_contains<T>(dim, B, verts, vstride ? vstride : E, nverts, p, inside, layout, as_stream(stream));
+}
+
+template <typename T>
+int trace_simplex_api(int dim, int64_t B, const T* verts, int64_t vstride, const T* origin, const T* dir, int64_t rstride,
+                      uint8_t* hit, T* s_out, T* uv, int layout, void* stream) {
+    const int64_t E = (int64_t)dim * dim;
+    if (B < 0 || dim < 2 || bad_layout(layout) || (vstride != 0 && vstride < E) || (rstride != 0 && rstride < dim) ||
+        (B > 0 && (verts == nullptr || origin == nullptr || dir == nullptr || hit == nullptr || s_out == nullptr)))
+        return GMB_ERR_INVALID_ARG;
+    if (dim > 7) return GMB_ERR_UNSUPPORTED;
+    if (layout == GMB_LAYOUT_SOA && (vstride != 0 || rstride != 0 || !all_aligned16(verts, origin, dir) ||
+                                     (uv != nullptr && !all_aligned16(uv))))
+        return GMB_ERR_INVALID_ARG;
+    return trace_simplex<T>(dim, B, verts, vstride ? vstride : E, origin, dir, rstride ? rstride : dim, hit, s_out, uv, layout,
+                            as_stream(stream));
+}
+
+template <typename T>
+int simplex_intersect_api(int dim, int64_t B, const T* verts, int64_t vstride, const uint8_t* nverts, const T* origin,
+                          const T* dir, int64_t rstride, T* interval, int layout, void* stream) {
+    const int64_t E = (int64_t)(dim + 1) * dim;
+    if (B < 0 || dim < 2 || bad_layout(layout) || (vstride != 0 && vstride < E) || (rstride != 0 && rstride < dim) ||
+        (B > 0 && (verts == nullptr || origin == nullptr || dir == nullptr || interval == nullptr)))
+        return GMB_ERR_INVALID_ARG;
+    if (dim > 7) return GMB_ERR_UNSUPPORTED;
+    if (layout == GMB_LAYOUT_SOA && (vstride != 0 || rstride != 0 || !all_aligned16(verts, origin, dir, interval)))
+        return GMB_ERR_INVALID_ARG;
+    return simplex_intersect<T>(dim, B, verts, vstride ? vstride : E, nverts, origin, dir, rstride ? rstride : dim, interval,
+                                layout, as_stream(stream));
 }
 
 template <typename T>
@@ -501,6 +546,22 @@ int gmb_stream_synchronize(void* stream) { return (int)cudaStreamSynchronize(as_
     int gmb_nullspace_##SUF(int N, int nb, int64_t B, const T* bases, T* null_basis, uint8_t* ok, int layout,         \
                             void* stream) {                                                                           \
         return nullspace<T>(N, nb, B, bases, null_basis, ok, layout, stream);                                         \
+    }                                                                                                                 \
+    int gmb_simplex_contains_##SUF(int dim, int64_t B, const T* verts, int64_t vert_stride, const uint8_t* nverts,    \
+                                   const T* p, uint8_t* inside, int layout, void* stream) {                           \
+        return simplex_contains_api<T>(dim, B, verts, vert_stride, nverts, p, inside, layout, stream);                \
+    }                                                                                                                 \
+    int gmb_trace_simplex_##SUF(int dim, int64_t B, const T* verts, int64_t vert_stride, const T* origin,             \
+                                const T* direction, int64_t ray_stride, uint8_t* hit, T* s, T* uv, int layout,        \
+                                void* stream) {                                                                       \
+        return trace_simplex_api<T>(dim, B, verts, vert_stride, origin, direction, ray_stride, hit, s, uv, layout,    \
+                                    stream);                                                                          \
+    }                                                                                                                 \
+    int gmb_simplex_intersect_##SUF(int dim, int64_t B, const T* verts, int64_t vert_stride, const uint8_t* nverts,   \
+                                    const T* origin, const T* direction, int64_t ray_stride, T* interval, int layout, \
+                                    void* stream) {                                                                   \
+        return simplex_intersect_api<T>(dim, B, verts, vert_stride, nverts, origin, direction, ray_stride, interval,  \
+                                        layout, stream);                                                              \
     }                                                                                                                 \
     int gmb_solve_residual_##SUF(int n, int64_t B, const T* A, const T* X, const T* Bm, const uint8_t* ok,            \
                                  double* stats4, int layout, int row_major, void* stream) {                           \

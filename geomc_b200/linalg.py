@@ -253,6 +253,45 @@ def nullspace(bases: Batch, N: int, nb: int):
     return null, ok
 
 
+# ---- batched simplex queries (geomc/shape/Simplex.h) ---------------------------------
+def simplex_contains(verts: Batch, p: Batch, dim: int, nverts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Simplex<T,N>::contains (Simplex.h:450): verts (B, (N+1)*N) vertex-major, p (B, N) -> inside uint8[B].
+    nverts (uint8[B], optional) = Simplex::n; simplexes with fewer than N+1 vertices contain nothing."""
+    layout, B, E, dt, dev, _ = _info(verts)
+    assert E == (dim + 1) * dim and _info(p)[2] == dim
+    inside = _u8(B, 1, dev)
+    _lib.call("gmb_simplex_contains", _SUF[dt], dim, B, _ptr(verts), 0, None if nverts is None else nverts.data_ptr(),
+              _ptr(p), inside.data_ptr(), layout, _stream_ptr(dev))
+    return inside
+
+
+def trace_simplex(verts: Batch, origin: Batch, direction: Batch, dim: int, want_uv: bool = True):
+    """trace_simplex<T,N> (Simplex.h:647): verts (B, N*N) = N vertices of N, rays (B, N) each ->
+    (hit uint8[B], s (B,), uv (B, N-1) or None).  s and uv are written only where hit (zero elsewhere);
+    want_uv=False solves with skip = N-1, as the reference does for a null `uv`."""
+    layout, B, E, dt, dev, _ = _info(verts)
+    assert E == dim * dim and _info(origin)[2] == dim and _info(direction)[2] == dim
+    hit = _u8(B, 1, dev)
+    s = torch.zeros(B, dtype=dt, device=dev)
+    uv = None
+    if want_uv:
+        uv = _new_like(verts, dim - 1)
+        (uv.data if isinstance(uv, BatchSoA) else uv).zero_()
+    _lib.call("gmb_trace_simplex", _SUF[dt], dim, B, _ptr(verts), 0, _ptr(origin), _ptr(direction), 0, hit.data_ptr(),
+              s.data_ptr(), _ptr(uv), layout, _stream_ptr(dev))
+    return hit, s, uv
+
+
+def simplex_intersect(verts: Batch, origin: Batch, direction: Batch, dim: int, nverts: Optional[torch.Tensor] = None) -> Batch:
+    """Simplex<T,N>::intersect(Ray) (Simplex.h:251): verts (B, (N+1)*N) -> the Rect<T,1> as (B, 2) = lo, hi."""
+    layout, B, E, dt, dev, _ = _info(verts)
+    assert E == (dim + 1) * dim and _info(origin)[2] == dim and _info(direction)[2] == dim
+    interval = _new_like(verts, 2)
+    _lib.call("gmb_simplex_intersect", _SUF[dt], dim, B, _ptr(verts), 0, None if nverts is None else nverts.data_ptr(),
+              _ptr(origin), _ptr(direction), 0, _ptr(interval), layout, _stream_ptr(dev))
+    return interval
+
+
 def solve_residual(a: Batch, x: Batch, b: Batch, ok: Optional[torch.Tensor], n: int, row_major: bool = True) -> torch.Tensor:
     """Device-side batch statistics: [sum of per-system max|Ax-b|, max, #ok==0, #non-finite] (float64[4])."""
     layout, B, E, dt, dev, _ = _info(a)

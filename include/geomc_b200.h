@@ -159,6 +159,41 @@ int gmb_nullspace_f32(int N, int nb, int64_t B, const float* bases, float* null_
 int gmb_nullspace_f64(int N, int nb, int64_t B, const double* bases, double* null_basis, uint8_t* ok, int layout,
                       void* stream);
 
+/* ---- "next" row (f)2: batched simplex queries, the in-library consumers of linear_solve --------
+ * (shape/Simplex.h).  dim = N = 2..7.  Vertices are vertex-major, as in Simplex::pts (Simplex.h:92).
+ * AoS strides are in elements, 0 = packed: `vert_stride` between consecutive simplexes (an array of
+ * geom::Simplex<T,N> objects passes sizeof(Simplex<T,N>)/sizeof(T)), `ray_stride` between consecutive
+ * origins / directions (an array of geom::Ray<T,N> passes 2N with direction = origin + N).  With
+ * GMB_LAYOUT_SOA every array is a packed interleaved container and the strides must be 0.
+ * nverts (nullable, one byte per simplex) = Simplex::n; NULL means every simplex has N + 1 vertices.
+ *
+ * gmb_simplex_contains: Simplex<T,N>::contains(p), Simplex.h:450-475.  verts = N+1 vertices of N;
+ *   inside[s] = 1 iff p_s is on or inside simplex s (0 for n < N+1 and for degenerate simplexes).
+ * gmb_trace_simplex: trace_simplex<T,N>(verts, ray, uv, s), Simplex.h:647-675.  verts = N vertices
+ *   of N (a triangle in 3D).  hit[s]; s[s] and uv[s] (N-1 surface coordinates, nullable) are written
+ *   only where hit.  As in the reference, uv == NULL solves with skip = N-1.  The reference stores
+ *   x[N] -- one past the end of its Vec<T,N>, undefined -- as the ray parameter (:675); this library
+ *   stores the coefficient it means, x[N-1].
+ * gmb_simplex_intersect: Simplex<T,N>::intersect(Ray), Simplex.h:251-296.  verts = N+1 vertices of N;
+ *   interval[s] = {lo, hi} of the Rect<T,1> the reference returns: the parameter range inside a full
+ *   simplex; (s, s) for n == N; (inf, -inf) = Rect::empty or (max, lowest) = Rect() when there is no hit. */
+int gmb_simplex_contains_f32(int dim, int64_t B, const float* verts, int64_t vert_stride, const uint8_t* nverts,
+                             const float* p, uint8_t* inside, int layout, void* stream);
+int gmb_simplex_contains_f64(int dim, int64_t B, const double* verts, int64_t vert_stride, const uint8_t* nverts,
+                             const double* p, uint8_t* inside, int layout, void* stream);
+int gmb_trace_simplex_f32(int dim, int64_t B, const float* verts, int64_t vert_stride, const float* origin,
+                          const float* direction, int64_t ray_stride, uint8_t* hit, float* s, float* uv, int layout,
+                          void* stream);
+int gmb_trace_simplex_f64(int dim, int64_t B, const double* verts, int64_t vert_stride, const double* origin,
+                          const double* direction, int64_t ray_stride, uint8_t* hit, double* s, double* uv, int layout,
+                          void* stream);
+int gmb_simplex_intersect_f32(int dim, int64_t B, const float* verts, int64_t vert_stride, const uint8_t* nverts,
+                              const float* origin, const float* direction, int64_t ray_stride, float* interval,
+                              int layout, void* stream);
+int gmb_simplex_intersect_f64(int dim, int64_t B, const double* verts, int64_t vert_stride, const uint8_t* nverts,
+                              const double* origin, const double* direction, int64_t ray_stride, double* interval,
+                              int layout, void* stream);
+
 /* ---- batch statistics (what the reference's tests assert, reduced on the device) ------------
  * stats[0] = sum over systems of max_i |(A x - b)_i| (only systems with ok != 0),
  * stats[1] = max of the same, stats[2] = number of systems with ok == 0,

@@ -222,6 +222,45 @@ class CpuLinalg:
         assert rc == 0
         return null, ok
 
+    # ---- simplex queries (shape/Simplex.h) ------------------------------------------
+    def simplex_contains(self, verts, p, N, nverts=None):
+        """Simplex<T,N>::contains (Simplex.h:450): verts (B, (N+1)*N), p (B, N) -> inside[B]."""
+        verts, p = self._prep(verts), self._prep(p)
+        B = verts.shape[0]
+        assert verts.shape[1] == (N + 1) * N and p.shape == (B, N)
+        nv = None if nverts is None else np.ascontiguousarray(nverts, np.uint8)
+        inside = np.zeros(B, np.uint8)
+        rc = self._fn("simplex_contains", verts.dtype)(C.c_int(N), C.c_int64(B), _ptr(verts), _ptr(nv), _ptr(p), _ptr(inside))
+        assert rc == 0
+        return inside
+
+    def trace_simplex(self, verts, origin, direction, N, want_uv=True):
+        """trace_simplex<T,N> (Simplex.h:647): verts (B, N*N), rays (B, N) -> (hit[B], s[B], uv (B, N-1)).
+        s and uv are only written where hit; the reference library's s is x[N] (out of bounds, :669) and is
+        not comparable -- the port returns x[N-1]."""
+        verts, origin, direction = self._prep(verts), self._prep(origin), self._prep(direction)
+        B = verts.shape[0]
+        assert verts.shape[1] == N * N and origin.shape == (B, N) and direction.shape == (B, N)
+        hit = np.zeros(B, np.uint8)
+        s = np.zeros(B, verts.dtype)
+        uv = np.zeros((B, N - 1), verts.dtype)
+        rc = self._fn("trace_simplex", verts.dtype)(C.c_int(N), C.c_int64(B), _ptr(verts), _ptr(origin), _ptr(direction),
+                                                    C.c_int(1 if want_uv else 0), _ptr(hit), _ptr(s), _ptr(uv))
+        assert rc == 0
+        return hit, s, uv
+
+    def simplex_intersect(self, verts, origin, direction, N, nverts=None):
+        """Simplex<T,N>::intersect(Ray) (Simplex.h:251): verts (B, (N+1)*N) -> Rect<T,1> as (B, 2) = lo, hi."""
+        verts, origin, direction = self._prep(verts), self._prep(origin), self._prep(direction)
+        B = verts.shape[0]
+        assert verts.shape[1] == (N + 1) * N and origin.shape == (B, N) and direction.shape == (B, N)
+        nv = None if nverts is None else np.ascontiguousarray(nverts, np.uint8)
+        lohi = np.zeros((B, 2), verts.dtype)
+        rc = self._fn("simplex_intersect", verts.dtype)(C.c_int(N), C.c_int64(B), _ptr(verts), _ptr(nv), _ptr(origin),
+                                                        _ptr(direction), _ptr(lohi))
+        assert rc == 0
+        return lohi
+
     # in-place, zero-copy variants used only by bench.py's CPU baseline timing loop
     def linear_solve_inplace(self, a, x, ok, n, m=1, skip=0, row_major=True):
         rc = self._fn("linear_solve", a.dtype)(C.c_int(n), C.c_int(m), C.c_int64(a.shape[0]), _ptr(a), _ptr(x),

@@ -21,6 +21,9 @@
 //   ref_inv_raw_*         geom::inv2x2/inv3x3/inv4x4 / invNxN(T*,T*,n)   MatrixInv.h:49/75/117/186
 //   ref_orthogonal_*      geom::orthogonal<T,N>(const Vec<T,N>[N-1])    Orthogonal.h:73 (+ N=2,3 overloads :101,:107)
 //   ref_nullspace_*       geom::nullspace<T,N>(bases, n, null_basis)    Orthogonal.h:136
+//   ref_simplex_contains_*   geom::Simplex<T,N>::contains(p)             shape/Simplex.h:450
+//   ref_trace_simplex_*      geom::trace_simplex<T,N>(verts, ray, uv, s) shape/Simplex.h:647
+//   ref_simplex_intersect_*  geom::Simplex<T,N>::intersect(ray)          shape/Simplex.h:251
 //
 // Build: see oracle/Makefile (g++ -std=c++23 -O3 -mavx2 -mfma -ffp-contract=fast
 //        --param=avoid-fma-max-bits=0 -fno-tree-loop-vectorize -fopenmp; the Makefile explains each flag).
@@ -29,6 +32,8 @@
 #include <geomc/linalg/Cholesky.h>
 #include <geomc/linalg/Orthogonal.h>
 #include <geomc/linalg/Vec.h>
+#include <geomc/linalg/Ray.h>
+#include <geomc/shape/Simplex.h>
 
 #include <cstdint>
 #include <cstring>
@@ -205,6 +210,91 @@ void nullspace_batch(int n, int64_t B, const T* bases, T* null_basis, uint8_t* o
     }
 }
 
+template <typename T, index_t N>
+void simplex_contains_batch(int64_t B, const T* verts, const uint8_t* nverts, const T* p, uint8_t* inside) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        geom::Simplex<T, N> sx;
+        std::memcpy(sx.pts[0].begin(), verts + s * (N + 1) * N, sizeof(T) * (N + 1) * N);
+        sx.n = nverts ? nverts[s] : N + 1;
+        geom::Vec<T, N> pt;
+        std::memcpy(pt.begin(), p + s * N, sizeof(T) * N);
+        inside[s] = sx.contains(pt) ? 1 : 0;
+    }
+}
+
+// `s_out` receives what the reference writes: x[N], one past the end of its Vec<T,N> (Simplex.h:669,
+// undefined behaviour) -- callers compare only `hit` and `uv`.
+template <typename T, index_t N>
+void trace_simplex_batch(int64_t B, const T* verts, const T* origin, const T* dir, int want_uv, uint8_t* hit, T* s_out,
+                         T* uv) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        geom::Vec<T, N> vs[N];
+        std::memcpy(vs[0].begin(), verts + s * N * N, sizeof(T) * N * N);
+        geom::Vec<T, N> o, d;
+        std::memcpy(o.begin(), origin + s * N, sizeof(T) * N);
+        std::memcpy(d.begin(), dir + s * N, sizeof(T) * N);
+        geom::Ray<T, N> ray(o, d);
+        geom::Vec<T, N - 1> uvv;
+        T sv = 0;
+        const bool h = geom::trace_simplex<T, N>(vs, ray, want_uv ? &uvv : nullptr, &sv);
+        hit[s] = h ? 1 : 0;
+        if (h) {
+            s_out[s] = sv;
+            if (want_uv) std::memcpy(uv + s * (N - 1), reinterpret_cast<const T*>(&uvv), sizeof(T) * (N - 1));
+        }
+    }
+}
+
+template <typename T, index_t N>
+void simplex_intersect_batch(int64_t B, const T* verts, const uint8_t* nverts, const T* origin, const T* dir, T* lohi) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < B; ++s) {
+        geom::Simplex<T, N> sx;
+        std::memcpy(sx.pts[0].begin(), verts + s * (N + 1) * N, sizeof(T) * (N + 1) * N);
+        sx.n = nverts ? nverts[s] : N + 1;
+        geom::Vec<T, N> o, d;
+        std::memcpy(o.begin(), origin + s * N, sizeof(T) * N);
+        std::memcpy(d.begin(), dir + s * N, sizeof(T) * N);
+        geom::Rect<T, 1> r = sx.intersect(geom::Ray<T, N>(o, d));
+        lohi[2 * s] = r.lo;
+        lohi[2 * s + 1] = r.hi;
+    }
+}
+
+#define FOR_N_2_7(X) X(2) X(3) X(4) X(5) X(6) X(7)
+
+template <typename T>
+int simplex_contains_dispatch(int n, int64_t B, const T* verts, const uint8_t* nverts, const T* p, uint8_t* inside) {
+    switch (n) {
+#define CASE(N) case N: simplex_contains_batch<T, N>(B, verts, nverts, p, inside); return 0;
+        FOR_N_2_7(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+template <typename T>
+int trace_simplex_dispatch(int n, int64_t B, const T* verts, const T* origin, const T* dir, int want_uv, uint8_t* hit,
+                           T* s_out, T* uv) {
+    switch (n) {
+#define CASE(N) case N: trace_simplex_batch<T, N>(B, verts, origin, dir, want_uv, hit, s_out, uv); return 0;
+        FOR_N_2_7(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+template <typename T>
+int simplex_intersect_dispatch(int n, int64_t B, const T* verts, const uint8_t* nverts, const T* origin, const T* dir,
+                               T* lohi) {
+    switch (n) {
+#define CASE(N) case N: simplex_intersect_batch<T, N>(B, verts, nverts, origin, dir, lohi); return 0;
+        FOR_N_2_7(CASE)
+#undef CASE
+        default: return -1;
+    }
+}
+
 #define FOR_N_2_16(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16)
 
 template <typename T>
@@ -314,6 +404,18 @@ int inv_dispatch(int n, int64_t B, const T* src, T* dst, uint8_t* ok, int srm, i
     }                                                                                                             \
     extern "C" int ref_nullspace_##SUF(int N_, int n, int64_t B, const T* bases, T* null_basis, uint8_t* ok) {    \
         return nullspace_dispatch<T>(N_, n, B, bases, null_basis, ok);                                            \
+    }                                                                                                             \
+    extern "C" int ref_simplex_contains_##SUF(int n, int64_t B, const T* verts, const uint8_t* nverts, const T* p,   \
+                                              uint8_t* inside) {                                                  \
+        return simplex_contains_dispatch<T>(n, B, verts, nverts, p, inside);                                      \
+    }                                                                                                             \
+    extern "C" int ref_trace_simplex_##SUF(int n, int64_t B, const T* verts, const T* origin, const T* dir,          \
+                                           int want_uv, uint8_t* hit, T* s_out, T* uv) {                          \
+        return trace_simplex_dispatch<T>(n, B, verts, origin, dir, want_uv, hit, s_out, uv);                      \
+    }                                                                                                             \
+    extern "C" int ref_simplex_intersect_##SUF(int n, int64_t B, const T* verts, const uint8_t* nverts,              \
+                                               const T* origin, const T* dir, T* lohi) {                          \
+        return simplex_intersect_dispatch<T>(n, B, verts, nverts, origin, dir, lohi);                             \
     }                                                                                                             \
     extern "C" int ref_inv_raw_##SUF(int n, int64_t B, T* src_destroyed, T* dst, uint8_t* ok) {                   \
         inv_raw_batch<T>(n, B, src_destroyed, dst, ok);                                                           \
