@@ -71,6 +71,9 @@ template <typename T> struct Abi;
         static constexpr auto host_plu_decomp = gmb_host_plu_decomp_##S;                                    \
         static constexpr auto orthogonal = gmb_orthogonal_##S;                                              \
         static constexpr auto nullspace = gmb_nullspace_##S;                                                \
+        static constexpr auto simplex_contains = gmb_simplex_contains_##S;                                  \
+        static constexpr auto trace_simplex = gmb_trace_simplex_##S;                                        \
+        static constexpr auto simplex_intersect = gmb_simplex_intersect_##S;                                \
     };
 GMB_ABI(float, f32)
 GMB_ABI(double, f64)
@@ -370,6 +373,123 @@ index_t nullspace(const V* bases, index_t n, V* null_basis, index_t N, index_t B
     check(gmb_stream_synchronize(nullptr), "sync");
     if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
     return detail::count_false(okb.data(), B);
+}
+
+// ---- row (f)2 of the scope table: batched simplex queries (shape/Simplex.h) ------------------------
+// Object forms, duck-typed on the members the reference's types have: Simplex::pts / ::n (Simplex.h:92-94),
+// Ray::origin / ::direction (Ray.h:24-26), Rect<T,1>::lo / ::hi.  Object arrays are uploaded as they are
+// and addressed through the strides of the C ABI; nothing is repacked on the host.
+namespace detail {
+template <typename S>
+using simplex_elem = vec_elem<decltype(std::declval<S&>().pts[0])>;
+
+template <typename T, typename Obj, typename Member>
+inline std::size_t member_offset(const Obj* o, const Member* m, const char* what) {
+    const std::size_t off = (std::size_t)(reinterpret_cast<const char*>(m) - reinterpret_cast<const char*>(o));
+    if (off % sizeof(T) != 0 || sizeof(Obj) % sizeof(T) != 0) throw Error(GMB_ERR_INVALID_ARG, what);
+    return off / sizeof(T);
+}
+
+// uploads `count` objects; returns the device array (as elements of T)
+template <typename T, typename Obj>
+inline DeviceArray<T> upload_objects(const Obj* objs, index_t count) {
+    DeviceArray<T> d((std::size_t)count * sizeof(Obj) / sizeof(T) + 1);
+    if (count > 0) d.upload(reinterpret_cast<const T*>(objs), (std::size_t)count * sizeof(Obj) / sizeof(T));
+    return d;
+}
+
+template <typename S>
+inline DeviceArray<std::uint8_t> upload_vertex_counts(const S* simplexes, index_t B) {
+    std::vector<std::uint8_t> nv((std::size_t)B);
+    for (index_t i = 0; i < B; ++i) nv[(std::size_t)i] = (std::uint8_t)simplexes[i].n;
+    DeviceArray<std::uint8_t> d((std::size_t)B + 1);
+    if (B > 0) d.upload(nv.data(), (std::size_t)B);
+    return d;
+}
+}  // namespace detail
+
+// for (s < B) inside[s] = simplexes[s].contains(p[s]);       -> number of points inside      (Simplex.h:450)
+template <typename S, typename V>
+index_t contains(const S* simplexes, const V* p, index_t B, bool* inside, int device = 0) {
+    using T = detail::simplex_elem<S>;
+    constexpr int N = (int)(sizeof(V) / sizeof(T));
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return 0;
+    const std::size_t voff = detail::member_offset<T>(simplexes, simplexes[0].pts[0].begin(), "Simplex layout");
+    DeviceArray<T> dS = detail::upload_objects<T>(simplexes, B), dP = detail::upload_objects<T>(p, B);
+    DeviceArray<std::uint8_t> dn = detail::upload_vertex_counts(simplexes, B), din((std::size_t)B);
+    check(Abi<T>::simplex_contains(N, B, dS.get() + voff, (std::int64_t)(sizeof(S) / sizeof(T)), dn.get(), dP.get(), din.get(),
+                                   GMB_LAYOUT_AOS, nullptr), "simplex_contains");
+    std::vector<std::uint8_t> inb((std::size_t)B);
+    din.download(inb.data(), (std::size_t)B);
+    check(gmb_stream_synchronize(nullptr), "sync");
+    index_t n_in = 0;
+    for (index_t i = 0; i < B; ++i) {
+        if (inside) inside[i] = inb[(std::size_t)i] != 0;
+        n_in += inb[(std::size_t)i] != 0;
+    }
+    return n_in;
+}
+
+// for (s < B) hit[s] = geom::trace_simplex<T,N>(verts + s*N, rays[s], uv ? &uv[s] : nullptr, &t[s]);   (Simplex.h:647)
+// verts: B groups of N packed Vec<T,N>; t[s] and uv[s] are written only where hit.  -> number of hits.
+// t[s] is the coefficient of -direction, x[N-1]; the reference itself stores x[N] (out of bounds, :675).
+template <typename V, typename R, typename VU, typename T>
+index_t trace_simplex(const V* verts, const R* rays, VU* uv, T* t, index_t B, bool* hit, int device = 0) {
+    static_assert(std::is_same<T, detail::vec_elem<V>>::value, "ray parameter type must be the vertices' element type");
+    constexpr int N = (int)(sizeof(V) / sizeof(T));
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return 0;
+    const std::size_t ooff = detail::member_offset<T>(rays, rays[0].origin.begin(), "Ray layout");
+    const std::size_t doff = detail::member_offset<T>(rays, rays[0].direction.begin(), "Ray layout");
+    DeviceArray<T> dV = detail::upload_objects<T>(verts, B * N), dR = detail::upload_objects<T>(rays, B);
+    DeviceArray<T> dt((std::size_t)B), duv(uv ? (std::size_t)B * (N - 1) : 1);
+    DeviceArray<std::uint8_t> dh((std::size_t)B);
+    check(Abi<T>::trace_simplex(N, B, dV.get(), 0, dR.get() + ooff, dR.get() + doff, (std::int64_t)(sizeof(R) / sizeof(T)), dh.get(),
+                                dt.get(), uv ? duv.get() : nullptr, GMB_LAYOUT_AOS, nullptr), "trace_simplex");
+    std::vector<std::uint8_t> hb((std::size_t)B);
+    std::vector<T> tb((std::size_t)B), uvb(uv ? (std::size_t)B * (N - 1) : 0);
+    dh.download(hb.data(), (std::size_t)B);
+    dt.download(tb.data(), (std::size_t)B);
+    if (uv) duv.download(uvb.data(), uvb.size());
+    check(gmb_stream_synchronize(nullptr), "sync");
+    index_t hits = 0;
+    for (index_t i = 0; i < B; ++i) {
+        const bool h = hb[(std::size_t)i] != 0;
+        if (hit) hit[i] = h;
+        hits += h;
+        if (!h) continue;
+        t[i] = tb[(std::size_t)i];
+        if (uv) std::memcpy(reinterpret_cast<T*>(&uv[i]), uvb.data() + (std::size_t)i * (N - 1), sizeof(T) * (N - 1));
+    }
+    return hits;
+}
+
+// for (s < B) intervals[s] = simplexes[s].intersect(rays[s]);   -> number of non-empty intervals   (Simplex.h:251)
+template <typename S, typename R, typename I>
+index_t intersect(const S* simplexes, const R* rays, index_t B, I* intervals, int device = 0) {
+    using T = detail::simplex_elem<S>;
+    constexpr int N = (int)(sizeof(R) / sizeof(T) / 2);
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return 0;
+    const std::size_t voff = detail::member_offset<T>(simplexes, simplexes[0].pts[0].begin(), "Simplex layout");
+    const std::size_t ooff = detail::member_offset<T>(rays, rays[0].origin.begin(), "Ray layout");
+    const std::size_t doff = detail::member_offset<T>(rays, rays[0].direction.begin(), "Ray layout");
+    DeviceArray<T> dS = detail::upload_objects<T>(simplexes, B), dR = detail::upload_objects<T>(rays, B), dI((std::size_t)B * 2);
+    DeviceArray<std::uint8_t> dn = detail::upload_vertex_counts(simplexes, B);
+    check(Abi<T>::simplex_intersect(N, B, dS.get() + voff, (std::int64_t)(sizeof(S) / sizeof(T)), dn.get(), dR.get() + ooff,
+                                    dR.get() + doff, (std::int64_t)(sizeof(R) / sizeof(T)), dI.get(), GMB_LAYOUT_AOS, nullptr),
+          "simplex_intersect");
+    std::vector<T> ib((std::size_t)B * 2);
+    dI.download(ib.data(), ib.size());
+    check(gmb_stream_synchronize(nullptr), "sync");
+    index_t nonempty = 0;
+    for (index_t i = 0; i < B; ++i) {
+        intervals[i].lo = ib[2 * (std::size_t)i];
+        intervals[i].hi = ib[2 * (std::size_t)i + 1];
+        nonempty += ib[2 * (std::size_t)i] <= ib[2 * (std::size_t)i + 1];
+    }
+    return nonempty;
 }
 
 }  // namespace batch

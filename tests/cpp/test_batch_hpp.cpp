@@ -9,6 +9,8 @@
 #ifdef WITH_GEOMC
 #include <geomc/linalg/Matrix.h>
 #include <geomc/linalg/Vec.h>
+#include <geomc/linalg/Ray.h>
+#include <geomc/shape/Simplex.h>
 #endif
 #include <cmath>
 #include <cstdio>
@@ -43,6 +45,21 @@ struct Vec {
     const T* begin() const { return v; }
     T& operator[](long i) { return v[i]; }
     T operator[](long i) const { return v[i]; }
+};
+template <typename T, long N>
+struct Ray {
+    Vec<T, N> origin, direction;
+};
+template <typename T, long N>
+struct Simplex {
+    Vec<T, N> pts[N + 1];
+    long n;
+};
+template <typename T, long N>
+struct Rect;
+template <typename T>
+struct Rect<T, 1> {
+    T lo, hi;
 };
 }  // namespace geom
 #endif
@@ -207,6 +224,62 @@ static void test_orthogonal_nullspace(long B) {
     }
 }
 
+// Simplex::contains / Simplex::intersect / trace_simplex on arrays of the reference's own objects
+template <typename T, long N>
+static void test_simplex_queries(long B) {
+    std::mt19937_64 rng(77 + N);
+    std::normal_distribution<double> g(0, 1);
+    std::uniform_real_distribution<double> u(0.05, 1);
+    std::vector<geom::Simplex<T, N>> sx(B);
+    std::vector<geom::Vec<T, N>> pin(B), pout(B), tri(B * N), target(B);
+    std::vector<geom::Ray<T, N>> rays(B), trays(B);
+    for (long s = 0; s < B; ++s) {
+        sx[s].n = N + 1;
+        double w[N + 1], wsum = 0;
+        for (long k = 0; k <= N; ++k) { w[k] = u(rng); wsum += w[k]; }
+        for (long k = 0; k <= N; ++k) for (long i = 0; i < N; ++i) sx[s].pts[k][i] = (T)g(rng);
+        for (long i = 0; i < N; ++i) {
+            double c = 0;
+            for (long k = 0; k <= N; ++k) c += w[k] / wsum * (double)sx[s].pts[k][i];
+            pin[s][i] = (T)c;
+            pout[s][i] = (T)(c + 50);
+            rays[s].origin[i] = (T)(4 * g(rng));
+        }
+        for (long i = 0; i < N; ++i) rays[s].direction[i] = pin[s][i] - rays[s].origin[i];
+        // a facet (N vertices) and a ray aimed at a point on it
+        double wf[N], wfs = 0;
+        for (long k = 0; k < N; ++k) { wf[k] = u(rng); wfs += wf[k]; }
+        for (long k = 0; k < N; ++k) for (long i = 0; i < N; ++i) tri[s * N + k][i] = (T)g(rng);
+        for (long i = 0; i < N; ++i) {
+            double c = 0;
+            for (long k = 0; k < N; ++k) c += wf[k] / wfs * (double)tri[s * N + k][i];
+            target[s][i] = (T)c;
+            trays[s].origin[i] = (T)(4 * g(rng));
+        }
+        for (long i = 0; i < N; ++i) trays[s].direction[i] = target[s][i] - trays[s].origin[i];
+    }
+    sx[5].n = N;                                                   // not a volume: contains nothing (Simplex.h:451)
+    std::vector<char> in(B), out(B), hit(B);
+    long n_in = gb::contains(sx.data(), pin.data(), B, reinterpret_cast<bool*>(in.data()));
+    long n_out = gb::contains(sx.data(), pout.data(), B, reinterpret_cast<bool*>(out.data()));
+    EXPECT(n_in == B - 1 && !in[5], "convex combinations must be inside (%ld of %ld, N=%ld)", n_in, B, N);
+    EXPECT(n_out == 0, "far points must be outside (%ld, N=%ld)", n_out, N);
+    sx[5].n = N + 1;
+    std::vector<geom::Rect<T, 1>> iv(B);
+    long nonempty = gb::intersect(sx.data(), rays.data(), B, iv.data());
+    long covers = 0;
+    const double tol = sizeof(T) == 4 ? 1e-2 : 1e-8;
+    for (long s = 0; s < B; ++s) covers += iv[s].lo <= 1 + tol && iv[s].hi >= 1 - tol;
+    EXPECT(nonempty == B && covers == B, "rays through interior points must cross the simplex around t = 1 (%ld, %ld of %ld, N=%ld)",
+           nonempty, covers, B, N);
+    std::vector<geom::Vec<T, N - 1>> uv(B);
+    std::vector<T> t(B, (T)-1);
+    long hits = gb::trace_simplex(tri.data(), trays.data(), uv.data(), t.data(), B, reinterpret_cast<bool*>(hit.data()));
+    double worst = 0;
+    for (long s = 0; s < B; ++s) worst = std::fmax(worst, std::fabs((double)t[s] - 1));
+    EXPECT(hits == B && worst < tol, "rays aimed at a facet point must hit at t = 1 (%ld of %ld, |t-1| %g, N=%ld)", hits, B, worst, N);
+}
+
 int main() {
     if (gmb_device_count() == 0) {
         // no CPU fallback: the call must fail loudly
@@ -236,6 +309,10 @@ int main() {
     test_orthogonal_nullspace<double, 4>(500);
     test_orthogonal_nullspace<float, 4>(500);
     test_orthogonal_nullspace<double, 7>(300);
+    test_simplex_queries<float, 3>(2000);
+    test_simplex_queries<double, 2>(1000);
+    test_simplex_queries<double, 3>(1000);
+    test_simplex_queries<double, 5>(500);
     std::printf(failures ? "FAILED (%d)\n" : "batch.hpp OK (%d failures)\n", failures);
     return failures ? 1 : 0;
 }
