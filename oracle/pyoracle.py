@@ -261,6 +261,82 @@ class CpuLinalg:
         assert rc == 0
         return lohi
 
+    # ---- mul / mul_acc (Matrix.h:386 / :433, MatrixMult.h:54-80) ----------------------
+    def mul(self, a, b, r, k, c, d_init=None, acc=False, a_rm=True, b_rm=True, d_rm=True):
+        """geom::mul(&d, a, b) / mul_acc: a (B, r*k), b (B, k*c) -> d (B, r*c).  The reference library only
+        instantiates a table of shapes (oracle/ref_driver_xform.cpp); others raise NotImplementedError."""
+        a, b = self._prep(a), self._prep(b)
+        B = a.shape[0]
+        assert a.shape[1] == r * k and b.shape == (B, k * c)
+        d = np.zeros((B, r * c), a.dtype) if d_init is None else self._prep(d_init)
+        rc = self._fn("mul", a.dtype)(C.c_int(r), C.c_int(k), C.c_int(c), C.c_int64(B), _ptr(a), _ptr(b), _ptr(d),
+                                      C.c_int(int(acc)), C.c_int(int(a_rm)), C.c_int(int(b_rm)), C.c_int(int(d_rm)))
+        if rc != 0:
+            raise NotImplementedError(f"mul {r}x{k}x{c} layouts {a_rm, b_rm, d_rm} not instantiated in {self.kind}")
+        return d
+
+    def mul_vec(self, a, v, n, vec_first=False, row_major=True):
+        """SimpleMatrix<T,n,n> * Vec<T,n> (MatrixMult.h:181) or Vec * SimpleMatrix (:239): -> (B, n)."""
+        a, v = self._prep(a), self._prep(v)
+        B = a.shape[0]
+        assert a.shape[1] == n * n and v.shape == (B, n)
+        out = np.zeros((B, n), a.dtype)
+        rc = self._fn("mul_vec", a.dtype)(C.c_int(n), C.c_int(int(vec_first)), C.c_int64(B), _ptr(a), _ptr(v), _ptr(out),
+                                          C.c_int(int(row_major)))
+        assert rc == 0
+        return out
+
+    # ---- SURVEY.md 8(f)3: AffineTransform (linalg/AffineTransform.h); records = mat (N+1)^2 | inv (N+1)^2 ----
+    def xf_from_matrix(self, m, N, row_major=True):
+        """geom::transformation(mat) (AffineTransform.h:862): m (B, N*N) -> (B, 2*(N+1)^2).
+        The port also returns inv()'s success flag, which the reference ignores."""
+        m = self._prep(m)
+        B = m.shape[0]
+        assert m.shape[1] == N * N
+        out = np.zeros((B, 2 * (N + 1) ** 2), m.dtype)
+        if self.kind == "reference":
+            rc = self._fn("xf_from_matrix", m.dtype)(C.c_int(N), C.c_int64(B), _ptr(m), _ptr(out), C.c_int(int(row_major)))
+            assert rc == 0
+            return out, None
+        ok = np.zeros(B, np.uint8)
+        rc = self._fn("xf_from_matrix", m.dtype)(C.c_int(N), C.c_int64(B), _ptr(m), _ptr(out), _ptr(ok), C.c_int(int(row_major)))
+        assert rc == 0
+        return out, ok
+
+    def xf_translation(self, t, N, scale=False):
+        """geom::translation(Vec) (AffineTransform.h:814) / geom::scale(Vec) (:838): t (B, N) -> records."""
+        t = self._prep(t)
+        B = t.shape[0]
+        assert t.shape[1] == N
+        out = np.zeros((B, 2 * (N + 1) ** 2), t.dtype)
+        rc = self._fn("xf_translation", t.dtype)(C.c_int(N), C.c_int64(B), _ptr(t), _ptr(out), C.c_int(int(scale)))
+        assert rc == 0
+        return out
+
+    def xf_compose(self, xf1, xf2, N, inverse=False):
+        """xf1 * xf2 (AffineTransform.h:142) or xf1 / xf2 (:154)."""
+        xf1, xf2 = self._prep(xf1), self._prep(xf2)
+        B = xf1.shape[0]
+        assert xf1.shape == xf2.shape == (B, 2 * (N + 1) ** 2)
+        out = np.zeros_like(xf1)
+        rc = self._fn("xf_compose", xf1.dtype)(C.c_int(N), C.c_int64(B), _ptr(xf1), _ptr(xf2), _ptr(out), C.c_int(int(inverse)))
+        assert rc == 0
+        return out
+
+    XF_MODES = ("apply", "apply_inverse", "apply_direction", "apply_inverse_direction", "apply_normal",
+                "apply_inverse_normal")
+
+    def xf_apply(self, xf, p, N, mode="apply"):
+        """AffineTransform::apply & co. (AffineTransform.h:224-293): xf (B or 1, 2*(N+1)^2), p (B, N) -> (B, N)."""
+        xf, p = self._prep(xf), self._prep(p)
+        B = p.shape[0]
+        assert xf.shape[0] in (1, B) and xf.shape[1] == 2 * (N + 1) ** 2 and p.shape[1] == N
+        out = np.zeros_like(p)
+        rc = self._fn("xf_apply", p.dtype)(C.c_int(N), C.c_int(self.XF_MODES.index(mode)), C.c_int64(B), _ptr(xf),
+                                           C.c_int64(xf.shape[0]), _ptr(p), _ptr(out))
+        assert rc == 0
+        return out
+
     # in-place, zero-copy variants used only by bench.py's CPU baseline timing loop
     def linear_solve_inplace(self, a, x, ok, n, m=1, skip=0, row_major=True):
         rc = self._fn("linear_solve", a.dtype)(C.c_int(n), C.c_int(m), C.c_int64(a.shape[0]), _ptr(a), _ptr(x),
