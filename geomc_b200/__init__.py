@@ -9,13 +9,15 @@ from . import _lib
 from ._lib import LAYOUT_AOS, LAYOUT_SOA, GmbError, lib
 from .linalg import (BatchSoA, apply_permutation, backsolve_lu, backsolve_plu, checksum, cholesky, cholesky_solve,
                      decomp_lup, decomp_plu, host_cholesky_solve, host_decomp_plu, host_inv, host_linear_solve, inv,
-                     linear_solve, linear_solve_vec, nullspace, orthogonal, simplex_contains, simplex_intersect,
-                     solve_residual, trace_simplex)
+                     linear_solve, linear_solve_vec, mul, nullspace, orthogonal, simplex_contains, simplex_intersect,
+                     solve_residual, trace_simplex, xf_apply, xf_compose, xf_from_matrix, xf_scale,
+                     xf_translation)
 
 __all__ = [
     "BatchSoA", "GmbError", "LAYOUT_AOS", "LAYOUT_SOA", "lib",
     "decomp_plu", "decomp_lup", "backsolve_lu", "backsolve_plu", "apply_permutation", "linear_solve",
     "linear_solve_vec", "cholesky", "cholesky_solve", "inv", "orthogonal", "nullspace", "solve_residual", "checksum",
     "simplex_contains", "trace_simplex", "simplex_intersect",
+    "mul", "xf_from_matrix", "xf_translation", "xf_scale", "xf_compose", "xf_apply",
     "host_linear_solve", "host_inv", "host_cholesky_solve", "host_decomp_plu",
 ]

@@ -45,6 +45,12 @@ _TYPED = {
     "gmb_simplex_contains": [_i, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp],
     "gmb_trace_simplex": [_i, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i, _vp],
     "gmb_simplex_intersect": [_i, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _i, _vp],
+    "gmb_mul": [_i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "gmb_xf_from_matrix": [_i, _i64, _vp, _vp, _vp, _i, _i, _vp],
+    "gmb_xf_translation": [_i, _i64, _vp, _vp, _i, _vp],
+    "gmb_xf_scale": [_i, _i64, _vp, _vp, _i, _vp],
+    "gmb_xf_compose": [_i, _i64, _vp, _vp, _vp, _i, _i, _vp],
+    "gmb_xf_apply": [_i, _i, _i64, _vp, _i64, _vp, _vp, _i, _vp],
     "gmb_host_plu_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _i],
     "gmb_host_inv": [_i, _i64, _vp, _vp, _vp, _i, _i, _i],
     "gmb_host_cholesky_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i],

@@ -44,6 +44,13 @@ template <typename T> int simplex_contains(int, int64_t, const T*, int64_t, cons
 template <typename T> int trace_simplex(int, int64_t, const T*, int64_t, const T*, const T*, int64_t, uint8_t*, T*, T*, int, cudaStream_t);
 template <typename T> int simplex_intersect(int, int64_t, const T*, int64_t, const uint8_t*, const T*, const T*, int64_t, T*, int, cudaStream_t);
 template <typename T> int generic_nullspace(int, int, int64_t, const T*, T*, uint8_t*, int, cudaStream_t);
+// gmb_xform_*.cu
+template <typename T> int mul_small(int, int, int, int64_t, const T*, const T*, T*, int, int, cudaStream_t);
+template <typename T> int mul_generic(int, int, int, int64_t, const T*, const T*, T*, int, int, cudaStream_t);
+template <typename T> int xf_from_matrix(int, int64_t, const T*, T*, uint8_t*, int, int, bool, cudaStream_t);
+template <typename T> int xf_translation(int, int64_t, const T*, T*, int, int, bool, cudaStream_t);
+template <typename T> int xf_compose(int, int64_t, const T*, const T*, T*, int, int, cudaStream_t);
+template <typename T> int xf_apply(int, int, int64_t, const T*, bool, const T*, T*, int, cudaStream_t);
 
 // Which fused-solve kernel serves (T, n)?  Measured on B200 (2^20 systems, AoS, CUDA events;
 // profiles/r1d_row_vs_column.md): the row-distributed kernel wins for float n in {12, 14, 15, 16}
@@ -418,6 +425,53 @@ int host_plu_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t*
     });
 }
 
+// ---- rows (f)4 / (f)3 ------------------------------------------------------------------------------
+template <typename T>
+int mul_api(int r, int k, int c, int64_t B, const T* A, const T* Bm, T* D, int acc, int layout, int arm, int brm, int drm,
+            void* stream) {
+    if (B < 0 || r < 1 || k < 1 || c < 1 || bad_layout(layout) || (B > 0 && (!A || !Bm || !D))) return GMB_ERR_INVALID_ARG;
+    if (r > GMB_MAX_N || k > GMB_MAX_N || c > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    const int flags = (acc ? 1 : 0) | (arm ? 2 : 0) | (brm ? 4 : 0) | (drm ? 8 : 0);
+    const bool fast = all_aligned16(A, Bm, D);
+    if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (fast && r <= 4 && k <= 4 && c <= 4) return mul_small<T>(r, k, c, B, A, Bm, D, flags, layout, as_stream(stream));
+    if (D == A || D == Bm) return GMB_ERR_INVALID_ARG;           // only the register shapes multiply in place
+    return mul_generic<T>(r, k, c, B, A, Bm, D, flags, layout, as_stream(stream));
+}
+
+static bool bad_xf_dim(int n) { return n < 2 || n > 7; }
+
+template <typename T>
+int xf_from_matrix_api(int n, int64_t B, const T* M, T* xf, uint8_t* ok, int layout, int rm, void* stream) {
+    if (B < 0 || n < 1 || bad_layout(layout) || (B > 0 && (!M || !xf))) return GMB_ERR_INVALID_ARG;
+    if (bad_xf_dim(n)) return GMB_ERR_UNSUPPORTED;
+    return xf_from_matrix<T>(n, B, M, xf, ok, layout, rm, all_aligned16(xf), as_stream(stream));
+}
+
+template <typename T>
+int xf_translation_api(int n, int64_t B, const T* t, T* xf, int scale, int layout, void* stream) {
+    if (B < 0 || n < 1 || bad_layout(layout) || (B > 0 && (!t || !xf))) return GMB_ERR_INVALID_ARG;
+    if (bad_xf_dim(n)) return GMB_ERR_UNSUPPORTED;
+    return xf_translation<T>(n, B, t, xf, scale, layout, all_aligned16(xf), as_stream(stream));
+}
+
+template <typename T>
+int xf_compose_api(int n, int64_t B, const T* xf1, const T* xf2, T* out, int inverse, int layout, void* stream) {
+    if (B < 0 || n < 1 || bad_layout(layout) || (B > 0 && (!xf1 || !xf2 || !out)) || (B > 0 && (out == xf1 || out == xf2)))
+        return GMB_ERR_INVALID_ARG;
+    if (bad_xf_dim(n)) return GMB_ERR_UNSUPPORTED;
+    return xf_compose<T>(n, B, xf1, xf2, out, inverse, layout, as_stream(stream));
+}
+
+template <typename T>
+int xf_apply_api(int n, int mode, int64_t B, const T* xf, int64_t xf_count, const T* p, T* out, int layout, void* stream) {
+    if (B < 0 || n < 1 || mode < 0 || mode > 5 || bad_layout(layout) || (xf_count != 1 && xf_count != B) ||
+        (B > 0 && (!xf || !p || !out)))
+        return GMB_ERR_INVALID_ARG;
+    if (bad_xf_dim(n)) return GMB_ERR_UNSUPPORTED;
+    return xf_apply<T>(n, mode, B, xf, xf_count == 1, p, out, layout, as_stream(stream));
+}
+
 }  // namespace gmb
 
 // ==================================================================== extern "C"
@@ -562,6 +616,28 @@ int gmb_stream_synchronize(void* stream) { return (int)cudaStreamSynchronize(as_
                                     void* stream) {                                                                   \
         return simplex_intersect_api<T>(dim, B, verts, vert_stride, nverts, origin, direction, ray_stride, interval,  \
                                         layout, stream);                                                              \
+    }                                                                                                                 \
+    int gmb_mul_##SUF(int r, int k, int c, int64_t B, const T* A, const T* Bm, T* D, int accumulate, int layout,     \
+                      int a_row_major, int b_row_major, int d_row_major, void* stream) {                              \
+        return mul_api<T>(r, k, c, B, A, Bm, D, accumulate, layout, a_row_major, b_row_major, d_row_major, stream);   \
+    }                                                                                                                 \
+    int gmb_xf_from_matrix_##SUF(int dim, int64_t B, const T* M, T* xf_out, uint8_t* ok, int layout, int row_major,   \
+                                 void* stream) {                                                                      \
+        return xf_from_matrix_api<T>(dim, B, M, xf_out, ok, layout, row_major, stream);                               \
+    }                                                                                                                 \
+    int gmb_xf_translation_##SUF(int dim, int64_t B, const T* t, T* xf_out, int layout, void* stream) {               \
+        return xf_translation_api<T>(dim, B, t, xf_out, 0, layout, stream);                                           \
+    }                                                                                                                 \
+    int gmb_xf_scale_##SUF(int dim, int64_t B, const T* sx, T* xf_out, int layout, void* stream) {                    \
+        return xf_translation_api<T>(dim, B, sx, xf_out, 1, layout, stream);                                          \
+    }                                                                                                                 \
+    int gmb_xf_compose_##SUF(int dim, int64_t B, const T* xf1, const T* xf2, T* out, int inverse, int layout,         \
+                             void* stream) {                                                                          \
+        return xf_compose_api<T>(dim, B, xf1, xf2, out, inverse, layout, stream);                                     \
+    }                                                                                                                 \
+    int gmb_xf_apply_##SUF(int dim, int mode, int64_t B, const T* xf, int64_t xf_count, const T* p, T* out,           \
+                           int layout, void* stream) {                                                                \
+        return xf_apply_api<T>(dim, mode, B, xf, xf_count, p, out, layout, stream);                                   \
     }                                                                                                                 \
     int gmb_solve_residual_##SUF(int n, int64_t B, const T* A, const T* X, const T* Bm, const uint8_t* ok,            \
                                  double* stats4, int layout, int row_major, void* stream) {                           \

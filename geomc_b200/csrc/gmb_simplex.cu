@@ -16,40 +16,13 @@
 #include "gmb_common.cuh"
 #include "gmb_io.cuh"
 #include "gmb_math.cuh"
+#include "gmb_work.cuh"
 
 #include <limits>
 
 namespace gmb {
 
 constexpr int kSimplexThreads = 128;
-
-// element e of record s: AoS `stride` elements per record; SoA tiles of W records
-template <typename T, int E, bool SOA>
-__device__ __forceinline__ void rec_load(const T* __restrict__ base, int64_t s, int64_t stride, T (&q)[E]) {
-    if constexpr (SOA) {
-        constexpr int W = soa_w<T>();
-        const T* p = base + (s / W) * (int64_t)(E * W) + (s % W);
-#pragma unroll
-        for (int e = 0; e < E; ++e) q[e] = __ldg(p + e * W);
-    } else {
-        const T* p = base + s * stride;
-#pragma unroll
-        for (int e = 0; e < E; ++e) q[e] = __ldg(p + e);
-    }
-}
-template <typename T, int E, bool SOA>
-__device__ __forceinline__ void rec_store(T* __restrict__ base, int64_t s, const T (&q)[E]) {
-    if constexpr (SOA) {
-        constexpr int W = soa_w<T>();
-        T* p = base + (s / W) * (int64_t)(E * W) + (s % W);
-#pragma unroll
-        for (int e = 0; e < E; ++e) p[e * W] = q[e];
-    } else {
-        T* p = base + s * (int64_t)E;
-#pragma unroll
-        for (int e = 0; e < E; ++e) p[e] = q[e];
-    }
-}
 
 // Vec-form linear_solve, LUDecomp.h:417-441, on K basis vectors `bases[K*i + d]` (= column-major
 // K x K) and M right-hand sides x[j][d].  K < 5: inverse, then X <- inv * X (sum from 0, k ascending,

@@ -108,6 +108,45 @@ __device__ __forceinline__ void load_bytes(const uint8_t* p, int64_t s0, int64_t
         for (int k = 0; k < K; ++k) b[v][k] = (s0 + v < B) ? p[(s0 + v) * K + k] : (uint8_t)k;
 }
 
+// ---- one record per thread, element by element (the kernels that keep ONE system per thread in both
+// layouts: gmb_simplex.cu, gmb_xform.cuh).  AoS: `stride` elements between records; SoA: tiles of W
+// records, consecutive threads read consecutive 4/8-byte words of one element plane (coalesced).
+// rec_*_part moves CNT elements starting at element `off` of records that hold ETOT elements.
+template <typename T, int ETOT, int CNT, bool SOA>
+__device__ __forceinline__ void rec_load_part(const T* __restrict__ base, int64_t s, int64_t stride, int off, T (&q)[CNT]) {
+    if constexpr (SOA) {
+        constexpr int W = soa_w<T>();
+        const T* p = base + (s / W) * (int64_t)(ETOT * W) + (int64_t)off * W + (s % W);
+#pragma unroll
+        for (int e = 0; e < CNT; ++e) q[e] = __ldg(p + e * W);
+    } else {
+        const T* p = base + s * stride + off;
+#pragma unroll
+        for (int e = 0; e < CNT; ++e) q[e] = __ldg(p + e);
+    }
+}
+template <typename T, int ETOT, int CNT, bool SOA>
+__device__ __forceinline__ void rec_store_part(T* __restrict__ base, int64_t s, int off, const T (&q)[CNT]) {
+    if constexpr (SOA) {
+        constexpr int W = soa_w<T>();
+        T* p = base + (s / W) * (int64_t)(ETOT * W) + (int64_t)off * W + (s % W);
+#pragma unroll
+        for (int e = 0; e < CNT; ++e) p[e * W] = q[e];
+    } else {
+        T* p = base + s * (int64_t)ETOT + off;
+#pragma unroll
+        for (int e = 0; e < CNT; ++e) p[e] = q[e];
+    }
+}
+template <typename T, int E, bool SOA>
+__device__ __forceinline__ void rec_load(const T* __restrict__ base, int64_t s, int64_t stride, T (&q)[E]) {
+    rec_load_part<T, E, E, SOA>(base, s, stride, 0, q);
+}
+template <typename T, int E, bool SOA>
+__device__ __forceinline__ void rec_store(T* __restrict__ base, int64_t s, const T (&q)[E]) {
+    rec_store_part<T, E, E, SOA>(base, s, 0, q);
+}
+
 template <typename T, int R, int C, bool RM>
 __device__ __forceinline__ void unflatten(const T (&q)[R * C], T (&a)[R][C]) {
 #pragma unroll

@@ -17,6 +17,10 @@ Reference function                                   -> here
     cholesky              Cholesky.h:37              -> cholesky
     (none)                                           -> cholesky_solve   (new: fused factor + solve)
     inv                   Matrix.h:717               -> inv
+    mul / mul_acc         Matrix.h:386 / :433        -> mul
+    transformation / translation / scale   AffineTransform.h:862 / :814 / :838   -> xf_from_matrix / xf_translation / xf_scale
+    AffineTransform `*`, `/`               AffineTransform.h:142 / :154          -> xf_compose
+    AffineTransform::apply & co.           AffineTransform.h:224-293             -> xf_apply
 """
 from __future__ import annotations
 
@@ -290,6 +294,84 @@ def simplex_intersect(verts: Batch, origin: Batch, direction: Batch, dim: int, n
     _lib.call("gmb_simplex_intersect", _SUF[dt], dim, B, _ptr(verts), 0, None if nverts is None else nverts.data_ptr(),
               _ptr(origin), _ptr(direction), 0, _ptr(interval), layout, _stream_ptr(dev))
     return interval
+
+
+def mul(a: Batch, b: Batch, r: int, k: int, c: int, out: Optional[Batch] = None, acc: bool = False,
+        a_row_major: bool = True, b_row_major: bool = True, d_row_major: bool = True) -> Batch:
+    """geom::mul(&d, a, b) / mul_acc (Matrix.h:386 / :433): a (B, r*k) * b (B, k*c) -> d (B, r*c).
+    c == 1: matrix * Vec; r == 1: Vec * matrix.  `out` may be `a` or `b` for shapes up to 4 x 4 x 4."""
+    layout, B, E, dt, dev, _ = _info(a)
+    assert E == r * k and _info(b)[2] == k * c and _info(b)[0] == layout
+    if out is None:
+        assert not acc, "mul_acc needs the destination to accumulate into"
+        out = _new_like(a, r * c)
+    assert _info(out)[2] == r * c and _info(out)[0] == layout
+    _lib.call("gmb_mul", _SUF[dt], r, k, c, B, _ptr(a), _ptr(b), _ptr(out), int(acc), layout, int(a_row_major),
+              int(b_row_major), int(d_row_major), _stream_ptr(dev))
+    return out
+
+
+XF_MODES = ("apply", "apply_inverse", "apply_direction", "apply_inverse_direction", "apply_normal", "apply_inverse_normal")
+
+
+def xf_from_matrix(m: Batch, dim: int, row_major: bool = True) -> Tuple[Batch, torch.Tensor]:
+    """geom::transformation(mat) (AffineTransform.h:862): m (B, N*N) -> (records (B, 2*(N+1)^2), ok uint8[B]).
+    A record is mat | inv, both (N+1) x (N+1) row-major; a singular m gives inv = identity (and ok = 0)."""
+    layout, B, E, dt, dev, _ = _info(m)
+    assert E == dim * dim
+    xf = _new_like(m, 2 * (dim + 1) ** 2)
+    ok = _u8(B, 1, dev)
+    _lib.call("gmb_xf_from_matrix", _SUF[dt], dim, B, _ptr(m), _ptr(xf), ok.data_ptr(), layout, int(row_major),
+              _stream_ptr(dev))
+    return xf, ok
+
+
+def _xf_from_vec(name: str, t: Batch, dim: int) -> Batch:
+    layout, B, E, dt, dev, _ = _info(t)
+    assert E == dim
+    xf = _new_like(t, 2 * (dim + 1) ** 2)
+    _lib.call(name, _SUF[dt], dim, B, _ptr(t), _ptr(xf), layout, _stream_ptr(dev))
+    return xf
+
+
+def xf_translation(t: Batch, dim: int) -> Batch:
+    """geom::translation(Vec<T,N>) (AffineTransform.h:814): t (B, N) -> records."""
+    return _xf_from_vec("gmb_xf_translation", t, dim)
+
+
+def xf_scale(sx: Batch, dim: int) -> Batch:
+    """geom::scale(Vec<T,N>) (AffineTransform.h:838): sx (B, N) -> records (inv diagonal = 1 / sx)."""
+    return _xf_from_vec("gmb_xf_scale", sx, dim)
+
+
+def xf_compose(xf1: Batch, xf2: Batch, dim: int, inverse: bool = False) -> Batch:
+    """xf1 * xf2 (AffineTransform.h:142: apply xf2, then xf1) or, with inverse=True, xf1 / xf2 (:154)."""
+    layout, B, E, dt, dev, _ = _info(xf1)
+    assert E == 2 * (dim + 1) ** 2 and _info(xf2)[2] == E and _info(xf2)[0] == layout
+    out = _new_like(xf1)
+    _lib.call("gmb_xf_compose", _SUF[dt], dim, B, _ptr(xf1), _ptr(xf2), _ptr(out), int(inverse), layout, _stream_ptr(dev))
+    return out
+
+
+def xf_apply(xf, p: Batch, dim: int, mode: str = "apply") -> Batch:
+    """AffineTransform::apply & co. (AffineTransform.h:224-293) on a point array p (B, N).
+    xf: a batch of B records (same layout as p), or ONE record as a tensor of shape (1, 2*(N+1)^2) / (2*(N+1)^2,)
+    applied to every point."""
+    layout, B, E, dt, dev, _ = _info(p)
+    assert E == dim
+    E_xf = 2 * (dim + 1) ** 2
+    if isinstance(xf, BatchSoA) and xf.B == 1:
+        xf = xf.to_aos()                                   # a one-record container is not a packed record
+    if isinstance(xf, torch.Tensor) and xf.numel() == E_xf:
+        assert xf.is_cuda and xf.is_contiguous() and xf.dtype == dt
+        count, pxf = 1, xf.data_ptr()
+    else:
+        assert _info(xf)[0] == layout and _info(xf)[1] == B and _info(xf)[2] == E_xf
+        count, pxf = B, _ptr(xf)
+    out = _new_like(p)
+    _lib.call("gmb_xf_apply", _SUF[dt], dim, XF_MODES.index(mode), B, pxf, count, _ptr(p), _ptr(out), layout,
+              _stream_ptr(dev))
+    return out
 
 
 def solve_residual(a: Batch, x: Batch, b: Batch, ok: Optional[torch.Tensor], n: int, row_major: bool = True) -> torch.Tensor:

@@ -194,6 +194,58 @@ int gmb_simplex_intersect_f64(int dim, int64_t B, const double* verts, int64_t v
                               const double* origin, const double* direction, int64_t ray_stride, double* interval,
                               int layout, void* stream);
 
+/* ---- "next" row (f)4: batched mul / mul_acc  (Matrix.h:386-421 / 433-456 -> MatrixMult.h:54-80) --------
+ * D (r x c) = A (r x k) * Bm (k x c) per system; accumulate != 0 -> D += A * Bm (mul_acc).  Each D(i,j) is the
+ * running sum `sum = 0 (or D(i,j)); sum = fma(A(i,n), Bm(n,j), sum)` for n ascending, as the reference's build
+ * evaluates `sum += a(r,n) * b(n,c)`.  c == 1 is matrix * Vec (MatrixMult.h:181-190), r == 1 is Vec * matrix
+ * (:239-248).  Each operand has its own row_major flag (MatrixGlue.h:28-58).  1 <= r, k, c <= 16.
+ * D may alias A or Bm when r, k, c <= 4 (the reference multiplies into a temporary then, Matrix.h:409-417);
+ * for larger shapes aliasing returns GMB_ERR_INVALID_ARG. */
+int gmb_mul_f32(int r, int k, int c, int64_t B, const float* A, const float* Bm, float* D, int accumulate, int layout,
+                int a_row_major, int b_row_major, int d_row_major, void* stream);
+int gmb_mul_f64(int r, int k, int c, int64_t B, const double* A, const double* Bm, double* D, int accumulate, int layout,
+                int a_row_major, int b_row_major, int d_row_major, void* stream);
+
+/* ---- "next" row (f)3: AffineTransform<T,N>  (linalg/AffineTransform.h), dim = N = 2..7 -------------------
+ * A transform record is PACKED: K*K elements of `mat` then K*K of `inv`, K = N + 1, both row-major
+ * (AffineTransform.h:91-93).  AoS = consecutive records of 2*K*K elements (note that the reference's objects
+ * can carry alignment padding -- sizeof(AffineTransform<float,2>) is 80, not 72 -- include/geomc_b200/batch.hpp
+ * packs and unpacks); SoA = an interleaved container with E = 2*K*K.
+ *
+ * gmb_xf_from_matrix: transformation(mat), :862-884.  M = N x N per system (row_major flag as elsewhere).
+ *   mat = M embedded in the identity, inv = inv(M) embedded likewise.  The reference ignores inv()'s result
+ *   (:873), so a singular M yields inv = identity; ok[s] (nullable) reports inv()'s return value.
+ * gmb_xf_translation / gmb_xf_scale: translation(tx) :814-821 (inv = -tx), scale(sx) :838-845 (inv = 1 / sx[i]).
+ * gmb_xf_compose: inverse == 0: xf1 * xf2 (:142-147 -> apply :300-305: mat = xf1.mat * xf2.mat,
+ *   inv = xf2.inv * xf1.inv); inverse != 0: xf1 / xf2 (:154-159 -> apply_inverse :312-317: mat = xf2.inv * xf1.mat,
+ *   inv = xf1.inv * xf2.mat).  `out` must not alias an input.
+ * gmb_xf_apply: p and out hold B vectors of N.  mode: 0 apply (:224), 1 apply_inverse (:262), 2 apply_direction
+ *   (:233), 3 apply_inverse_direction (:271), 4 apply_normal (:248), 5 apply_inverse_normal (:284).
+ *   xf_count == B: one transform per point (layout as the other arguments); xf_count == 1: ONE packed record
+ *   (2*K*K contiguous elements, whatever `layout` says -- also when B == 1) applied to the whole point array. */
+#define GMB_XF_APPLY 0
+#define GMB_XF_APPLY_INVERSE 1
+#define GMB_XF_APPLY_DIRECTION 2
+#define GMB_XF_APPLY_INVERSE_DIRECTION 3
+#define GMB_XF_APPLY_NORMAL 4
+#define GMB_XF_APPLY_INVERSE_NORMAL 5
+int gmb_xf_from_matrix_f32(int dim, int64_t B, const float* M, float* xf_out, uint8_t* ok, int layout, int row_major,
+                           void* stream);
+int gmb_xf_from_matrix_f64(int dim, int64_t B, const double* M, double* xf_out, uint8_t* ok, int layout, int row_major,
+                           void* stream);
+int gmb_xf_translation_f32(int dim, int64_t B, const float* t, float* xf_out, int layout, void* stream);
+int gmb_xf_translation_f64(int dim, int64_t B, const double* t, double* xf_out, int layout, void* stream);
+int gmb_xf_scale_f32(int dim, int64_t B, const float* sx, float* xf_out, int layout, void* stream);
+int gmb_xf_scale_f64(int dim, int64_t B, const double* sx, double* xf_out, int layout, void* stream);
+int gmb_xf_compose_f32(int dim, int64_t B, const float* xf1, const float* xf2, float* out, int inverse, int layout,
+                       void* stream);
+int gmb_xf_compose_f64(int dim, int64_t B, const double* xf1, const double* xf2, double* out, int inverse, int layout,
+                       void* stream);
+int gmb_xf_apply_f32(int dim, int mode, int64_t B, const float* xf, int64_t xf_count, const float* p, float* out,
+                     int layout, void* stream);
+int gmb_xf_apply_f64(int dim, int mode, int64_t B, const double* xf, int64_t xf_count, const double* p, double* out,
+                     int layout, void* stream);
+
 /* ---- batch statistics (what the reference's tests assert, reduced on the device) ------------
  * stats[0] = sum over systems of max_i |(A x - b)_i| (only systems with ok != 0),
  * stats[1] = max of the same, stats[2] = number of systems with ok == 0,
