@@ -112,6 +112,10 @@ __device__ __forceinline__ void load_bytes(const uint8_t* p, int64_t s0, int64_t
 // layouts: gmb_simplex.cu, gmb_xform.cuh).  AoS: `stride` elements between records; SoA: tiles of W
 // records, consecutive threads read consecutive 4/8-byte words of one element plane (coalesced).
 // rec_*_part moves CNT elements starting at element `off` of records that hold ETOT elements.
+// AoS chunks whose byte size is a multiple of 16 move with 128-bit accesses when their address is 16-byte
+// aligned (checked per thread; warp-uniform whenever the record size is a multiple of 16 too): a warp-wide
+// scalar access to records >= 128 bytes apart costs one L1 wavefront per lane, so this is a 4x (float) / 2x
+// (double) cut in LSU work -- measured: per-point AffineTransform::apply on AoS records was wavefront-bound.
 template <typename T, int ETOT, int CNT, bool SOA>
 __device__ __forceinline__ void rec_load_part(const T* __restrict__ base, int64_t s, int64_t stride, int off, T (&q)[CNT]) {
     if constexpr (SOA) {
@@ -121,6 +125,24 @@ __device__ __forceinline__ void rec_load_part(const T* __restrict__ base, int64_
         for (int e = 0; e < CNT; ++e) q[e] = __ldg(p + e * W);
     } else {
         const T* p = base + s * stride + off;
+        constexpr int V = soa_v<T>();
+        if constexpr (CNT % V == 0) {
+            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                using VT = typename VecOf<T>::type;
+                const VT* pv = reinterpret_cast<const VT*>(p);
+                VT tmp[CNT / V];
+#pragma unroll
+                for (int i = 0; i < CNT / V; ++i) tmp[i] = __ldg(pv + i);
+#pragma unroll
+                for (int i = 0; i < CNT / V; ++i) {
+                    T t[V];
+                    unpack(tmp[i], t);
+#pragma unroll
+                    for (int v = 0; v < V; ++v) q[i * V + v] = t[v];
+                }
+                return;
+            }
+        }
 #pragma unroll
         for (int e = 0; e < CNT; ++e) q[e] = __ldg(p + e);
     }
@@ -134,6 +156,21 @@ __device__ __forceinline__ void rec_store_part(T* __restrict__ base, int64_t s, 
         for (int e = 0; e < CNT; ++e) p[e * W] = q[e];
     } else {
         T* p = base + s * (int64_t)ETOT + off;
+        constexpr int V = soa_v<T>();
+        if constexpr (CNT % V == 0) {
+            if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+                using VT = typename VecOf<T>::type;
+                VT* pv = reinterpret_cast<VT*>(p);
+#pragma unroll
+                for (int i = 0; i < CNT / V; ++i) {
+                    T t[V];
+#pragma unroll
+                    for (int v = 0; v < V; ++v) t[v] = q[i * V + v];
+                    pv[i] = pack(t);
+                }
+                return;
+            }
+        }
 #pragma unroll
         for (int e = 0; e < CNT; ++e) p[e] = q[e];
     }

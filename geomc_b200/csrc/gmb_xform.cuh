@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(kXfThreads)
 k_xf_apply(const T* __restrict__ xf, const T* __restrict__ P, T* __restrict__ out, int mode, int64_t B) {
     using X = Xf<T, N>;
     constexpr int K = X::K;
-    constexpr int ITER = BCAST ? 4 : 1;
+    constexpr int ITER = BCAST ? 8 : 1;
     const bool use_inv = mode == 1 || mode == 3 || mode == 4;
     const bool hom = mode <= 1;
     const bool transposed = mode >= 4;
@@ -313,17 +313,23 @@ k_xf_apply(const T* __restrict__ xf, const T* __restrict__ P, T* __restrict__ ou
     T m[N * K];
     if constexpr (BCAST) rec_load_part<T, X::E, N * K, false>(xf, 0, X::E, off, m);
     else rec_load_part<T, X::E, N * K, SOA>(xf, s_first, X::E, off, m);
+    // all of this thread's points are requested before any is used (ITER independent loads in flight)
+    T p[ITER][N];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int64_t s = s_first + (int64_t)it * kXfThreads;
+        if (s < B) rec_load<T, N, SOA>(P, s, N, p[it]);
+    }
 #pragma unroll
     for (int it = 0; it < ITER; ++it) {
         const int64_t s = s_first + (int64_t)it * kXfThreads;
         if (s >= B) break;
-        T p[N], o[N];
-        rec_load<T, N, SOA>(P, s, N, p);
+        T o[N];
 #pragma unroll
         for (int r = 0; r < N; ++r) {
             T x = (T)0;
 #pragma unroll
-            for (int c = 0; c < N; ++c) x = fma_rn(transposed ? m[K * c + r] : m[K * r + c], p[c], x);
+            for (int c = 0; c < N; ++c) x = fma_rn(transposed ? m[K * c + r] : m[K * r + c], p[it][c], x);
             const T xh = fma_rn(m[K * r + N], (T)1, x);
             o[r] = hom ? xh : x;
         }
@@ -408,7 +414,7 @@ int xf_apply(int n, int mode, int64_t B, const T* xf, bool bcast, const T* p, T*
     dispatch_int<2, 3, 4, 5, 6, 7>(n, [&](auto N) {
         dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
             dispatch_bool(bcast, [&](auto BC) {
-                const int64_t per_block = (int64_t)kXfThreads * (BC.value ? 4 : 1);
+                const int64_t per_block = (int64_t)kXfThreads * (BC.value ? 8 : 1);
                 GMB_XF_LAUNCH((k_xf_apply<T, N.value, SOA.value, BC.value>), ceil_div(B, per_block), kXfThreads, st, xf, p,
                               out, mode, B);
             });

@@ -15,6 +15,10 @@
 //     cholesky                         Cholesky.h:37 / :83
 //     cholesky_solve                   (new; the reference has no Cholesky solve)
 //     inv                              Matrix.h:717 -> MatrixInv.h:49-337
+//     orthogonal / nullspace           Orthogonal.h:73 / :136
+//     contains / trace_simplex / intersect      shape/Simplex.h:450 / :647 / :251
+//     mul / mul_acc                    Matrix.h:386 / :433
+//     transformation / translation / scale / compose / apply...   AffineTransform.h:862 / :814 / :838 / :142 / :224-293
 //
 // Three forms of every function:
 //   (1) device form  -- DeviceBatch / BatchSoA arguments already resident in HBM, asynchronous;
@@ -74,6 +78,12 @@ template <typename T> struct Abi;
         static constexpr auto simplex_contains = gmb_simplex_contains_##S;                                  \
         static constexpr auto trace_simplex = gmb_trace_simplex_##S;                                        \
         static constexpr auto simplex_intersect = gmb_simplex_intersect_##S;                                \
+        static constexpr auto mul = gmb_mul_##S;                                                            \
+        static constexpr auto xf_from_matrix = gmb_xf_from_matrix_##S;                                      \
+        static constexpr auto xf_translation = gmb_xf_translation_##S;                                      \
+        static constexpr auto xf_scale = gmb_xf_scale_##S;                                                  \
+        static constexpr auto xf_compose = gmb_xf_compose_##S;                                              \
+        static constexpr auto xf_apply = gmb_xf_apply_##S;                                                  \
     };
 GMB_ABI(float, f32)
 GMB_ABI(double, f64)
@@ -490,6 +500,170 @@ index_t intersect(const S* simplexes, const R* rays, index_t B, I* intervals, in
         nonempty += ib[2 * (std::size_t)i] <= ib[2 * (std::size_t)i + 1];
     }
     return nonempty;
+}
+
+// ---- row (f)4 of the scope table: mul / mul_acc (Matrix.h:386-456 -> MatrixMult.h:54-80) ------------
+// for (s < B) geom::mul(&into[s], a[s], b[s]);   (accumulate: geom::mul_acc)      `into` may be `a` or `b`
+// for shapes up to 4 x 4 x 4.  Matrix objects as in the other object forms (elem_t, ROWDIM, COLDIM, Layout,
+// data_begin()); dimensions 1..16.
+template <typename Md, typename Ma, typename Mb>
+void mul(Md* into, const Ma* a, const Mb* b, index_t B, bool accumulate = false, int device = 0) {
+    using T = detail::elem_of<Ma>;
+    constexpr int R = (int)Ma::ROWDIM, K = (int)Ma::COLDIM, C = (int)Mb::COLDIM;
+    static_assert((int)Mb::ROWDIM == K && (int)Md::ROWDIM == R && (int)Md::COLDIM == C, "dimension mismatch");
+    static_assert(std::is_same<T, detail::elem_of<Mb>>::value && std::is_same<T, detail::elem_of<Md>>::value, "element types must agree");
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return;
+    auto ha = detail::pack(a, B, R * K);
+    auto hb = detail::pack(b, B, K * C);
+    DeviceBatch<T> dA(B, R * K, Layout::AoS), dB(B, K * C, Layout::AoS), dD(B, R * C, Layout::AoS);
+    dA.upload_aos(ha.data());
+    dB.upload_aos(hb.data());
+    std::vector<T> hd;
+    if (accumulate) {
+        hd = detail::pack(into, B, R * C);
+        dD.upload_aos(hd.data());
+    } else {
+        hd.resize((std::size_t)(B * R * C));
+    }
+    check(Abi<T>::mul(R, K, C, B, dA.data(), dB.data(), dD.data(), accumulate ? 1 : 0, GMB_LAYOUT_AOS, (int)Ma::Layout == 0 ? 1 : 0,
+                      (int)Mb::Layout == 0 ? 1 : 0, (int)Md::Layout == 0 ? 1 : 0, nullptr), "mul");
+    dD.download_aos(hd.data());
+    check(gmb_stream_synchronize(nullptr), "sync");
+    detail::unpack(into, hd, B, R * C, nullptr);
+}
+template <typename Md, typename Ma, typename Mb>
+void mul_acc(Md* into, const Ma* a, const Mb* b, index_t B, int device = 0) { mul(into, a, b, B, true, device); }
+
+// ---- row (f)3 of the scope table: AffineTransform (linalg/AffineTransform.h) -------------------------
+// Object forms, duck-typed on AffineTransform's members `mat` and `inv` (:91-93, SimpleMatrix<T,N+1,N+1>).
+// The device works on packed records (mat | inv, row-major); objects are packed / unpacked here because
+// SimpleMatrix can carry alignment padding.
+namespace detail {
+template <typename X> using xf_elem = elem_of<typename std::remove_reference<decltype(std::declval<X&>().mat)>::type>;
+template <typename X> constexpr int xf_K() { return (int)std::remove_reference<decltype(std::declval<X&>().mat)>::type::ROWDIM; }
+
+template <typename X>
+std::vector<xf_elem<X>> pack_xf(const X* xf, index_t B) {
+    using T = xf_elem<X>;
+    constexpr int KK = xf_K<X>() * xf_K<X>();
+    std::vector<T> v((std::size_t)(B * 2 * KK));
+    for (index_t s = 0; s < B; ++s) {
+        std::memcpy(v.data() + s * 2 * KK, xf[s].mat.data_begin(), sizeof(T) * KK);
+        std::memcpy(v.data() + s * 2 * KK + KK, xf[s].inv.data_begin(), sizeof(T) * KK);
+    }
+    return v;
+}
+template <typename X>
+void unpack_xf(X* xf, const std::vector<xf_elem<X>>& v, index_t B) {
+    using T = xf_elem<X>;
+    constexpr int KK = xf_K<X>() * xf_K<X>();
+    for (index_t s = 0; s < B; ++s) {
+        std::memcpy(xf[s].mat.data_begin(), v.data() + s * 2 * KK, sizeof(T) * KK);
+        std::memcpy(xf[s].inv.data_begin(), v.data() + s * 2 * KK + KK, sizeof(T) * KK);
+    }
+}
+}  // namespace detail
+
+// for (s < B) out[s] = geom::transformation(m[s]);       AffineTransform.h:862.  -> number of singular matrices
+// (whose transforms carry inv = identity, as in the reference).
+template <typename X, typename Mx>
+index_t transformation(X* out, const Mx* m, index_t B, int device = 0) {
+    using T = detail::elem_of<Mx>;
+    constexpr int N = (int)Mx::ROWDIM, E = 2 * (N + 1) * (N + 1);
+    static_assert(detail::xf_K<X>() == N + 1 && (int)Mx::COLDIM == N, "AffineTransform<T,N> from an N x N matrix");
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return 0;
+    auto hm = detail::pack(m, B, N * N);
+    DeviceBatch<T> dM(B, N * N, Layout::AoS), dX(B, E, Layout::AoS);
+    DeviceArray<std::uint8_t> dok((std::size_t)B);
+    dM.upload_aos(hm.data());
+    check(Abi<T>::xf_from_matrix(N, B, dM.data(), dX.data(), dok.get(), GMB_LAYOUT_AOS, (int)Mx::Layout == 0 ? 1 : 0, nullptr),
+          "transformation");
+    std::vector<T> hx((std::size_t)(B * E));
+    std::vector<std::uint8_t> okb((std::size_t)B);
+    dX.download_aos(hx.data());
+    dok.download(okb.data(), (std::size_t)B);
+    check(gmb_stream_synchronize(nullptr), "sync");
+    detail::unpack_xf(out, hx, B);
+    return detail::count_false(okb.data(), B);
+}
+
+namespace detail {
+template <typename X, typename V>
+void xf_from_vectors(X* out, const V* v, index_t B, bool is_scale, int device) {
+    using T = xf_elem<X>;
+    constexpr int N = xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
+    static_assert(sizeof(V) == sizeof(T) * N, "packed Vec<T,N> expected");
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return;
+    DeviceBatch<T> dV(B, N, Layout::AoS), dX(B, E, Layout::AoS);
+    dV.upload_aos(reinterpret_cast<const T*>(v));
+    check((is_scale ? Abi<T>::xf_scale : Abi<T>::xf_translation)(N, B, dV.data(), dX.data(), GMB_LAYOUT_AOS, nullptr), "translation/scale");
+    std::vector<T> hx((std::size_t)(B * E));
+    dX.download_aos(hx.data());
+    check(gmb_stream_synchronize(nullptr), "sync");
+    unpack_xf(out, hx, B);
+}
+}  // namespace detail
+
+// for (s < B) out[s] = geom::translation(tx[s]);  /  geom::scale(sx[s]);        AffineTransform.h:814 / :838
+template <typename X, typename V>
+void translation(X* out, const V* tx, index_t B, int device = 0) { detail::xf_from_vectors(out, tx, B, false, device); }
+template <typename X, typename V>
+void scale(X* out, const V* sx, index_t B, int device = 0) { detail::xf_from_vectors(out, sx, B, true, device); }
+
+// for (s < B) out[s] = xf1[s] * xf2[s];   (inverse: xf1[s] / xf2[s])            AffineTransform.h:142 / :154
+// `out` may be xf1 or xf2 (the host copies are independent of the inputs).
+template <typename X>
+void compose(X* out, const X* xf1, const X* xf2, index_t B, bool inverse = false, int device = 0) {
+    using T = detail::xf_elem<X>;
+    constexpr int N = detail::xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return;
+    auto h1 = detail::pack_xf(xf1, B), h2 = detail::pack_xf(xf2, B);
+    DeviceBatch<T> d1(B, E, Layout::AoS), d2(B, E, Layout::AoS), dO(B, E, Layout::AoS);
+    d1.upload_aos(h1.data());
+    d2.upload_aos(h2.data());
+    check(Abi<T>::xf_compose(N, B, d1.data(), d2.data(), dO.data(), inverse ? 1 : 0, GMB_LAYOUT_AOS, nullptr), "compose");
+    dO.download_aos(h1.data());
+    check(gmb_stream_synchronize(nullptr), "sync");
+    detail::unpack_xf(out, h1, B);
+}
+
+// The apply family on point arrays (AffineTransform.h:224-293); mode = GMB_XF_APPLY ... GMB_XF_APPLY_INVERSE_NORMAL.
+//   one transform for the whole array:   for (s < B) out[s] = xf.apply(p[s]);
+template <typename X, typename V, typename = decltype(std::declval<const X&>().mat)>
+void apply(const X& xf, const V* p, V* out, index_t B, int mode = GMB_XF_APPLY, int device = 0) {
+    using T = detail::xf_elem<X>;
+    constexpr int N = detail::xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
+    static_assert(sizeof(V) == sizeof(T) * N, "packed Vec<T,N> expected");
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return;
+    auto hx = detail::pack_xf(&xf, 1);
+    DeviceArray<T> dX((std::size_t)E);
+    DeviceBatch<T> dP(B, N, Layout::AoS), dO(B, N, Layout::AoS);
+    dX.upload(hx.data(), (std::size_t)E);
+    dP.upload_aos(reinterpret_cast<const T*>(p));
+    check(Abi<T>::xf_apply(N, mode, B, dX.get(), 1, dP.data(), dO.data(), GMB_LAYOUT_AOS, nullptr), "apply");
+    dO.download_aos(reinterpret_cast<T*>(out));
+    check(gmb_stream_synchronize(nullptr), "sync");
+}
+//   one transform per point:             for (s < B) out[s] = xf[s].apply(p[s]);
+template <typename X, typename V>
+void apply(const X* xf, const V* p, V* out, index_t B, int mode = GMB_XF_APPLY, int device = 0) {
+    using T = detail::xf_elem<X>;
+    constexpr int N = detail::xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
+    static_assert(sizeof(V) == sizeof(T) * N, "packed Vec<T,N> expected");
+    check(gmb_set_device(device), "set_device");
+    if (B <= 0) return;
+    auto hx = detail::pack_xf(xf, B);
+    DeviceBatch<T> dX(B, E, Layout::AoS), dP(B, N, Layout::AoS), dO(B, N, Layout::AoS);
+    dX.upload_aos(hx.data());
+    dP.upload_aos(reinterpret_cast<const T*>(p));
+    check(Abi<T>::xf_apply(N, mode, B, dX.data(), B, dP.data(), dO.data(), GMB_LAYOUT_AOS, nullptr), "apply");
+    dO.download_aos(reinterpret_cast<T*>(out));
+    check(gmb_stream_synchronize(nullptr), "sync");
 }
 
 }  // namespace batch

@@ -11,6 +11,7 @@
 #include <geomc/linalg/Vec.h>
 #include <geomc/linalg/Ray.h>
 #include <geomc/shape/Simplex.h>
+#include <geomc/linalg/AffineTransform.h>
 #endif
 #include <cmath>
 #include <cstdio>
@@ -60,6 +61,10 @@ struct Rect;
 template <typename T>
 struct Rect<T, 1> {
     T lo, hi;
+};
+template <typename T, long N>
+struct AffineTransform {
+    SimpleMatrix<T, N + 1, N + 1> mat, inv;
 };
 }  // namespace geom
 #endif
@@ -280,6 +285,59 @@ static void test_simplex_queries(long B) {
     EXPECT(hits == B && worst < tol, "rays aimed at a facet point must hit at t = 1 (%ld of %ld, |t-1| %g, N=%ld)", hits, B, worst, N);
 }
 
+// transformation / translation / compose / apply on arrays of AffineTransform objects, and mul on the
+// matrices inside them (rows (f)3 and (f)4)
+template <typename T, long N>
+static void test_affine(long B) {
+    std::mt19937_64 rng(99 + N);
+    std::normal_distribution<double> g(0, 1);
+    const double tol = sizeof(T) == 4 ? 2e-3 : 1e-10;
+    std::vector<geom::SimpleMatrix<T, N, N>> M(B);
+    std::vector<geom::Vec<T, N>> tx(B), p(B), q(B), back(B), q1(B);
+    for (long s = 0; s < B; ++s)
+        for (long r = 0; r < N; ++r) {
+            for (long c = 0; c < N; ++c) M[s](r, c) = (T)(g(rng) + (r == c ? 4 : 0));
+            tx[s][r] = (T)g(rng);
+            p[s][r] = (T)g(rng);
+        }
+    for (long r = 0; r < N; ++r) for (long c = 0; c < N; ++c) M[2](r, c) = 0;          // singular
+    std::vector<geom::AffineTransform<T, N>> xm(B), xt(B), xf(B);
+    long singular = gb::transformation(xm.data(), M.data(), B);
+    EXPECT(singular == 1, "exactly one singular matrix expected (%ld)", singular);
+    for (long r = 0; r <= N; ++r) for (long c = 0; c <= N; ++c)
+        EXPECT(xm[2].inv(r, c) == (r == c ? 1 : 0), "a singular matrix leaves inv = identity (AffineTransform.h:873)");
+    gb::translation(xt.data(), tx.data(), B);
+    gb::compose(xf.data(), xt.data(), xm.data(), B);                 // translation(t) * transformation(M): p -> M p + t
+    gb::apply(xf.data(), p.data(), q.data(), B);
+    gb::apply(xf.data(), q.data(), back.data(), B, GMB_XF_APPLY_INVERSE);
+    gb::apply(xf[7], p.data(), q1.data(), B);
+    double worst = 0, worst_back = 0, worst1 = 0;
+    for (long s = 0; s < B; ++s)
+        for (long r = 0; r < N; ++r) {
+            double acc = (double)tx[s][r], acc1 = (double)tx[7][r];
+            for (long c = 0; c < N; ++c) {
+                acc += (double)M[s](r, c) * (double)p[s][c];
+                acc1 += (double)M[7](r, c) * (double)p[s][c];
+            }
+            worst = std::fmax(worst, std::fabs(acc - (double)q[s][r]));
+            worst1 = std::fmax(worst1, std::fabs(acc1 - (double)q1[s][r]));
+            if (s != 2) worst_back = std::fmax(worst_back, std::fabs((double)back[s][r] - (double)p[s][r]));
+        }
+    EXPECT(worst < tol * 10 && worst1 < tol * 10, "apply must compute M p + t (%g, %g, N=%ld)", worst, worst1, N);
+    EXPECT(worst_back < tol * 100, "apply_inverse must undo apply (%g, N=%ld)", worst_back, N);
+    // mat * inv = identity, computed with the batched mul on the objects' own matrices; then mul_acc adds it again
+    std::vector<geom::SimpleMatrix<T, N + 1, N + 1>> a(B), b(B), prod(B);
+    for (long s = 0; s < B; ++s) { a[s] = xf[s].mat; b[s] = xf[s].inv; }
+    gb::mul(prod.data(), a.data(), b.data(), B);
+    double worst_id = 0;
+    for (long s = 0; s < B; ++s) if (s != 2)
+        for (long r = 0; r <= N; ++r) for (long c = 0; c <= N; ++c)
+            worst_id = std::fmax(worst_id, std::fabs((double)prod[s](r, c) - (r == c ? 1.0 : 0.0)));
+    EXPECT(worst_id < tol * 100, "mat * inv must be the identity (%g, N=%ld)", worst_id, N);
+    gb::mul_acc(prod.data(), a.data(), b.data(), B);
+    EXPECT(std::fabs((double)prod[0](0, 0) - 2.0) < tol * 100 && std::fabs((double)prod[0](0, 1)) < tol * 100, "mul_acc accumulates");
+}
+
 int main() {
     if (gmb_device_count() == 0) {
         // no CPU fallback: the call must fail loudly
@@ -313,6 +371,10 @@ int main() {
     test_simplex_queries<double, 2>(1000);
     test_simplex_queries<double, 3>(1000);
     test_simplex_queries<double, 5>(500);
+    test_affine<float, 3>(3000);
+    test_affine<double, 2>(1000);
+    test_affine<double, 3>(1000);
+    test_affine<double, 6>(400);
     std::printf(failures ? "FAILED (%d)\n" : "batch.hpp OK (%d failures)\n", failures);
     return failures ? 1 : 0;
 }
