@@ -19,6 +19,13 @@
 //     a(r,c) = fma(-b, a(i,c), a(r,c)), skipped when b == 0 (:235-241); the rider column is updated
 //     unconditionally (= backsolve_lu's forward sweep, :345-353);
 //   * slots whose rows are all above the diagonal are skipped statically.
+// Two exchange forms (template flag SHFLX; the dispatcher picks per (T, n), measured):
+//   * bounce buffer (above): LSU-bound -- ncu on 16x16 float: 65 % LSU wavefront utilisation, top stall MIO throttle,
+//     because the dynamic slot is reached with predicated 128-bit shared accesses over every candidate slot;
+//   * register-only: each lane collapses its candidate slots to one row with a select chain on (ps == k), a shuffle
+//     from the pivot's lane broadcasts it, row i is broadcast the same way and dropped into slot ps with predicated
+//     moves.  ALU work instead of LSU wavefronts; 16x16 float 1.23e9 -> 1.62e9 systems/s with 4 lanes per system.
+// WANT_LU = false (fused solve without an LU output): the L part of a row is dead, so only columns >= i travel.
 // Backward sweep: column-oriented (x(c) /= u(c,c); x(r) = fma(-x(c), u(r,c), x(r)) for r < c), rows
 // are in position order so everything is statically indexed; one shuffle per column.
 #pragma once
@@ -51,13 +58,13 @@ template <> struct InfOf<double> { __device__ static __forceinline__ double get(
 // DECOMP = true : decomp_plu in place (LUDecomp.h:188): the rider carries the row's ORIGINAL index,
 //                 so after the exchanges slot p holds reorder[p]; no rider arithmetic, no backward sweep.
 //                 (A is then read and written through `LU`; perm / parity / degenerate counts are stored.)
-template <typename T, int N, bool SOA, bool RM, bool DECOMP>
-__global__ void __launch_bounds__(kRowThreads, GMB_ROW_MIN_BLOCKS)
+template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G = row_group(N, (int)sizeof(T) / 4), int MINB = GMB_ROW_MIN_BLOCKS,
+          bool WANT_LU = true, bool SHFLX = false>
+__global__ void __launch_bounds__(kRowThreads, MINB)
 k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
             uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
             int64_t B) {
     constexpr int WORDS = (int)sizeof(T) / 4;
-    constexpr int G = row_group(N, WORDS);
     constexpr int RL = row_rl(N, G);
     constexpr int NC = N + 1;                                  // augmented row: n columns + the rider
     constexpr int V = soa_v<T>();                              // elements per 128-bit access
@@ -142,11 +149,41 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         const bool do_swap = pvt != i;
         parity = parity != do_swap;
         const int pl = pvt % G, ps = pvt / G;
+        // without an LU output the L part of a row (columns < i) is dead: only the 16-byte chunks from column i on travel
+        const int Q0 = WANT_LU ? 0 : i / V;
 
+        T piv[NC];
+        if constexpr (SHFLX) {
+            // Register-only exchange.  The pivot row sits in a slot that is only known at run time: each lane first
+            // collapses its candidate slots to ONE row with a select chain on (ps == k), then a shuffle from the
+            // pivot's lane broadcasts it; row i (static lane and slot) is broadcast the same way and the pivot's
+            // former owner drops it into slot ps with predicated moves.  No shared memory, no 128-bit register
+            // quads to keep aligned; costs ALU work instead of LSU wavefronts (the bounce-buffer form is LSU-bound).
+            const int c0 = WANT_LU ? 0 : i;
+            const int gbase = (int)(threadIdx.x & 31) & ~(G - 1);
+            const bool mine_is_pvt = do_swap && (lane_g == pl);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                if (c >= c0) {
+                    T v = a[oi_slot][c];
+#pragma unroll
+                    for (int k = oi_slot + 1; k < RL; ++k) v = (ps == k) ? a[k][c] : v;
+                    const T pc = __shfl_sync(0xffffffffu, v, gbase + pl);          // row pvt (= row i when !do_swap: ps, pl static then)
+                    const T ri = __shfl_sync(0xffffffffu, a[oi_slot][c], gbase + oi_lane);   // row i
+                    piv[c] = pc;
+#pragma unroll
+                    for (int k = oi_slot; k < RL; ++k) {
+                        const bool to_pvt = mine_is_pvt && (ps == k);
+                        const bool to_i = do_swap && (lane_g == oi_lane) && (k == oi_slot);
+                        a[k][c] = to_pvt ? ri : (to_i ? pc : a[k][c]);
+                    }
+                }
+            }
+        } else {
         // rows i and pvt -> bounce buffer (row i always: it is also the broadcast copy of the pivot row)
         if (lane_g == oi_lane) {
 #pragma unroll
-            for (int q = 0; q < NCH; ++q) {
+            for (int q = 0; q < NCH; ++q) if (q >= Q0) {
                 T t[V];
 #pragma unroll
                 for (int v = 0; v < V; ++v) t[v] = (q * V + v < NC) ? a[oi_slot][q * V + v] : (T)0;
@@ -157,7 +194,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         for (int k = oi_slot; k < RL; ++k) {
             if (do_swap && lane_g == pl && ps == k) {
 #pragma unroll
-                for (int q = 0; q < NCH; ++q) {
+                for (int q = 0; q < NCH; ++q) if (q >= Q0) {
                     T t[V];
 #pragma unroll
                     for (int v = 0; v < V; ++v) t[v] = (q * V + v < NC) ? a[k][q * V + v] : (T)0;
@@ -168,9 +205,8 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         __syncwarp();
         // pivot row (after the exchange) for everybody; the two owners also take their new rows
         const T* prow = do_swap ? buf1 : buf0;
-        T piv[NC];
 #pragma unroll
-        for (int q = 0; q < NCH; ++q) {
+        for (int q = 0; q < NCH; ++q) if (q >= Q0) {
             T t[V];
             unpack(reinterpret_cast<const VT*>(prow)[q], t);
 #pragma unroll
@@ -179,13 +215,14 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         }
         if (do_swap && lane_g == oi_lane) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) a[oi_slot][c] = piv[c];
+            for (int c = 0; c < NC; ++c)
+                if (c >= Q0 * V) a[oi_slot][c] = piv[c];
         }
 #pragma unroll
         for (int k = oi_slot; k < RL; ++k) {
             if (do_swap && lane_g == pl && ps == k) {
 #pragma unroll
-                for (int q = 0; q < NCH; ++q) {
+                for (int q = 0; q < NCH; ++q) if (q >= Q0) {
                     T t[V];
                     unpack(reinterpret_cast<const VT*>(buf0)[q], t);
 #pragma unroll
@@ -196,6 +233,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         }
         __syncwarp();
 
+        }
         // multipliers and rank-1 update of this lane's own rows below the pivot
         const T pv = piv[i];
 #pragma unroll
@@ -226,7 +264,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     constexpr int NSYS = 32 / G;
     constexpr int SA = stage_stride<N * N>();
     const int64_t s_warp0 = ((int64_t)blockIdx.x * kRowThreads + (threadIdx.x & ~31u)) / G;
-    if (!SOA && LU != nullptr && s_warp0 + NSYS <= B) {
+    if (WANT_LU && !SOA && LU != nullptr && s_warp0 + NSYS <= B) {
         T* smw = reinterpret_cast<T*>(gmb_dyn_smem) + (threadIdx.x >> 5) * (NSYS * SA);
         T* smd = smw + ((threadIdx.x & 31) / G) * SA;
 #pragma unroll
@@ -238,7 +276,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
             }
         }
         warp_stage_out<T, N * N, NSYS>(LU + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
-    } else if (LU != nullptr && valid) {
+    } else if (WANT_LU && LU != nullptr && valid) {
 #pragma unroll
         for (int k = 0; k < RL; ++k) {
             const int p = k * G + lane_g;
@@ -300,27 +338,44 @@ constexpr size_t row_stage_bytes() {
     return (size_t)(kRowThreads / 32) * (32 / row_group(N, (int)sizeof(T) / 4)) * stage_stride<N * N>() * sizeof(T);
 }
 
+// Exchange variant per (T, n) for the call WITHOUT an LU output (measured, profiles/r1h_row_exchange.md; 2^20 systems):
+// float: shuffle exchange with 2 lanes per system up to n = 14 and 4 lanes for n = 15, 16; double: shuffle exchange
+// with 2 lanes for n = 10..13, bounce buffer (trailing chunks only) elsewhere.
+template <typename T, int N> struct RowNoLu {
+    static constexpr int WORDS = (int)sizeof(T) / 4;
+    static constexpr bool shfl = WORDS == 1 ? true : (N >= 10 && N <= 13);
+    static constexpr int G = shfl ? ((WORDS == 1 && N >= 15) ? 4 : 2) : row_group(N, WORDS);
+    static constexpr int minb = (shfl && G == 4) ? 3 : GMB_ROW_MIN_BLOCKS;
+};
+
 template <typename T>
 int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout, int rm,
                       cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     dispatch_int<9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
-        constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
-        const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
-        if (grid == 0) {
+        if (B == 0) {
             rc = GMB_OK;
             return;
         }
         dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
             dispatch_bool(rm != 0, [&](auto RM) {
-                auto kern = k_row_solve<T, N.value, SOA.value, RM.value, false>;
-                const size_t smem = (SOA.value || LU == nullptr) ? 0 : row_stage_bytes<T, N.value>();
-                if (smem > 0) {   // static + dynamic may exceed the 48 KB default
-                    static bool raised = false;   // per instantiation
-                    if (!raised) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    raised = true;
+                if (LU == nullptr) {
+                    using P = RowNoLu<T, N.value>;
+                    auto kern = k_row_solve<T, N.value, SOA.value, RM.value, false, P::G, P::minb, false, P::shfl>;
+                    const unsigned grid = (unsigned)ceil_div(B * P::G, kRowThreads);
+                    kern<<<grid, kRowThreads, 0, st>>>(A, Bm, X, nullptr, ok, nullptr, nullptr, nullptr, skip, B);
+                } else {
+                    constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
+                    const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
+                    auto kern = k_row_solve<T, N.value, SOA.value, RM.value, false>;
+                    const size_t smem = SOA.value ? 0 : row_stage_bytes<T, N.value>();
+                    if (smem > 0) {   // static + dynamic may exceed the 48 KB default
+                        static bool raised = false;   // per instantiation
+                        if (!raised) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                        raised = true;
+                    }
+                    kern<<<grid, kRowThreads, smem, st>>>(A, Bm, X, LU, ok, nullptr, nullptr, nullptr, skip, B);
                 }
-                kern<<<grid, kRowThreads, smem, st>>>(A, Bm, X, LU, ok, nullptr, nullptr, nullptr, skip, B);
             });
         });
         rc = after_launch();

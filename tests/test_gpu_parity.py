@@ -70,6 +70,10 @@ def run_all(gm, port, n, A, b1, b3, S, soa, expect=None):
             check(down(x), e[1], f"linear_solve x {tag}")
             check(down(ok), e[2], f"linear_solve ok {tag}")
             check(down(lua), e[0], f"linear_solve a (LU) {tag}")
+            # the same call without the LU output takes its own kernels for n >= 9 (only the live part of a row is exchanged)
+            x_nolu, ok_nolu = gm.linear_solve(dA, db1, n, 1, 0, rm)
+            check(down(x_nolu), e[1], f"linear_solve (no LU output) x {tag}")
+            check(down(ok_nolu), e[2], f"linear_solve (no LU output) ok {tag}")
             x3, ok3 = gm.linear_solve(dA, db3, n, 3, 1, rm)
             e = (None, expect[f"solve3s1_{r}_x"], expect[f"solve3s1_{r}_ok"]) if expect is not None else port.linear_solve(A, b3, n, 3, 1, rm)
             check(down(x3), e[1], f"linear_solve m=3 skip=1 x {tag}")
