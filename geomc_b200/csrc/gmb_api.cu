@@ -438,7 +438,6 @@ int mul_api(int r, int k, int c, int64_t B, const T* A, const T* Bm, T* D, int a
     const bool fast = all_aligned16(A, Bm, D);
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && r <= 4 && k <= 4 && c <= 4) return mul_small<T>(r, k, c, B, A, Bm, D, flags, layout, as_stream(stream));
-    if (D == A || D == Bm) return GMB_ERR_INVALID_ARG;           // only the register shapes multiply in place
     return mul_generic<T>(r, k, c, B, A, Bm, D, flags, layout, as_stream(stream));
 }
 

@@ -35,7 +35,10 @@
 
 namespace gmb {
 
-constexpr int kRowThreads = 128;
+#ifndef GMB_ROW_THREADS
+#define GMB_ROW_THREADS 128
+#endif
+constexpr int kRowThreads = GMB_ROW_THREADS;
 #ifndef GMB_ROW_REG_BUDGET
 #define GMB_ROW_REG_BUDGET 140     // register words for the row block (picks G); measured: 140 beats 72 by 12-40%
 #endif
@@ -153,6 +156,9 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         const int Q0 = WANT_LU ? 0 : i / V;
 
         T piv[NC];
+#ifdef GMB_ROW_STEP_SYNC
+        if constexpr (SHFLX) __syncthreads();      // experiment: keep the block's warps on the same instruction-cache lines
+#endif
         if constexpr (SHFLX) {
             // Register-only exchange.  The pivot row sits in a slot that is only known at run time: each lane first
             // collapses its candidate slots to ONE row with a select chain on (ps == k), then a shuffle from the

@@ -81,9 +81,14 @@ k_mul_small(const T* A, const T* Bm, T* D, int flags, int64_t B) {
 }
 
 // ================================================================================ (f)4 mul, any shape up to 16
-// One thread per (system, row of D): the row of A sits in registers, B is read through L1 (every thread of a
-// warp works on the same row index of consecutive systems, so SoA planes are read coalesced).  D must not
-// alias A or B on this path.
+// A CTA of 128 threads takes S consecutive systems: A, B (and D for mul_acc) are staged into shared memory with
+// coalesced loads, each in its own flat order but with the inner dimension padded to 17 words (flat (q, m) at
+// q * 17 + m, zero filled): consecutive threads write consecutive banks whatever the layout flag, and the strided
+// reads below are conflict-free.  Each thread then owns one 4 x 4 tile of one system's D: per k it reads four a's
+// and four b's and issues 16 FMAs, k ascending (the reference's term order, MatrixMult.h:58-61).  Rows / columns
+// past the end read the zero padding and only feed tile entries that are never stored.  The tiles go back through shared memory in D's flat order and leave with coalesced stores.
+// Every input of a system is staged before any of its outputs is written and CTAs own disjoint systems, so D may
+// alias A or B here too.
 template <typename T>
 struct ElemAddr {
     int layout;
@@ -97,25 +102,121 @@ struct ElemAddr {
     }
 };
 
+constexpr int kMulThreads = 128;
+constexpr int kMulPad = 17;                                       // staged operands: flat (q, m) -> q * 17 + m: odd stride, no bank conflicts
+
+// n / d for n < 2^20, d <= 4096 with one multiply-high (the staging loops split flat indices by run-time sizes)
+struct FastDiv {
+    uint32_t d, m;
+    FastDiv() = default;
+    explicit FastDiv(int div) : d((uint32_t)div), m(div > 1 ? (uint32_t)((1ull << 32) / (uint32_t)div + 1) : 0) {}
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d > 1 ? __umulhi(n, m) : n; }
+    __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+struct MulShape {
+    int R, K, C, S;
+    FastDiv ea, a2, eb, b2, ed, s, tps, tc;      // R*K, (K|R), K*C, (C|K), R*C, S, threads per system, tiles per row
+};
+
 template <typename T>
-__global__ void __launch_bounds__(128)
-g_mul(int R, int K, int C, int64_t B, const T* __restrict__ A, const T* __restrict__ Bm, T* __restrict__ D, int flags,
-      int layout) {
-    const int64_t s = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    const int r = blockIdx.y;
-    if (s >= B) return;
+__global__ void __launch_bounds__(kMulThreads)
+k_mul_tiled(MulShape sh, int64_t B, const T* A, const T* Bm, T* D, int flags, int layout) {
+    extern __shared__ __align__(16) unsigned char gmb_mul_smem[];
+    const int R = sh.R, K = sh.K, C = sh.C, S = sh.S;
     const bool acc = flags & kMulAcc, arm = flags & kMulARm, brm = flags & kMulBRm, drm = flags & kMulDRm;
+    const int per_sys = 2 * 16 * kMulPad + R * C;                     // staged elements per system: A and B blocks of 16 x 17, then D
+    T* sm = reinterpret_cast<T*>(gmb_mul_smem);
+    const int64_t s0 = (int64_t)blockIdx.x * S;
+    const int ns = (int)min((int64_t)S, B - s0);
     const ElemAddr<T> ata{layout, R * K}, atb{layout, K * C}, atd{layout, R * C};
-    T arow[GMB_MAX_N];
+    const bool soa = layout == GMB_LAYOUT_SOA;
+
+    // ---- stage: consecutive threads take consecutive addresses (AoS) / consecutive systems of one plane (SoA).
+    // flat index -> (system in CTA, element): AoS idx = sl * E + e, SoA idx = e * S + sl.  Loads are issued in
+    // batches of U before any is stored (a plain load -> store loop would serialise on the global-memory latency).
+    // The padding is left uninitialised: whatever it holds only reaches tile entries that are never stored.
+    constexpr int U = 8;
+    auto stage = [&](const T* g, const ElemAddr<T>& at, int E, const FastDiv& fe, const FastDiv& f2, int dst_off, bool pad) {
+        for (int base = threadIdx.x; base < S * E; base += kMulThreads * U) {
+            T v[U];
+            uint32_t sl[U], e[U];
 #pragma unroll
-    for (int k = 0; k < GMB_MAX_N; ++k) arow[k] = k < K ? __ldg(A + ata(s, arm ? K * r + k : R * k + r)) : (T)0;
-    for (int c = 0; c < C; ++c) {
-        const int64_t di = atd(s, drm ? C * r + c : R * c + r);
-        T sum = acc ? D[di] : (T)0;
+            for (int u = 0; u < U; ++u) {
+                const uint32_t idx = (uint32_t)(base + u * kMulThreads);
+                if (soa) sh.s.divmod(idx, e[u], sl[u]);
+                else fe.divmod(idx, sl[u], e[u]);
+                const bool ok = idx < (uint32_t)(S * E) && (int)sl[u] < ns;
+                v[u] = ok ? g[at(s0 + (ok ? sl[u] : 0), (int)(ok ? e[u] : 0))] : (T)0;
+                if (!ok) sl[u] = 0xffffffffu;
+            }
 #pragma unroll
-        for (int k = 0; k < GMB_MAX_N; ++k)
-            if (k < K) sum = fma_rn(arow[k], __ldg(Bm + atb(s, brm ? C * k + c : K * c + k)), sum);
-        D[di] = sum;
+            for (int u = 0; u < U; ++u) {
+                if (sl[u] != 0xffffffffu) {
+                    uint32_t q = 0, m = e[u];
+                    if (pad) f2.divmod(e[u], q, m);
+                    sm[sl[u] * per_sys + dst_off + (pad ? q * kMulPad + m : e[u])] = v[u];
+                }
+            }
+        }
+    };
+    stage(A, ata, R * K, sh.ea, sh.a2, 0, true);
+    stage(Bm, atb, K * C, sh.eb, sh.b2, 16 * kMulPad, true);
+    if (acc) stage(D, atd, R * C, sh.ed, sh.ed, 2 * 16 * kMulPad, false);
+    __syncthreads();
+
+    // ---- one 4 x 4 tile per thread
+    uint32_t sl, tile, tr, tc;
+    sh.tps.divmod(threadIdx.x, sl, tile);
+    sh.tc.divmod(tile, tr, tc);
+    const int r0 = (int)tr * 4, c0 = (int)tc * 4;
+    const bool active = (int)sl < ns;
+    T d[4][4];
+    if (active) {
+        const T* sa = sm + sl * per_sys;
+        const T* sb = sa + 16 * kMulPad;
+        const T* sd = sb + 16 * kMulPad;
+        // a(r,k) and b(k,c) in the staged flat order: row-major (q, m) = (row, column), column-major the other way round
+        const int a_r = arm ? kMulPad : 1, a_k = arm ? 1 : kMulPad, b_k = brm ? kMulPad : 1, b_c = brm ? 1 : kMulPad;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + i, c = c0 + j;
+                d[i][j] = (acc && r < R && c < C) ? sd[drm ? C * r + c : R * c + r] : (T)0;
+            }
+        for (int k = 0; k < K; ++k) {
+            T a4[4], b4[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a4[i] = sa[(r0 + i) * a_r + k * a_k];
+                b4[i] = sb[k * b_k + (c0 + i) * b_c];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) d[i][j] = fma_rn(a4[i], b4[j], d[i][j]);       // MatrixMult.h:60
+        }
+    }
+    __syncthreads();                                                  // everyone is done reading D's staged copy
+    if (active) {
+        T* sd = sm + sl * per_sys + 2 * 16 * kMulPad;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = r0 + i, c = c0 + j;
+                if (r < R && c < C) sd[drm ? C * r + c : R * c + r] = d[i][j];
+            }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < S * R * C; idx += kMulThreads) {
+        uint32_t sl2, e;
+        if (soa) sh.s.divmod((uint32_t)idx, e, sl2);
+        else sh.ed.divmod((uint32_t)idx, sl2, e);
+        if ((int)sl2 < ns) D[atd(s0 + sl2, (int)e)] = sm[sl2 * per_sys + 2 * 16 * kMulPad + e];
     }
 }
 
@@ -364,8 +465,22 @@ template <typename T>
 int mul_generic(int r, int k, int c, int64_t B, const T* A, const T* Bm, T* D, int flags, int layout, cudaStream_t st) {
     int rc = GMB_OK;
     if (B > 0) {
-        dim3 grid((unsigned)ceil_div(B, 128), (unsigned)r);
-        g_mul<T><<<grid, 128, 0, st>>>(r, k, c, B, A, Bm, D, flags, layout);
+        const int tiles_c = (c + 3) / 4, tps = ((r + 3) / 4) * tiles_c;
+        const size_t per_sys = (size_t)(2 * 16 * kMulPad + r * c);
+        int S = kMulThreads / tps;
+        const int cap = (int)((48 * 1024) / (per_sys * sizeof(T)));
+        if (S > cap) S = cap;
+        if (layout == GMB_LAYOUT_SOA) {                    // keep a CTA inside one tile so that a plane segment is contiguous
+            const int W = soa_w<T>();
+            while (W % S != 0) --S;
+        }
+        MulShape sh;
+        sh.R = r; sh.K = k; sh.C = c; sh.S = S;
+        sh.ea = FastDiv(r * k); sh.a2 = FastDiv((flags & kMulARm) ? k : r);
+        sh.eb = FastDiv(k * c); sh.b2 = FastDiv((flags & kMulBRm) ? c : k);
+        sh.ed = FastDiv(r * c); sh.s = FastDiv(S); sh.tps = FastDiv(tps); sh.tc = FastDiv(tiles_c);
+        const unsigned grid = (unsigned)ceil_div(B, S);
+        k_mul_tiled<T><<<grid, kMulThreads, (size_t)S * per_sys * sizeof(T), st>>>(sh, B, A, Bm, D, flags, layout);
     }
     rc = after_launch();
     return rc;

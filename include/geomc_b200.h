@@ -199,8 +199,7 @@ int gmb_simplex_intersect_f64(int dim, int64_t B, const double* verts, int64_t v
  * running sum `sum = 0 (or D(i,j)); sum = fma(A(i,n), Bm(n,j), sum)` for n ascending, as the reference's build
  * evaluates `sum += a(r,n) * b(n,c)`.  c == 1 is matrix * Vec (MatrixMult.h:181-190), r == 1 is Vec * matrix
  * (:239-248).  Each operand has its own row_major flag (MatrixGlue.h:28-58).  1 <= r, k, c <= 16.
- * D may alias A or Bm when r, k, c <= 4 (the reference multiplies into a temporary then, Matrix.h:409-417);
- * for larger shapes aliasing returns GMB_ERR_INVALID_ARG. */
+ * D may alias A or Bm (the reference multiplies into a temporary then, Matrix.h:409-417). */
 int gmb_mul_f32(int r, int k, int c, int64_t B, const float* A, const float* Bm, float* D, int accumulate, int layout,
                 int a_row_major, int b_row_major, int d_row_major, void* stream);
 int gmb_mul_f64(int r, int k, int c, int64_t B, const double* A, const double* Bm, double* D, int accumulate, int layout,
