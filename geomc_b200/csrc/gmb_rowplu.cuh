@@ -62,8 +62,8 @@ template <> struct InfOf<double> { __device__ static __forceinline__ double get(
 //                 so after the exchanges slot p holds reorder[p]; no rider arithmetic, no backward sweep.
 //                 (A is then read and written through `LU`; perm / parity / degenerate counts are stored.)
 template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G = row_group(N, (int)sizeof(T) / 4), int MINB = GMB_ROW_MIN_BLOCKS,
-          bool WANT_LU = true, bool SHFLX = false>
-__global__ void __launch_bounds__(kRowThreads, MINB)
+          bool WANT_LU = true, bool SHFLX = false, int THREADS = kRowThreads>
+__global__ void __launch_bounds__(THREADS, MINB)
 k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
             uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
             int64_t B) {
@@ -78,11 +78,11 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     constexpr int ST = SOA ? soa_w<T>() : 1;
     using VT = typename VecOf<T>::type;
 
-    __shared__ __align__(16) uint32_t bounce[(kRowThreads / G) * GS];
+    __shared__ __align__(16) uint32_t bounce[(THREADS / G) * GS];
 
     const int lane_g = (G == 1) ? 0 : (int)(threadIdx.x % G);
     const int group = (int)(threadIdx.x / G);
-    int64_t s = ((int64_t)blockIdx.x * kRowThreads + threadIdx.x) / G;
+    int64_t s = ((int64_t)blockIdx.x * THREADS + threadIdx.x) / G;
     const bool valid = s < B;
     if (!valid) s = B - 1;                                     // keep all lanes for the shuffles / syncwarp
     T* buf0 = reinterpret_cast<T*>(bounce + group * GS);       // row i
@@ -156,9 +156,6 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         const int Q0 = WANT_LU ? 0 : i / V;
 
         T piv[NC];
-#ifdef GMB_ROW_STEP_SYNC
-        if constexpr (SHFLX) __syncthreads();      // experiment: keep the block's warps on the same instruction-cache lines
-#endif
         if constexpr (SHFLX) {
             // Register-only exchange.  The pivot row sits in a slot that is only known at run time: each lane first
             // collapses its candidate slots to ONE row with a select chain on (ps == k), then a shuffle from the
@@ -269,7 +266,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     extern __shared__ __align__(16) unsigned char gmb_dyn_smem[];
     constexpr int NSYS = 32 / G;
     constexpr int SA = stage_stride<N * N>();
-    const int64_t s_warp0 = ((int64_t)blockIdx.x * kRowThreads + (threadIdx.x & ~31u)) / G;
+    const int64_t s_warp0 = ((int64_t)blockIdx.x * THREADS + (threadIdx.x & ~31u)) / G;
     if (WANT_LU && !SOA && LU != nullptr && s_warp0 + NSYS <= B) {
         T* smw = reinterpret_cast<T*>(gmb_dyn_smem) + (threadIdx.x >> 5) * (NSYS * SA);
         T* smd = smw + ((threadIdx.x & 31) / G) * SA;
@@ -345,13 +342,15 @@ constexpr size_t row_stage_bytes() {
 }
 
 // Exchange variant per (T, n) for the call WITHOUT an LU output (measured, profiles/r1h_row_exchange.md; 2^20 systems):
-// float: shuffle exchange with 2 lanes per system up to n = 14 and 4 lanes for n = 15, 16; double: shuffle exchange
-// with 2 lanes for n = 10..13, bounce buffer (trailing chunks only) elsewhere.
+// float: shuffle exchange with 2 lanes per system up to n = 14, with 4 lanes and 256-thread CTAs for n = 15, 16;
+// double: shuffle exchange with 2 lanes for n = 10..14 (256-thread CTAs, one per SM's register file, from n = 13),
+// bounce buffer (trailing chunks only) for n = 9, 15, 16.
 template <typename T, int N> struct RowNoLu {
     static constexpr int WORDS = (int)sizeof(T) / 4;
-    static constexpr bool shfl = WORDS == 1 ? true : (N >= 10 && N <= 13);
+    static constexpr bool shfl = WORDS == 1 ? true : (N >= 10 && N <= 14);
     static constexpr int G = shfl ? ((WORDS == 1 && N >= 15) ? 4 : 2) : row_group(N, WORDS);
-    static constexpr int minb = (shfl && G == 4) ? 3 : GMB_ROW_MIN_BLOCKS;
+    static constexpr int threads = (shfl && ((WORDS == 1 && G == 4) || (WORDS == 2 && N >= 13))) ? 256 : kRowThreads;
+    static constexpr int minb = (WORDS == 2 && threads == 256) ? 1 : GMB_ROW_MIN_BLOCKS;
 };
 
 template <typename T>
@@ -367,9 +366,9 @@ int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* 
             dispatch_bool(rm != 0, [&](auto RM) {
                 if (LU == nullptr) {
                     using P = RowNoLu<T, N.value>;
-                    auto kern = k_row_solve<T, N.value, SOA.value, RM.value, false, P::G, P::minb, false, P::shfl>;
-                    const unsigned grid = (unsigned)ceil_div(B * P::G, kRowThreads);
-                    kern<<<grid, kRowThreads, 0, st>>>(A, Bm, X, nullptr, ok, nullptr, nullptr, nullptr, skip, B);
+                    auto kern = k_row_solve<T, N.value, SOA.value, RM.value, false, P::G, P::minb, false, P::shfl, P::threads>;
+                    const unsigned grid = (unsigned)ceil_div(B * P::G, P::threads);
+                    kern<<<grid, P::threads, 0, st>>>(A, Bm, X, nullptr, ok, nullptr, nullptr, nullptr, skip, B);
                 } else {
                     constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
                     const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);

@@ -126,6 +126,8 @@ int main(int argc, char** argv) {
     SHX(2, 1, false)
     SHX(2, 2, false)
     SHX(2, 2, true)
+    SHX(4, 1, false)
+    SHX(4, 2, false)
     SHX(4, 3, false)
     SHX(4, 4, false)
     SHX(8, 4, false)

@@ -41,11 +41,11 @@ static float time_ms(F&& f, int reps = 4) {
     return best;
 }
 
-template <typename T, int N, int G, int MINB, bool SHX>
+template <typename T, int N, int G, int MINB, bool SHX, int THREADS = 128>
 static float run(const T* A, const T* b, T* x, uint8_t* ok, int64_t B) {
-    auto kern = k_row_solve<T, N, false, true, false, G, MINB, false, SHX>;
-    const unsigned grid = (unsigned)((B * G + kRowThreads - 1) / kRowThreads);
-    float ms = time_ms([&] { kern<<<grid, kRowThreads>>>(A, b, x, nullptr, ok, nullptr, nullptr, nullptr, 0, B); });
+    auto kern = k_row_solve<T, N, false, true, false, G, MINB, false, SHX, THREADS>;
+    const unsigned grid = (unsigned)((B * G + THREADS - 1) / THREADS);
+    float ms = time_ms([&] { kern<<<grid, THREADS>>>(A, b, x, nullptr, ok, nullptr, nullptr, nullptr, 0, B); });
     CK(cudaGetLastError());
     return ms;
 }
@@ -82,15 +82,16 @@ static void sweep(int64_t B) {
     CK(cudaMemcpy(hok0.data(), ok0, B, cudaMemcpyDeviceToHost));
     float t2 = run<T, N, 2, 2, true>(A, b, x, ok, B);   int b2 = check();
     float t4 = run<T, N, 4, 3, true>(A, b, x, ok, B);   int b4 = check();
-    float t8 = run<T, N, 8, 4, true>(A, b, x, ok, B);   int b8 = check();
-    printf("| %s | %2d | %d | %.3f | %.3f | %.3f | %.3f | %d |\n", sizeof(T) == 4 ? "float" : "double", N, G0, t0, t2, t4, t8, b2 + b4 + b8);
+    float t8 = run<T, N, 2, 1, true, 256>(A, b, x, ok, B);   int b8 = check();
+    float t9 = run<T, N, 4, 2, true, 256>(A, b, x, ok, B);   int b9 = check();
+    printf("| %s | %2d | %d | %.3f | %.3f | %.3f | %.3f | %.3f | %d |\n", sizeof(T) == 4 ? "float" : "double", N, G0, t0, t2, t4, t8, t9, b2 + b4 + b8 + b9);
     fflush(stdout);
     cudaFree(A); cudaFree(b); cudaFree(x0); cudaFree(x); cudaFree(ok0); cudaFree(ok);
 }
 
 int main(int argc, char** argv) {
     const int64_t B = argc > 1 ? atoll(argv[1]) : (1 << 20);
-    printf("| type | n | bounce G | bounce ms | shuffle G=2 ms | shuffle G=4 ms | shuffle G=8 ms | mismatches |\n|---|---|---|---|---|---|---|---|\n");
+    printf("| type | n | bounce G | bounce ms | shuffle G=2 ms | shuffle G=4 ms | shuffle G=2, 256 thr | shuffle G=4, 256 thr | mismatches |\n|---|---|---|---|---|---|---|---|---|\n");
 #define BOTH(N) sweep<float, N>(B); sweep<double, N>(B);
     BOTH(9) BOTH(10) BOTH(11) BOTH(12) BOTH(13) BOTH(14) BOTH(15) BOTH(16)
     return 0;
