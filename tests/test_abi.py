@@ -45,6 +45,16 @@ def test_argument_validation_and_no_cpu_fallback():
     assert L.gmb_plu_solve_f32(4, 1, 8, None, None, None, None, None, 0, 0, 1, None) == -1
     assert L.gmb_plu_solve_f32(4, 1, 8, None, None, None, None, None, 0, 7, 1, None) == -1
     assert L.gmb_plu_solve_f32(17, 1, 0, None, None, None, None, None, 0, 0, 1, None) == -2
+    # rows (f)3 / (f)4: shapes, dimensions, modes, transform counts and aliasing are checked the same way
+    assert L.gmb_mul_f32(4, 4, 4, 8, None, None, None, 0, 0, 1, 1, 1, None) == -1
+    assert L.gmb_mul_f64(17, 4, 4, 0, None, None, None, 0, 0, 1, 1, 1, None) == -2
+    assert L.gmb_mul_f64(0, 4, 4, 0, None, None, None, 0, 0, 1, 1, 1, None) == -1
+    assert L.gmb_xf_from_matrix_f32(8, 0, None, None, None, 0, 1, None) == -2        # dimensions 2..7
+    assert L.gmb_xf_from_matrix_f32(3, 4, None, None, None, 0, 1, None) == -1
+    assert L.gmb_xf_apply_f64(3, 6, 0, None, 0, None, None, 0, None) == -1           # mode 0..5
+    assert L.gmb_xf_apply_f64(3, 0, 5, 16, 2, 16, 16, 0, None) == -1                 # one transform, or one per point
+    assert L.gmb_xf_compose_f32(3, 5, 16, 32, 16, 0, 0, None) == -1                  # out must not alias an input
+    assert L.gmb_xf_translation_f32(1, 0, None, None, 0, None) == -2
     if L.gmb_device_count() == 0:
         a = np.zeros((8, 16), np.float32)
         b = np.zeros((8, 4), np.float32)

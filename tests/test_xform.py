@@ -277,6 +277,36 @@ def test_gpu_xf_equals_oracle(dt, soa):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_gpu_empty_and_tiny_batches(dt):
+    """B = 0 launches nothing and returns empty results; B = 1 and a ragged B = 3 match the oracle in both layouts."""
+    torch, gm = _gm()
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    port = po.port()
+    N = 3
+    E = 2 * (N + 1) ** 2
+    for soa in (False, True):
+        empty = (lambda e: gm.BatchSoA(0, e, tdt)) if soa else (lambda e: torch.empty((0, e), dtype=tdt, device="cuda"))
+        assert _host(gm.mul(empty(16), empty(16), 4, 4, 4)).shape == (0, 16)
+        assert _host(gm.mul(empty(81), empty(81), 9, 9, 9)).shape == (0, 81)
+        xf, ok = gm.xf_from_matrix(empty(N * N), N)
+        assert _host(xf).shape == (0, E) and ok.shape == (0,)
+        assert _host(gm.xf_compose(empty(E), empty(E), N)).shape == (0, E)
+        assert _host(gm.xf_apply(empty(E), empty(N), N)).shape == (0, N)
+        impl = GpuImpl(soa)
+        rng = np.random.default_rng(8)
+        for B in (1, 3):
+            m = rng.standard_normal((B, N * N)).astype(dt)
+            p = rng.standard_normal((B, N)).astype(dt)
+            xm = port.xf_from_matrix(m, N)[0]
+            eq(impl.xf_from_matrix(m, N)[0], xm, f"B={B} transformation")
+            eq(impl.xf_apply(xm, p, N, "apply_inverse"), port.xf_apply(xm, p, N, "apply_inverse"), f"B={B} apply_inverse")
+            a = rng.standard_normal((B, 35)).astype(dt)
+            b = rng.standard_normal((B, 15)).astype(dt)
+            eq(impl.mul(a, b, 7, 5, 3), port.mul(a, b, 7, 5, 3), f"B={B} mul 7x5x3")
+
+
+@pytest.mark.gpu
 def test_gpu_inverse_round_trip_full_size():
     """Size-independent property at 2^22 systems: inv on the device, then M * M^-1 on the device, is the identity."""
     torch, gm = _gm()
