@@ -118,7 +118,7 @@ struct FastDiv {
 };
 struct MulShape {
     int R, K, C, S;
-    FastDiv ea, a2, eb, b2, ed, s, tps, tc;      // R*K, (K|R), K*C, (C|K), R*C, S, threads per system, tiles per row
+    FastDiv ea, a2, eb, b2, ed, s, tps, tc, sv;  // R*K, (K|R), K*C, (C|K), R*C, S, threads per system, tiles per row, S / V
 };
 
 template <typename T>
@@ -162,9 +162,86 @@ k_mul_tiled(MulShape sh, int64_t B, const T* A, const T* Bm, T* D, int flags, in
             }
         }
     };
-    stage(A, ata, R * K, sh.ea, sh.a2, 0, true);
-    stage(Bm, atb, K * C, sh.eb, sh.b2, 16 * kMulPad, true);
-    if (acc) stage(D, atd, R * C, sh.ed, sh.ed, 2 * 16 * kMulPad, false);
+    // AoS fast path: the CTA's S records are ONE contiguous range; when the inner dimension is a multiple of the
+    // vector width a 128-bit load never straddles a row, so one index split serves V elements.
+    constexpr int V = soa_v<T>();
+    using VT = typename VecOf<T>::type;
+    auto stage_vec = [&](const T* g, int E, int inner, const FastDiv& fe, const FastDiv& f2, int dst_off, bool pad) {
+        const VT* gv = reinterpret_cast<const VT*>(g + s0 * (int64_t)E);
+        const int nvec = ns * E / V;
+        for (int base = threadIdx.x; base < nvec; base += kMulThreads * U) {
+            VT v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kMulThreads;
+                if (i < nvec) v[u] = __ldg(gv + i);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kMulThreads;
+                if (i < nvec) {
+                    uint32_t sl, e, q = 0, m;
+                    fe.divmod((uint32_t)(i * V), sl, e);
+                    m = e;
+                    if (pad) f2.divmod(e, q, m);
+                    T t[V];
+                    unpack(v[u], t);
+                    T* dst = sm + sl * per_sys + dst_off + (pad ? q * kMulPad + m : e);
+#pragma unroll
+                    for (int w = 0; w < V; ++w) dst[w] = t[w];
+                }
+            }
+        }
+    };
+    // SoA fast path: a 128-bit load covers V consecutive systems of one element plane (the CTA's systems sit inside
+    // one tile and start on a multiple of V); one index split serves V systems.
+    auto stage_vec_soa = [&](const T* g, int E, const FastDiv& f2, int dst_off, bool pad) {
+        constexpr int W = soa_w<T>();
+        const T* tile = g + (s0 / W) * (int64_t)(E * W) + (s0 % W);
+        const int svec = S / V, nvec = E * svec;
+        for (int base = threadIdx.x; base < nvec; base += kMulThreads * U) {
+            VT v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kMulThreads;
+                if (i < nvec) {
+                    uint32_t e, j;
+                    sh.sv.divmod((uint32_t)i, e, j);
+                    v[u] = __ldg(reinterpret_cast<const VT*>(tile + (int64_t)e * W) + j);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = base + u * kMulThreads;
+                if (i < nvec) {
+                    uint32_t e, j, q = 0, m;
+                    sh.sv.divmod((uint32_t)i, e, j);
+                    m = e;
+                    if (pad) f2.divmod(e, q, m);
+                    T t[V];
+                    unpack(v[u], t);
+                    T* dst = sm + (j * V) * per_sys + dst_off + (pad ? q * kMulPad + m : e);
+#pragma unroll
+                    for (int w = 0; w < V; ++w) dst[w * per_sys] = t[w];
+                }
+            }
+        }
+    };
+    const bool soa_vec = soa && ns == S && S % V == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 &&
+                         (reinterpret_cast<uintptr_t>(Bm) & 15) == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0;
+    auto vec_ok = [&](const T* g, int E, int inner) {
+        return !soa && inner % V == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && ((int64_t)S * E) % V == 0;
+    };
+    if (soa_vec) stage_vec_soa(A, R * K, sh.a2, 0, true);
+    else if (vec_ok(A, R * K, arm ? K : R)) stage_vec(A, R * K, arm ? K : R, sh.ea, sh.a2, 0, true);
+    else stage(A, ata, R * K, sh.ea, sh.a2, 0, true);
+    if (soa_vec) stage_vec_soa(Bm, K * C, sh.b2, 16 * kMulPad, true);
+    else if (vec_ok(Bm, K * C, brm ? C : K)) stage_vec(Bm, K * C, brm ? C : K, sh.eb, sh.b2, 16 * kMulPad, true);
+    else stage(Bm, atb, K * C, sh.eb, sh.b2, 16 * kMulPad, true);
+    if (acc) {
+        if (soa_vec) stage_vec_soa(D, R * C, sh.ed, 2 * 16 * kMulPad, false);
+        else stage(D, atd, R * C, sh.ed, sh.ed, 2 * 16 * kMulPad, false);
+    }
     __syncthreads();
 
     // ---- one 4 x 4 tile per thread
@@ -212,6 +289,30 @@ k_mul_tiled(MulShape sh, int64_t B, const T* A, const T* Bm, T* D, int flags, in
             }
     }
     __syncthreads();
+    if (!soa && (R * C) % V == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0 && ((int64_t)S * R * C) % V == 0 && per_sys % V == 0) {
+        VT* gv = reinterpret_cast<VT*>(D + s0 * (int64_t)(R * C));
+        const int nvec = ns * R * C / V;
+        for (int i = threadIdx.x; i < nvec; i += kMulThreads) {
+            uint32_t sl2, e;
+            sh.ed.divmod((uint32_t)(i * V), sl2, e);
+            gv[i] = *reinterpret_cast<const VT*>(sm + sl2 * per_sys + 2 * 16 * kMulPad + e);
+        }
+        return;
+    }
+    if (soa_vec) {
+        constexpr int W = soa_w<T>();
+        T* tile = D + (s0 / W) * (int64_t)(R * C * W) + (s0 % W);
+        const int svec = S / V, nvec = R * C * svec;
+        for (int i = threadIdx.x; i < nvec; i += kMulThreads) {
+            uint32_t e, j;
+            sh.sv.divmod((uint32_t)i, e, j);
+            T t[V];
+#pragma unroll
+            for (int w = 0; w < V; ++w) t[w] = sm[(j * V + w) * per_sys + 2 * 16 * kMulPad + e];
+            reinterpret_cast<VT*>(tile + (int64_t)e * W)[j] = pack(t);
+        }
+        return;
+    }
     for (int idx = threadIdx.x; idx < S * R * C; idx += kMulThreads) {
         uint32_t sl2, e;
         if (soa) sh.s.divmod((uint32_t)idx, e, sl2);
@@ -478,7 +579,7 @@ int mul_generic(int r, int k, int c, int64_t B, const T* A, const T* Bm, T* D, i
         sh.R = r; sh.K = k; sh.C = c; sh.S = S;
         sh.ea = FastDiv(r * k); sh.a2 = FastDiv((flags & kMulARm) ? k : r);
         sh.eb = FastDiv(k * c); sh.b2 = FastDiv((flags & kMulBRm) ? c : k);
-        sh.ed = FastDiv(r * c); sh.s = FastDiv(S); sh.tps = FastDiv(tps); sh.tc = FastDiv(tiles_c);
+        sh.ed = FastDiv(r * c); sh.s = FastDiv(S); sh.tps = FastDiv(tps); sh.tc = FastDiv(tiles_c); sh.sv = FastDiv(S >= soa_v<T>() ? S / soa_v<T>() : 1);
         const unsigned grid = (unsigned)ceil_div(B, S);
         k_mul_tiled<T><<<grid, kMulThreads, (size_t)S * per_sys * sizeof(T), st>>>(sh, B, A, Bm, D, flags, layout);
     }

@@ -87,6 +87,28 @@ def run(case):
         A, b = gm.BatchSoA.from_aos(grid((B, 256), f32)), gm.BatchSoA.from_aos(grid((B, 16), f32))
         x, ok = b.empty_like(), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
+    if case in ("mul4", "mul16"):         # batched mul, SoA 4x4x4 float / AoS 16x16x16 float
+        n = 4 if case == "mul4" else 16
+        B = 1 << (24 if n == 4 else 19)
+        a, b = grid((B, n * n), f32), grid((B, n * n), f32)
+        if n == 4:
+            a, b = gm.BatchSoA.from_aos(a), gm.BatchSoA.from_aos(b)
+        d = a.empty_like() if n == 4 else torch.empty_like(a)
+        return lambda: gm.mul(a, b, n, n, n, out=d)
+    if case in ("xf3", "apply3", "apply3one", "compose3"):   # AffineTransform<float,3>, SoA containers, 2^23 transforms / points
+        B = 1 << 23
+        m = gm.BatchSoA.from_aos(grid((B, 9), f32) + 3 * torch.eye(3, device=dev).reshape(1, 9))
+        if case == "xf3":
+            return lambda: gm.xf_from_matrix(m, 3)
+        xm, _ = gm.xf_from_matrix(m, 3)
+        p = gm.BatchSoA.from_aos(grid((B, 3), f32))
+        if case == "apply3":
+            return lambda: gm.xf_apply(xm, p, 3, "apply")
+        if case == "compose3":
+            xt = gm.xf_translation(p, 3)
+            return lambda: gm.xf_compose(xt, xm, 3)
+        one = xm.to_aos()[5:6].contiguous()
+        return lambda: gm.xf_apply(one, p, 3, "apply")
     raise SystemExit(f"unknown case {case}")
 
 
