@@ -56,7 +56,7 @@ template <typename T> int xf_apply(int, int, int64_t, const T*, bool, const T*, 
 // profiles/r1d_row_vs_column.md, profiles/r1h_row_exchange.md).  With an LU output the row-distributed kernel
 // (bounce-buffer exchange of whole rows) wins for float n in {12, 14, 15, 16} and for double n = 10 and n >= 12;
 // without one -- the common call -- only the live part of a row travels and the register-only shuffle exchange
-// applies: the row kernel then wins for every float n >= 9 and every double n >= 10.
+// applies: the row kernel then wins for every float n >= 8 and for double n = 7, 8 and n >= 10.
 // GMB_ROWPLU_MIN_N=<n> in the environment overrides the table (17 disables the row kernel, 9 forces it).
 template <typename T>
 static bool use_row_kernel(int n, bool want_lu) {
@@ -65,7 +65,8 @@ static bool use_row_kernel(int n, bool want_lu) {
         return e ? std::atoi(e) : -1;
     }();
     if (forced >= 0) return n >= forced;
-    if (!want_lu) return sizeof(T) == 4 ? n >= 9 : n >= 10;
+    if (!want_lu) return sizeof(T) == 4 ? n >= 8 : (n == 7 || n == 8 || n >= 10);
+    if (n < 9) return false;
     if (sizeof(T) == 4) return n == 12 || n >= 14;
     return n == 10 || n >= 12;
 }
@@ -151,7 +152,7 @@ int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* o
         int rc = small_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
-    if (fast && m == 1 && n >= 9 && use_row_kernel<T>(n, LU != nullptr)) {
+    if (fast && m == 1 && n >= 7 && use_row_kernel<T>(n, LU != nullptr)) {
         int rc = rowplu_solve<T>(n, B, A, Bm, X, ok, LU, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }

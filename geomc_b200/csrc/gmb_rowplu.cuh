@@ -344,11 +344,12 @@ constexpr size_t row_stage_bytes() {
 // Exchange variant per (T, n) for the call WITHOUT an LU output (measured, profiles/r1h_row_exchange.md; 2^20 systems):
 // float: shuffle exchange with 2 lanes per system up to n = 14, with 4 lanes and 256-thread CTAs for n = 15, 16;
 // double: shuffle exchange with 2 lanes for n = 10..14 (256-thread CTAs, one per SM's register file, from n = 13),
-// bounce buffer (trailing chunks only) for n = 9, 15, 16.
+// bounce buffer (trailing chunks only) for n = 9, 15, 16.  Below 9 the column-distributed kernel is the default; the row
+// kernel takes 8 x 8 (2 lanes: float 0.68 -> 0.39 ms, double 1.38 -> 0.92 ms per 2^22 systems) and double 7 x 7 (one lane).
 template <typename T, int N> struct RowNoLu {
     static constexpr int WORDS = (int)sizeof(T) / 4;
-    static constexpr bool shfl = WORDS == 1 ? true : (N >= 10 && N <= 14);
-    static constexpr int G = shfl ? ((WORDS == 1 && N >= 15) ? 4 : 2) : row_group(N, WORDS);
+    static constexpr bool shfl = WORDS == 1 ? true : (N <= 8 || (N >= 10 && N <= 14));
+    static constexpr int G = !shfl ? row_group(N, WORDS) : (N <= 7 ? 1 : ((WORDS == 1 && N >= 15) ? 4 : 2));
     static constexpr int threads = (shfl && ((WORDS == 1 && G == 4) || (WORDS == 2 && N >= 13))) ? 256 : kRowThreads;
     static constexpr int minb = (WORDS == 2 && threads == 256) ? 1 : GMB_ROW_MIN_BLOCKS;
 };
@@ -357,7 +358,7 @@ template <typename T>
 int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout, int rm,
                       cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
-    dispatch_int<9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+    dispatch_int<7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
         if (B == 0) {
             rc = GMB_OK;
             return;

@@ -84,15 +84,18 @@ static void sweep(int64_t B) {
     float t4 = run<T, N, 4, 3, true>(A, b, x, ok, B);   int b4 = check();
     float t8 = run<T, N, 2, 1, true, 256>(A, b, x, ok, B);   int b8 = check();
     float t9 = run<T, N, 4, 2, true, 256>(A, b, x, ok, B);   int b9 = check();
-    printf("| %s | %2d | %d | %.3f | %.3f | %.3f | %.3f | %.3f | %d |\n", sizeof(T) == 4 ? "float" : "double", N, G0, t0, t2, t4, t8, t9, b2 + b4 + b8 + b9);
+    float t1 = 0;
+    if constexpr (N <= 8) { t1 = run<T, N, 1, 2, true>(A, b, x, ok, B); b9 += check(); }
+    printf("| %s | %2d | %d | %.3f | %.3f | %.3f | %.3f | %.3f | %.3f | %d |\n", sizeof(T) == 4 ? "float" : "double", N, G0, t0, t2, t4, t8, t9, t1, b2 + b4 + b8 + b9);
     fflush(stdout);
     cudaFree(A); cudaFree(b); cudaFree(x0); cudaFree(x); cudaFree(ok0); cudaFree(ok);
 }
 
 int main(int argc, char** argv) {
     const int64_t B = argc > 1 ? atoll(argv[1]) : (1 << 20);
-    printf("| type | n | bounce G | bounce ms | shuffle G=2 ms | shuffle G=4 ms | shuffle G=2, 256 thr | shuffle G=4, 256 thr | mismatches |\n|---|---|---|---|---|---|---|---|---|\n");
+    printf("| type | n | bounce G | bounce ms | shuffle G=2 ms | shuffle G=4 ms | shuffle G=2, 256 thr | shuffle G=4, 256 thr | shuffle G=1 | mismatches |\n|---|---|---|---|---|---|---|---|---|---|\n");
 #define BOTH(N) sweep<float, N>(B); sweep<double, N>(B);
+    if (argc > 2) { BOTH(5) BOTH(6) BOTH(7) BOTH(8) return 0; }
     BOTH(9) BOTH(10) BOTH(11) BOTH(12) BOTH(13) BOTH(14) BOTH(15) BOTH(16)
     return 0;
 }

@@ -78,7 +78,7 @@ def run(case):
     if case.startswith("solve"):          # solve<f|d><n>: fused PLU solve, AoS, n x n
         dt = f32 if case[5] == "f" else f64
         n = int(case[6:])
-        B = 1 << 20
+        B = int(os.environ.get("PROF_B", 1 << 20))
         A, b = grid((B, n * n), dt), grid((B, n), dt)
         x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, n, x_out=x, ok_out=ok)

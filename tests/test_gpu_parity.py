@@ -290,7 +290,7 @@ def test_both_large_n_solve_kernels(force):
 
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("n", [2, 4, 6, 9, 12, 16])
+@pytest.mark.parametrize("n", [2, 4, 6, 7, 8, 9, 12, 15, 16])
 def test_skip_rows_single_rhs(gm, port, dt, n, soa):
     """`skip` > 0 with ONE right-hand side goes through the register / column / row kernels (the m = 3
     cases above take the generic path): rows < skip keep their forward-substituted values
