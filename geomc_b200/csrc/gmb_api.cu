@@ -29,6 +29,7 @@ template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*
 // gmb_rowplu_*.cu
 template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
+template <typename T> int rowinv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int row_backsolve(int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
 // gmb_generic.cu
 template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
@@ -211,6 +212,18 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
         // adjugate path only exists in the register kernels (the generic kernel is PLU-based and would
         // change the arithmetic): an unaligned AoS batch is rejected rather than computed differently
         return fast ? small_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st) : GMB_ERR_INVALID_ARG;
+    }
+    // The row-distributed kernel (gmb_rowinv.cuh) is 1.2x (7 x 7 double) to 3x (16 x 16 float) faster than the
+    // column-distributed one from n = 8 (float) / n = 6 (double) on and slower below (profiles/r1j_row_inverse.md);
+    // GMB_ROWINV=0 / 1 forces the column / row kernel for every n >= 5 (tests).
+    static const int row_inv = [] {
+        const char* e = std::getenv("GMB_ROWINV");
+        return !e ? -1 : (e[0] == '0' ? 0 : 1);
+    }();
+    const bool use_row_inv = row_inv >= 0 ? row_inv == 1 : n >= (sizeof(T) == 4 ? 8 : 6);
+    if (fast && n >= 5 && use_row_inv) {
+        int rc = rowinv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     if (fast && n >= 5) {
         int rc = subwarp_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);

@@ -288,6 +288,23 @@ def test_both_large_n_solve_kernels(force):
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
 
 
+@pytest.mark.parametrize("force", ["0", "1"])
+def test_both_large_n_inverse_kernels(force):
+    """inv for n >= 5 has a row-distributed (gmb_rowinv.cuh) and a column-distributed kernel; the dispatcher picks per
+    (type, n).  GMB_ROWINV=0 / 1 forces one for every n: rerun the oracle comparison for n = 5..16 in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GMB_ROWINV=force)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = " or ".join(f"{n}-" for n in range(5, 17))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
+                        "-k", f"test_random_vs_oracle and ({sel})"],
+                       env=env, capture_output=True, text=True, cwd=root, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [2, 4, 6, 7, 8, 9, 12, 15, 16])
