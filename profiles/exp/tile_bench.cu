@@ -1,7 +1,7 @@
 // Experiment harness for the shared-memory resident fused PLU solve (gmb_tile.cuh) against the production register
 // kernel (gmb_rowplu.cuh), float, AoS, row-major: times both on the same random batch and compares bit for bit.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false --expt-relaxed-constexpr \
-//        -I geomc_b200/csrc profiles/exp/tile_bench.cu -o profiles/exp/tile_bench
+//        -I geomc_b200/csrc -I profiles/exp profiles/exp/tile_bench.cu -o profiles/exp/tile_bench
 //   profiles/exp/tile_bench [systems] [n|0 = all]
 #include <cstdio>
 #include <cstdlib>
@@ -10,6 +10,7 @@
 
 #include "gmb_rowplu.cuh"
 #include "gmb_tile.cuh"
+#include "gmb_tile4.cuh"
 
 namespace gmb { std::atomic<int64_t> g_launch_count{0}; }
 using namespace gmb;
@@ -48,6 +49,17 @@ static float run_tile(const float* A, const float* b, float* x, uint8_t* ok, int
     constexpr size_t smem = tile_smem_bytes<float, N, NT>();
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((B + NT - 1) / NT);
+    float ms = time_ms([&] { kern<<<grid, NT, smem>>>(A, b, x, ok, 0, B); });
+    CK(cudaGetLastError());
+    return ms;
+}
+
+template <int NT, int MINB>
+static float run_tile4(const float* A, const float* b, float* x, uint8_t* ok, int64_t B) {
+    auto kern = k_tile4_solve<false, NT, MINB>;
+    constexpr size_t smem = tile4_smem_bytes<NT>();
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((B + NT / 4 - 1) / (NT / 4));
     float ms = time_ms([&] { kern<<<grid, NT, smem>>>(A, b, x, ok, 0, B); });
     CK(cudaGetLastError());
     return ms;
@@ -117,6 +129,16 @@ static void bench(int64_t B) {
         float ms = run_tile<N, NT_, MB_>(A, b, x, ok, B);                             \
         report("tile NT=" #NT_ " minb=" #MB_, ms, true);                              \
     }
+#define TILE4(NT_, MB_)                                                               \
+    if constexpr (N == 16) {                                                          \
+        CK(cudaMemset(x, 0, B * N * 4)); CK(cudaMemset(ok, 7, B));                    \
+        float ms = run_tile4<NT_, MB_>(A, b, x, ok, B);                               \
+        report("tile4 NT=" #NT_ " minb=" #MB_, ms, true);                             \
+    }
+    TILE4(128, 1)
+    TILE4(128, 6)
+    TILE4(256, 3)
+    TILE4(64, 1)
     TILE(32, 1)
     { float ms = run_tile<N, 32, 1, 1>(A, b, x, ok, B); report("tile NT=32 ingest only", ms, false); }
     { float ms = run_tile<N, 32, 1, 2>(A, b, x, ok, B); report("tile NT=32 no ingest", ms, false); }
