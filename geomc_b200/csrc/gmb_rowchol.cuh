@@ -64,17 +64,43 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
         const T d = sqrt_rn(sdiag);
         if (lane_g == ok_lane) a[ok_slot][k] = d;
         // column k of L for this lane's rows below k (Cholesky.h:50)
+        // one reciprocal of L(k,k) for the whole column and the rider (RcpOf, gmb_math.cuh): same bits as div_rn
+        const RcpOf<T> rcd(d);
+        T vq[RL];
+        T ykq = (T)0;
+        {
+            bool all_ok = true;
+#pragma unroll
+            for (int sl = 0; sl < RL; ++sl) {
+                if (sl >= ok_slot) {                           // static
+                    const int p = sl * G + lane_g;
+                    bool okq;
+                    vq[sl] = rcd.fast(a[sl][k], okq);
+                    all_ok = all_ok && (okq || !(p > k && p < N));
+                }
+            }
+            if (SOLVE) {
+                bool okq;
+                ykq = rcd.fast(y[ok_slot], okq);
+                all_ok = all_ok && (okq || lane_g != ok_lane);
+            }
+            if (!all_ok) {
+#pragma unroll
+                for (int sl = 0; sl < RL; ++sl)
+                    if (sl >= ok_slot) vq[sl] = div_rn(a[sl][k], d);
+                if (SOLVE) ykq = div_rn(y[ok_slot], d);
+            }
+        }
 #pragma unroll
         for (int sl = 0; sl < RL; ++sl) {
             if (sl >= ok_slot) {                               // static
                 const int p = sl * G + lane_g;
-                const T v = div_rn(a[sl][k], d);
+                const T v = vq[sl];
                 if (p > k && p < N) a[sl][k] = v;
             }
         }
         if (SOLVE) {
             // forward substitution: y(k) = b(k) / L(k,k), then b(r) -= y(k) L(r,k) for r > k
-            const T ykq = div_rn(y[ok_slot], d);
             const T yk = (G == 1) ? ykq : __shfl_sync(0xffffffffu, ykq, ok_lane, G);
             if (lane_g == ok_lane) y[ok_slot] = yk;
 #pragma unroll

@@ -119,11 +119,30 @@ k_row_inv(const T* __restrict__ A, T* __restrict__ Ainv, uint8_t* __restrict__ o
 
         // multipliers and updates of this lane's own rows below the pivot (:232-246); riders never skipped
         const T pv = piv[i];
+        T bq[RL];
+        // one reciprocal per pivot (RcpOf, gmb_math.cuh) when a lane has three or more rows to divide; with fewer the
+        // replicated reciprocal costs what it saves (double n >= 13, eight lanes: -6 .. -17 % measured)
+        constexpr bool SRCP = RL >= 3;
+        if constexpr (SRCP) {
+            const RcpOf<T> rc(pv);
+            bool all_ok = true;
+#pragma unroll
+            for (int k = oi_slot; k < RL; ++k) {
+                const int p = k * G + lane_g;
+                bool ok;
+                bq[k] = rc.fast(a[k][i], ok);
+                all_ok = all_ok && (ok || !((p > i) && (p < N)));
+            }
+            if (!all_ok) {
+#pragma unroll
+                for (int k = oi_slot; k < RL; ++k) bq[k] = div_rn(a[k][i], pv);
+            }
+        }
 #pragma unroll
         for (int k = oi_slot; k < RL; ++k) {
             const int p = k * G + lane_g;
             const bool below = (p > i) && (p < N) && !dead;
-            const T b = div_rn(a[k][i], pv);
+            const T b = SRCP ? bq[k] : div_rn(a[k][i], pv);
             const bool upd = below && (b != (T)0);
 #pragma unroll
             for (int c = i + 1; c < N; ++c) {
@@ -149,9 +168,10 @@ k_row_inv(const T* __restrict__ A, T* __restrict__ Ainv, uint8_t* __restrict__ o
     for (int c = N - 1; c >= 0; --c) {
         const int oc_lane = c % G, oc_slot = c / G;            // static
         if constexpr (G == 1) {
+            const RcpOf<T> rc(a[oc_slot][c]);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const T q = div_rn(a[oc_slot][N + j], a[oc_slot][c]);
+                const T q = quot(a[oc_slot][N + j], rc);
                 a[oc_slot][N + j] = q;
 #pragma unroll
                 for (int k = 0; k <= oc_slot; ++k) {
@@ -169,8 +189,23 @@ k_row_inv(const T* __restrict__ A, T* __restrict__ Ainv, uint8_t* __restrict__ o
                 const T t = __shfl_sync(0xffffffffu, a[oc_slot][N + j], gbase + oc_lane);
                 num[j / G] = (lane_g == j % G) ? t : num[j / G];
             }
+            if constexpr (JL < 3) {
 #pragma unroll
-            for (int jj = 0; jj < JL; ++jj) quo[jj] = div_rn(num[jj], ucc);
+                for (int jj = 0; jj < JL; ++jj) quo[jj] = div_rn(num[jj], ucc);
+            } else {
+                const RcpOf<T> rc(ucc);
+                bool all_ok = true;
+#pragma unroll
+                for (int jj = 0; jj < JL; ++jj) {
+                    bool ok;
+                    quo[jj] = rc.fast(num[jj], ok);
+                    all_ok = all_ok && ok;
+                }
+                if (!all_ok) {
+#pragma unroll
+                    for (int jj = 0; jj < JL; ++jj) quo[jj] = div_rn(num[jj], ucc);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const T xc = __shfl_sync(0xffffffffu, quo[j / G], gbase + j % G);

@@ -238,12 +238,33 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
 
         }
         // multipliers and rank-1 update of this lane's own rows below the pivot
+        // multipliers: one reciprocal per pivot, three operations per quotient (RcpOf, gmb_math.cuh); a lane whose
+        // operands leave the fast domain redoes its quotients with div_rn -- same bits either way.  Measured
+        // (profiles/r1l_shared_reciprocal.md): double +6..21 %, float n >= 13 +4..7 %, float n <= 12 -3..-6 % (the
+        // window tests cost what the shorter chains save), so small float sizes keep the plain division.
+        constexpr bool SRCP = sizeof(T) == 8 ? (G >= 2 && !(DECOMP && N == 12)) : N >= 13;   // measured exceptions: one-lane double, 12 x 12 double decomp
         const T pv = piv[i];
+        T bq[RL];
+        if constexpr (SRCP) {
+            const RcpOf<T> rc(pv);
+            bool all_ok = true;
+#pragma unroll
+            for (int k = oi_slot; k < RL; ++k) {
+                const int p = k * G + lane_g;
+                bool ok;
+                bq[k] = rc.fast(a[k][i], ok);
+                all_ok = all_ok && (ok || !((p > i) && (p < N)));
+            }
+            if (!all_ok) {
+#pragma unroll
+                for (int k = oi_slot; k < RL; ++k) bq[k] = div_rn(a[k][i], pv);
+            }
+        }
 #pragma unroll
         for (int k = oi_slot; k < RL; ++k) {
             const int p = k * G + lane_g;
             const bool below = (p > i) && (p < N);
-            const T b = div_rn(a[k][i], pv);                   // :234
+            const T b = SRCP ? bq[k] : div_rn(a[k][i], pv);    // :234
             const bool upd = below && !dead && (b != (T)0);    // :235
             if (below && !dead) a[k][i] = b;                   // :245
 #pragma unroll

@@ -189,10 +189,26 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
         // multipliers from the owner lane, then the rank-1 update of the local columns
         const T piv = a[i][k];
         const bool mine = (G == 1) || (lane_g == owner);
+        // one reciprocal per pivot, three operations per quotient (RcpOf, gmb_math.cuh); the owner lane redoes its
+        // quotients with div_rn when an operand leaves the fast domain -- same bits either way
+        T bq[N];
+        {
+            const RcpOf<T> rc(piv);
+            bool all_ok = true;
+#pragma unroll
+            for (int r = i + 1; r < N; ++r) {
+                bool ok;
+                bq[r] = rc.fast(a[r][k], ok);
+                all_ok = all_ok && ok;
+            }
+            if (mine && !all_ok) {
+#pragma unroll
+                for (int r = i + 1; r < N; ++r) bq[r] = div_rn(a[r][k], piv);
+            }
+        }
 #pragma unroll
         for (int r = i + 1; r < N; ++r) {
-            T b = div_rn(a[r][k], piv);
-            b = shfl_t<G>(b, owner);
+            T b = shfl_t<G>(bq[r], owner);
             const bool upd = !dead && (b != (T)0);
             if (mine) a[r][k] = dead ? a[r][k] : b;             // L(r,i)
 #pragma unroll
