@@ -143,6 +143,34 @@ def test_random_vs_oracle(gm, port, dt, n, soa):
     run_all(gm, port, n, A, b1, b3, S, soa)
 
 
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 8, 9, 12, 13, 16])
+def test_extreme_magnitudes_vs_oracle(gm, port, dt, n, soa):
+    """Rows scaled by powers of two far outside the fast domain of the shared-reciprocal division (RcpOf, gmb_math.cuh:
+    float operands beyond 2^+-57, double quotients near the ends of the exponent range), subnormal and zero entries,
+    overflowing multipliers: every quotient must still be the correctly rounded one (= the oracle's)."""
+    from oracle import pyoracle as po
+    f32 = np.dtype(dt) == np.float32
+    rng = np.random.default_rng(777 + 10 * n + np.dtype(dt).itemsize)
+    B = 257
+    kmax, ksub = (70, 140) if f32 else (520, 1040)
+    A = rng.standard_normal((B, n, n))
+    A = np.ldexp(A, rng.integers(-kmax, kmax + 1, size=(B, n, 1)))            # row scaling
+    A[3::7] = np.ldexp(A[3::7], rng.integers(-8, 9, size=A[3::7].shape))       # element scaling
+    A[5::11, :, 0] = np.ldexp(A[5::11, :, 0], -ksub)                          # subnormal / underflowing first column
+    A[2::13, 1, :] = 0.0
+    A[4::17, :, 1] = 0.0                                                      # a zero column: degenerate
+    with np.errstate(all="ignore"):
+        A = A.astype(dt).reshape(B, n * n)
+        b1 = np.ldexp(rng.standard_normal((B, n)), rng.integers(-kmax // 2, kmax // 2 + 1, size=(B, n))).astype(dt)
+        b3 = np.ldexp(rng.standard_normal((B, n * 3)), rng.integers(-kmax // 2, kmax // 2 + 1, size=(B, n * 3))).astype(dt)
+        S = po.spd_exact(rng, B, n, np.float64).reshape(B, n, n)
+        k = rng.integers(-kmax // 3, kmax // 3 + 1, size=(B, n))
+        S = np.ldexp(S, k[:, :, None] + k[:, None, :]).astype(dt).reshape(B, n * n)   # D S D stays symmetric positive definite
+    run_all(gm, port, n, A, b1, b3, S, soa)
+
+
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 def test_empty_and_tiny_batches(gm, dt):
     for B in (0, 1, 3):
@@ -282,7 +310,7 @@ def test_both_large_n_solve_kernels(force):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = " or ".join(f"{n}-" for n in range(9, 17))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
-                        "-k", f"(test_random_vs_oracle or test_golden) and ({sel}) and not both_large"],
+                        "-k", f"(test_random_vs_oracle or test_golden or test_extreme_magnitudes) and ({sel}) and not both_large"],
                        env=env, capture_output=True, text=True, cwd=root, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
@@ -299,7 +327,7 @@ def test_both_large_n_inverse_kernels(force):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = " or ".join(f"{n}-" for n in range(5, 17))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
-                        "-k", f"test_random_vs_oracle and ({sel})"],
+                        "-k", f"(test_random_vs_oracle or test_extreme_magnitudes) and ({sel})"],
                        env=env, capture_output=True, text=True, cwd=root, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
@@ -344,7 +372,7 @@ def test_both_large_n_decomp_kernels(force):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = " or ".join(f"{n}-" for n in range(7, 17))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
-                        "-k", f"(test_random_vs_oracle or test_golden) and ({sel}) and not both_large"],
+                        "-k", f"(test_random_vs_oracle or test_golden or test_extreme_magnitudes) and ({sel}) and not both_large"],
                        env=env, capture_output=True, text=True, cwd=root, timeout=1200)
     assert r.returncode == 0, r.stdout[-3000:]
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
