@@ -36,4 +36,18 @@ inline void dispatch_bool(bool b, F&& f) {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: remember, per kernel instantiation, which devices have
+// had their dynamic shared-memory limit raised (one bit per device ordinal), so that a process driving several GPUs
+// through the C ABI gets the opt-in on every one of them and the common case costs one cudaGetDevice.
+template <class K>
+inline void raise_dyn_smem(K kern, size_t bytes, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(done.load(std::memory_order_relaxed) & bit)) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        done.fetch_or(bit, std::memory_order_relaxed);
+    }
+}
+
 }  // namespace gmb

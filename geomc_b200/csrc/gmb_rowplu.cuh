@@ -397,9 +397,8 @@ int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* 
                     auto kern = k_row_solve<T, N.value, SOA.value, RM.value, false>;
                     const size_t smem = SOA.value ? 0 : row_stage_bytes<T, N.value>();
                     if (smem > 0) {   // static + dynamic may exceed the 48 KB default
-                        static bool raised = false;   // per instantiation
-                        if (!raised) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                        raised = true;
+                        static std::atomic<uint64_t> raised{0};   // per instantiation, one bit per device
+                        raise_dyn_smem(kern, smem, raised);
                     }
                     kern<<<grid, kRowThreads, smem, st>>>(A, Bm, X, LU, ok, nullptr, nullptr, nullptr, skip, B);
                 }
@@ -426,9 +425,8 @@ int rowplu_decomp_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, u
                 auto kern = k_row_solve<T, N.value, SOA.value, RM.value, true>;
                 const size_t smem = SOA.value ? 0 : row_stage_bytes<T, N.value>();
                 if (smem > 0) {   // static + dynamic may exceed the 48 KB default
-                    static bool raised = false;   // per instantiation
-                    if (!raised) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    raised = true;
+                    static std::atomic<uint64_t> raised{0};   // per instantiation, one bit per device
+                    raise_dyn_smem(kern, smem, raised);
                 }
                 kern<<<grid, kRowThreads, smem, st>>>(A, nullptr, nullptr, A, nullptr, perm, parity, degen, 0, B);
             });

@@ -358,11 +358,8 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
                                     ? 0
                                     : (size_t)(kSubThreads / 32) * (32 / G) * stage_stride<N * N>() * sizeof(T);
             if (smem > 48 * 1024) {
-                static bool raised = false;       // per instantiation
-                if (!raised) {
-                    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    raised = true;
-                }
+                static std::atomic<uint64_t> raised{0};   // per instantiation, one bit per device
+                raise_dyn_smem(kern, smem, raised);
             }
             kern<<<grid, kSubThreads, smem, st>>>(A, Bm, X, LU, ok, perm, parity, degen, skip, B);
         });
