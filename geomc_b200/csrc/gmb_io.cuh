@@ -39,12 +39,53 @@ __device__ __forceinline__ double2 ldg_stream(const double2* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
 }
+// 256-bit global loads (sm_100a, LDG.E.256): one whole 32-byte sector per lane and instruction.  A lane that walks its
+// own AoS row with 128-bit loads touches every sector twice, half of it each time, and with L1::no_allocate the second
+// half comes from L2 again.
+__device__ __forceinline__ void ldg_stream256(const float* p, float (&o)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]) : "l"(p));
+}
+__device__ __forceinline__ void ldg_stream256(const double* p, double (&o)[4]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
 __device__ __forceinline__ void unpack(const float4& v, float (&o)[4])  { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 __device__ __forceinline__ void unpack(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
 __device__ __forceinline__ float4  pack(const float (&o)[4])  { return make_float4(o[0], o[1], o[2], o[3]); }
 __device__ __forceinline__ double2 pack(const double (&o)[2]) { return make_double2(o[0], o[1]); }
 
 // ---- SoA tile access: q[v][e] for the V systems owned by this lane -------------------------
+// One row of N elements of a row-major AoS record into registers (dst[0..N-1], static indices after unrolling):
+// 256-bit loads when the row is a multiple of 32 bytes and the batch is 32-byte aligned (`al32`, warp-uniform),
+// 128-bit loads otherwise.  N * sizeof(T) must be a multiple of 16.
+template <typename T, int N>
+__device__ __forceinline__ void ldg_row(const T* __restrict__ p, T* dst, bool al32) {
+    constexpr int V = 16 / (int)sizeof(T);
+    static_assert((N * (int)sizeof(T)) % 16 == 0, "row must be a multiple of 16 bytes");
+    using VT = typename VecOf<T>::type;
+    if constexpr ((N * (int)sizeof(T)) % 32 == 0) {
+        if (al32) {
+#pragma unroll
+            for (int q = 0; q < N / (2 * V); ++q) {
+                T t[2 * V];
+                ldg_stream256(p + q * 2 * V, t);
+#pragma unroll
+                for (int v = 0; v < 2 * V; ++v) dst[q * 2 * V + v] = t[v];
+            }
+            return;
+        }
+    }
+    const VT* src = reinterpret_cast<const VT*>(p);
+#pragma unroll
+    for (int q = 0; q < N / V; ++q) {
+        T t[V];
+        unpack(ldg_stream(src + q), t);
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[q * V + v] = t[v];
+    }
+}
+
 template <typename T, int E>
 __device__ __forceinline__ void soa_load(const T* __restrict__ base, int64_t tile, int lane, T (&q)[soa_v<T>()][E]) {
     constexpr int V = soa_v<T>();

@@ -44,11 +44,19 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
     for (int k = 0; k < RL; ++k) {
         const int p = k * G + lane_g;
         const int pr = p < N ? p : 0;
+        if constexpr (!SOA && RM && (N * (int)sizeof(T)) % 16 == 0) {
+            // whole row with 128- / 256-bit loads (per-lane scalar loads at a stride of one record use 1/8 of every
+            // sector they touch); the upper triangle is never looked at (Cholesky.h:40-56 reads the lower one only)
+            ldg_row<T, N>(A + baseA + (int64_t)pr * N, a[k], (reinterpret_cast<uintptr_t>(A) & 31) == 0);
 #pragma unroll
-        for (int c = 0; c < N; ++c) {
-            a[k][c] = (T)0;
-            if (c <= k * G + (G - 1)) {                        // static: some lane's row in this slot reaches column c
-                if (c <= pr) a[k][c] = A[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
+            for (int c = 0; c < N; ++c) a[k][c] = (c <= pr) ? a[k][c] : (T)0;
+        } else {
+#pragma unroll
+            for (int c = 0; c < N; ++c) {
+                a[k][c] = (T)0;
+                if (c <= k * G + (G - 1)) {                    // static: some lane's row in this slot reaches column c
+                    if (c <= pr) a[k][c] = A[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
+                }
             }
         }
         y[k] = SOLVE ? Bm[baseX + (int64_t)pr * ST] : (T)0;

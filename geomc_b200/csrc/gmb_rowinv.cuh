@@ -46,14 +46,8 @@ k_row_inv(const T* __restrict__ A, T* __restrict__ Ainv, uint8_t* __restrict__ o
         const bool live = p < N;
         const int pr = live ? p : 0;
         if (!SOA && same_layout && (N * (int)sizeof(T)) % 16 == 0) {
-            const VT* src = reinterpret_cast<const VT*>(A + baseA + (int64_t)pr * N);
-#pragma unroll
-            for (int q = 0; q < N / V; ++q) {
-                T t[V];
-                unpack(ldg_stream(src + q), t);
-#pragma unroll
-                for (int v = 0; v < V; ++v) a[k][q * V + v] = t[v];
-            }
+            if constexpr ((N * (int)sizeof(T)) % 16 == 0)
+                ldg_row<T, N>(A + baseA + (int64_t)pr * N, a[k], N <= 8 && (reinterpret_cast<uintptr_t>(A) & 31) == 0);   // 256-bit loads: 8 x 8 +6 %, 16 x 16 -15 % (measured)
         } else {
 #pragma unroll
             for (int c = 0; c < N; ++c) a[k][c] = A[baseA + (int64_t)(same_layout ? N * pr + c : N * c + pr) * ST];

@@ -100,14 +100,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         const bool live = p < N;
         const int pr = live ? p : 0;
         if constexpr (!SOA && RM && (N * (int)sizeof(T)) % 16 == 0) {
-            const VT* src = reinterpret_cast<const VT*>(A + baseA + (int64_t)pr * N);
-#pragma unroll
-            for (int q = 0; q < N / V; ++q) {
-                T t[V];
-                unpack(ldg_stream(src + q), t);
-#pragma unroll
-                for (int v = 0; v < V; ++v) a[k][q * V + v] = t[v];
-            }
+            ldg_row<T, N>(A + baseA + (int64_t)pr * N, a[k], (reinterpret_cast<uintptr_t>(A) & 31) == 0);
         } else {
 #pragma unroll
             for (int c = 0; c < N; ++c) a[k][c] = A[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];

@@ -226,6 +226,40 @@ def test_unaligned_aos_batches_take_the_elementwise_kernels(gm, port, n):
     check(down(p).astype(np.int64), e[1], "unaligned decomp perm")
 
 
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [8, 12, 16])
+def test_batches_aligned_to_16_but_not_32_bytes(gm, port, dt, n):
+    """The row kernels read AoS rows with 256-bit loads when the batch is 32-byte aligned and with 128-bit loads when
+    it is only 16-byte aligned (ldg_row, gmb_io.cuh): same results either way."""
+    rng = np.random.default_rng(31 * n)
+    B = 333
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    off = 16 // np.dtype(dt).itemsize
+    A = rng.standard_normal((B, n * n)).astype(dt)
+    b = rng.standard_normal((B, n)).astype(dt)
+    from oracle import pyoracle as po
+    S = po.spd_exact(rng, B, n, dt)
+    bufs = []
+    for h in (A, b, S):
+        buf = torch.zeros(h.size + off, dtype=tdt, device="cuda")
+        v = buf[off:].view(*h.shape)
+        v.copy_(torch.from_numpy(h))
+        assert v.data_ptr() % 32 == 16
+        bufs.append(v)
+    dA, db, dS = bufs
+    x, ok = gm.linear_solve(dA, db, n)
+    _, xe, oke = port.linear_solve(A, b, n)
+    check(down(x), xe, f"16-byte aligned linear_solve n={n}")
+    check(down(ok), oke, "16-byte aligned ok")
+    out, oki = gm.inv(dA, n)
+    e = port.inv(A, n, True, True, np.zeros_like(A))
+    check(down(out)[down(oki) != 0], e[0][e[1] != 0], f"16-byte aligned inv n={n}")
+    Lp, okp = port.cholesky(S, n, True)
+    xs, oks = gm.cholesky_solve(dS, db, n)
+    check(down(oks), okp, "16-byte aligned cholesky ok")
+    check(down(xs), port.cholesky_solve(Lp, b, n, 1, True), f"16-byte aligned cholesky_solve n={n}")
+
+
 def test_host_api_matches_device_api(gm, port):
     rng = np.random.default_rng(9)
     B, n = 70001, 4
