@@ -124,6 +124,20 @@ template <typename T, int E>
 __device__ __forceinline__ void aos_load(const T* __restrict__ base, int64_t s, T (&q)[E]) {
     const T* p = base + s * (int64_t)E;
     constexpr int BYTES = E * (int)sizeof(T);
+    if constexpr (BYTES % 32 == 0) {
+        // 256-bit loads (one whole sector per lane and instruction) when the batch is 32-byte aligned
+        if ((reinterpret_cast<uintptr_t>(base) & 31) == 0) {
+            constexpr int V2 = 32 / (int)sizeof(T);
+            T tmp2[E / V2][V2];
+#pragma unroll
+            for (int i = 0; i < E / V2; ++i) ldg_stream256(p + i * V2, tmp2[i]);
+#pragma unroll
+            for (int i = 0; i < E / V2; ++i)
+#pragma unroll
+                for (int v = 0; v < V2; ++v) q[i * V2 + v] = tmp2[i][v];
+            return;
+        }
+    }
     if constexpr (BYTES % 16 == 0) {
         using VT = typename VecOf<T>::type;
         constexpr int V = soa_v<T>();
