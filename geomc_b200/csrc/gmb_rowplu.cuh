@@ -121,12 +121,19 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         // pivot search in column i over positions >= i
         T best_v = (T)-2;
         int best_p = 1 << 20;
+        // position tests against the static step: slot k > oi_slot lies wholly below row i, slot oi_slot is split by
+        // the lane; a slot is "live" statically unless it is the ragged last one (fewer compares on the ALU pipe)
+        auto row_live = [&](int k) { return ((k + 1) * G <= N) || (k * G + lane_g < N); };
+        auto at_or_below = [&](int k) { return (k > oi_slot || lane_g >= oi_lane) && row_live(k); };
+        auto is_below = [&](int k) { return (k > oi_slot || lane_g > oi_lane) && row_live(k); };
 #pragma unroll
         for (int k = oi_slot; k < RL; ++k) {
             const int p = k * G + lane_g;
-            const bool cand = (p >= i) && (p < N);
+            const bool cand = at_or_below(k);
             T v = abs_(a[k][i]);
-            if (v != v) v = (p == i) ? InfOf<T>::get() : (T)-1;     // NaN: diagonal keeps the pivot, others never win
+            // NaN: `v > best_v` is false, so a NaN below the diagonal never wins; a NaN ON the diagonal keeps the pivot
+            // (:205-213 start from |m(i,i)| and nothing compares greater than NaN): it becomes +Inf here
+            if (k == oi_slot) v = ((lane_g == oi_lane) && (v != v)) ? InfOf<T>::get() : v;
             const bool take = cand && (v > best_v);
             best_v = take ? v : best_v;
             best_p = take ? p : best_p;
@@ -243,10 +250,9 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
             bool all_ok = true;
 #pragma unroll
             for (int k = oi_slot; k < RL; ++k) {
-                const int p = k * G + lane_g;
                 bool ok;
                 bq[k] = rc.fast(a[k][i], ok);
-                all_ok = all_ok && (ok || !((p > i) && (p < N)));
+                all_ok = all_ok && (ok || !is_below(k));
             }
             if (!all_ok) {
 #pragma unroll
@@ -255,8 +261,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         }
 #pragma unroll
         for (int k = oi_slot; k < RL; ++k) {
-            const int p = k * G + lane_g;
-            const bool below = (p > i) && (p < N);
+            const bool below = is_below(k);
             const T b = SRCP ? bq[k] : div_rn(a[k][i], pv);    // :234
             const bool upd = below && !dead && (b != (T)0);    // :235
             if (below && !dead) a[k][i] = b;                   // :245
