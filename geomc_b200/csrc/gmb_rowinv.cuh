@@ -66,12 +66,16 @@ k_row_inv(const T* __restrict__ A, T* __restrict__ Ainv, uint8_t* __restrict__ o
         // pivot search in column i over positions >= i (LUDecomp.h:205-213)
         T best_v = (T)-2;
         int best_p = 1 << 20;
+        auto row_live = [&](int k) { return ((k + 1) * G <= N) || (k * G + lane_g < N); };   // static unless the slot is ragged
+        auto at_or_below = [&](int k) { return (k > oi_slot || lane_g >= oi_lane) && row_live(k); };
+        auto is_below = [&](int k) { return (k > oi_slot || lane_g > oi_lane) && row_live(k); };
 #pragma unroll
         for (int k = oi_slot; k < RL; ++k) {
             const int p = k * G + lane_g;
-            const bool cand = (p >= i) && (p < N);
+            const bool cand = at_or_below(k);
             T v = abs_(a[k][i]);
-            if (v != v) v = (p == i) ? InfOf<T>::get() : (T)-1;     // NaN: diagonal keeps the pivot, others never win
+            // a NaN below the diagonal never wins (`v > best_v` is false); a NaN ON the diagonal keeps the pivot
+            if (k == oi_slot) v = ((lane_g == oi_lane) && (v != v)) ? InfOf<T>::get() : v;
             const bool take = cand && (v > best_v);
             best_v = take ? v : best_v;
             best_p = take ? p : best_p;
@@ -122,10 +126,9 @@ k_row_inv(const T* __restrict__ A, T* __restrict__ Ainv, uint8_t* __restrict__ o
             bool all_ok = true;
 #pragma unroll
             for (int k = oi_slot; k < RL; ++k) {
-                const int p = k * G + lane_g;
                 bool ok;
                 bq[k] = rc.fast(a[k][i], ok);
-                all_ok = all_ok && (ok || !((p > i) && (p < N)));
+                all_ok = all_ok && (ok || !is_below(k));
             }
             if (!all_ok) {
 #pragma unroll
@@ -134,8 +137,7 @@ k_row_inv(const T* __restrict__ A, T* __restrict__ Ainv, uint8_t* __restrict__ o
         }
 #pragma unroll
         for (int k = oi_slot; k < RL; ++k) {
-            const int p = k * G + lane_g;
-            const bool below = (p > i) && (p < N) && !dead;
+            const bool below = is_below(k) && !dead;
             const T b = SRCP ? bq[k] : div_rn(a[k][i], pv);
             const bool upd = below && (b != (T)0);
 #pragma unroll

@@ -53,6 +53,10 @@ constexpr int row_group(int n, int words) {
     return 16;
 }
 
+#ifndef GMB_ROW_SRCP_FLOAT_MIN_N
+#define GMB_ROW_SRCP_FLOAT_MIN_N 13
+#endif
+
 template <typename T> struct InfOf;
 template <> struct InfOf<float>  { __device__ static __forceinline__ float get()  { return __int_as_float(0x7f800000); } };
 template <> struct InfOf<double> { __device__ static __forceinline__ double get() { return __longlong_as_double(0x7ff0000000000000LL); } };
@@ -242,7 +246,7 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         // operands leave the fast domain redoes its quotients with div_rn -- same bits either way.  Measured
         // (profiles/r1l_shared_reciprocal.md): double +6..21 %, float n >= 13 +4..7 %, float n <= 12 -3..-6 % (the
         // window tests cost what the shorter chains save), so small float sizes keep the plain division.
-        constexpr bool SRCP = sizeof(T) == 8 ? (G >= 2 && !(DECOMP && N == 12)) : N >= 13;   // measured exceptions: one-lane double, 12 x 12 double decomp
+        constexpr bool SRCP = sizeof(T) == 8 ? (G >= 2 && !(DECOMP && N == 12)) : N >= GMB_ROW_SRCP_FLOAT_MIN_N;   // measured exceptions: one-lane double, 12 x 12 double decomp
         const T pv = piv[i];
         T bq[RL];
         if constexpr (SRCP) {
