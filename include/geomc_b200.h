@@ -25,6 +25,9 @@
  *     (uint8), `degenerate` (uint8 count), `perm` (uint8[B][n], AoS in every layout: the reference's
  *     index_t reorder[] narrowed; row i of P*M is row perm[i] of M, LUDecomp.h:182-183).  Any of
  *     these output pointers may be NULL.
+ *   - Alignment: AoS batches that start on a 16-byte boundary take the vectorised kernels (32-byte alignment -- any
+ *     cudaMalloc'ed buffer -- additionally enables 256-bit loads); other AoS batches are served by element-wise
+ *     kernels with identical results; a SoA container must be 16-byte aligned.
  *   - Return value: 0 = success; < 0 = GMB_ERR_*; > 0 = a cudaError_t from the launch.
  *     There is NO CPU fallback: without a CUDA device every compute call fails.
  */
