@@ -123,6 +123,25 @@ int main(int argc, char** argv) {
         CK(cudaGetLastError());                                                                                  \
         report("row shuffle-exchange G=" #G_ " minb=" #MB_ " lu=" #LU_, ms, true);                               \
     }
+#define SHXT(G_, MB_, TH_)                                                                                       \
+    if (want("shx")) {                                                                                           \
+        auto kern = k_row_solve<float, N, false, true, false, G_, MB_, false, true, TH_>;                        \
+        const unsigned grid = (unsigned)((B * G_ + TH_ - 1) / TH_);                                              \
+        CK(cudaMemset(x, 0, B * N * 4));                                                                         \
+        float ms = time_ms([&] { kern<<<grid, TH_>>>(A, b, x, nullptr, ok, nullptr, nullptr, nullptr, 0, B); }); \
+        CK(cudaGetLastError());                                                                                  \
+        report("row shuffle G=" #G_ " minb=" #MB_ " threads=" #TH_, ms, true);                                   \
+    }
+    SHXT(4, 2, 256)
+    SHXT(4, 1, 256)
+    SHXT(4, 3, 128)
+    SHXT(4, 4, 128)
+    SHXT(4, 1, 384)
+    SHXT(4, 1, 512)
+    SHXT(4, 5, 96)
+    SHXT(4, 8, 64)
+    SHXT(2, 1, 256)
+    SHXT(2, 2, 256)
     SHX(2, 1, false)
     SHX(2, 2, false)
     SHX(2, 2, true)
