@@ -233,8 +233,12 @@ k_row_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, con
     for (int k = 0; k < RL; ++k) {
         const int p = k * G + lane_g;
         const int pr = p < N ? p : 0;
+        if constexpr (!SOA && RM && (N * (int)sizeof(T)) % 16 == 0) {
+            ldg_row<T, N>(LUm + baseA + (int64_t)pr * N, a[k], (reinterpret_cast<uintptr_t>(LUm) & 31) == 0);   // whole row, 128 / 256 bit
+        } else {
 #pragma unroll
-        for (int c = 0; c < N; ++c) a[k][c] = LUm[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
+            for (int c = 0; c < N; ++c) a[k][c] = LUm[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
+        }
         const int src = PLU ? (int)perm[s * N + pr] : pr;
         x[k] = Bm[baseX + (int64_t)src * ST];
     }
