@@ -6,7 +6,7 @@ call by hand-written sm_100a CUDA kernels behind a C ABI (include/geomc_b200.h).
 There is no CPU fallback: importing works anywhere, computing needs the built library and a GPU.
 """
 from . import _lib
-from ._lib import LAYOUT_AOS, LAYOUT_SOA, GmbError, lib
+from ._lib import LAYOUT_AOS, LAYOUT_SOA, GmbError, lib, set_option
 from .linalg import (BatchSoA, apply_permutation, backsolve_lu, backsolve_plu, checksum, cholesky, cholesky_solve,
                      decomp_lup, decomp_plu, host_cholesky_solve, host_decomp_plu, host_inv, host_linear_solve, inv,
                      linear_solve, linear_solve_vec, mul, nullspace, orthogonal, simplex_contains, simplex_intersect,

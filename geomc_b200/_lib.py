@@ -59,7 +59,7 @@ _TYPED = {
 
 # every symbol include/geomc_b200.h declares (tests/test_abi.py checks the header against this)
 UNTYPED = ["gmb_version", "gmb_error_string", "gmb_device_count", "gmb_soa_tile_width", "gmb_soa_elems",
-           "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count", "gmb_set_device",
+           "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count", "gmb_set_option", "gmb_set_device",
            "gmb_device_alloc", "gmb_device_free", "gmb_memcpy_h2d", "gmb_memcpy_d2h", "gmb_memset_device",
            "gmb_stream_synchronize"]
 EXPORTS = UNTYPED + [f"{k}_{s}" for k in _TYPED for s in ("f32", "f64")]
@@ -95,8 +95,35 @@ def lib() -> C.CDLL:
     L.gmb_host_free.restype = None
     L.gmb_host_free.argtypes = [_vp]
     L.gmb_launch_count.restype = _i64
+    L.gmb_set_option.restype = _i
+    L.gmb_set_option.argtypes = [C.c_char_p, _i]
+    L.gmb_set_device.restype = _i
+    L.gmb_set_device.argtypes = [_i]
+    L.gmb_device_alloc.restype = _vp
+    L.gmb_device_alloc.argtypes = [C.c_size_t]
+    L.gmb_device_free.restype = None
+    L.gmb_device_free.argtypes = [_vp]
+    for name in ("gmb_memcpy_h2d", "gmb_memcpy_d2h"):
+        getattr(L, name).restype = _i
+        getattr(L, name).argtypes = [_vp, _vp, C.c_size_t, _vp]
+    L.gmb_memset_device.restype = _i
+    L.gmb_memset_device.argtypes = [_vp, _i, C.c_size_t, _vp]
+    L.gmb_stream_synchronize.restype = _i
+    L.gmb_stream_synchronize.argtypes = [_vp]
+    # test / tuning harness: GMB_OPT_<NAME>=<int> in the environment of THIS python process is forwarded to
+    # gmb_set_option (the shared library itself never reads the environment)
+    for key, val in os.environ.items():
+        if key.startswith("GMB_OPT_"):
+            rc = L.gmb_set_option(key[len("GMB_OPT_"):].lower().encode(), int(val))
+            if rc != 0:
+                raise GmbError(f"unknown option in the environment: {key}")
     _lib = L
     return L
+
+
+def set_option(name: str, value: int) -> None:
+    """Force a kernel family (tests, tuning); -1 restores the measured dispatch table."""
+    check(lib().gmb_set_option(name.encode(), int(value)), f"gmb_set_option({name})")
 
 
 def check(rc: int, what: str) -> None:

@@ -14,6 +14,13 @@ namespace gmb {
 
 std::atomic<int64_t> g_launch_count{0};
 
+// Run-time dispatch options (gmb_set_option): -1 = the measured per-(type, n) table, anything else forces a kernel
+// family.  The library itself never reads the environment; tests and tuning scripts set these through the C ABI.
+std::atomic<int> g_opt_rowplu_min_n{-1};     // fused solve: row-distributed kernel from this n on (17 = never)
+std::atomic<int> g_opt_rowdecomp_min_n{-1};  // decomp_plu: row-distributed kernel from this n on
+std::atomic<int> g_opt_rowinv{-1};           // inverse n >= 5: 0 = column-distributed kernel, 1 = row-distributed
+std::atomic<int> g_opt_rowfast{-1};          // speculative solve (gmb_rowfast.cuh): 0 = off, 1 = wherever it exists
+
 // gmb_small.cu
 template <typename T> int small_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int small_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
@@ -31,6 +38,8 @@ template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uin
 template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int rowinv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int row_backsolve(int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
+// gmb_rowfast_*.cu
+template <typename T> int rowfast_solve(int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 // gmb_generic.cu
 template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
 template <typename T> int generic_solve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
@@ -58,18 +67,24 @@ template <typename T> int xf_apply(int, int, int64_t, const T*, bool, const T*, 
 // (bounce-buffer exchange of whole rows) wins for float n in {12, 14, 15, 16} and for double n = 10 and n >= 12;
 // without one -- the common call -- only the live part of a row travels and the register-only shuffle exchange
 // applies: the row kernel then wins for every float n >= 8 and for double n = 7, 8 and n >= 10.
-// GMB_ROWPLU_MIN_N=<n> in the environment overrides the table (17 disables the row kernel, 9 forces it).
+// gmb_set_option("rowplu_min_n", n) overrides the table (17 disables the row kernel, 9 forces it).
 template <typename T>
 static bool use_row_kernel(int n, bool want_lu) {
-    static const int forced = [] {
-        const char* e = std::getenv("GMB_ROWPLU_MIN_N");
-        return e ? std::atoi(e) : -1;
-    }();
+    const int forced = g_opt_rowplu_min_n.load(std::memory_order_relaxed);
     if (forced >= 0) return n >= forced;
     if (!want_lu) return sizeof(T) == 4 ? n >= 8 : (n == 7 || n == 8 || n >= 10);
     if (n < 9) return false;
     if (sizeof(T) == 4) return n == 12 || n >= 14;
     return n == 10 || n >= 12;
+}
+
+template <typename T>
+static bool use_rowfast(int n) {
+    const int forced = g_opt_rowfast.load(std::memory_order_relaxed);
+    if (forced >= 0) return forced != 0;
+    // measured against the exact row kernel (profiles/r2a_rowfast.md, 2^20 systems, AoS): float n = 13, 15, 16 win
+    // (16 x 16: 0.58 -> 0.39 ms); n <= 12 and 14 run two lanes per system in the exact kernel and stay there
+    return sizeof(T) == 4 && (n == 13 || n >= 15);
 }
 
 static bool bad_layout(int layout) { return layout != GMB_LAYOUT_AOS && layout != GMB_LAYOUT_SOA; }
@@ -83,14 +98,11 @@ static bool all_aligned16(P... ptrs) {
     return ((reinterpret_cast<uintptr_t>(ptrs) % 16 == 0) && ...);
 }
 
-// Same question for decomp_plu (GMB_ROWDECOMP_MIN_N overrides).  Measured (2^21 systems, SoA, in place):
+// Same question for decomp_plu (option "rowdecomp_min_n" overrides).  Measured (2^21 systems, SoA, in place):
 // the row kernel wins for float n >= 9 (n = 16: 1.35x) and double n >= 10 (n = 16: 2.3x); ties below.
 template <typename T>
 static bool use_row_decomp(int n) {
-    static const int forced = [] {
-        const char* e = std::getenv("GMB_ROWDECOMP_MIN_N");
-        return e ? std::atoi(e) : -1;
-    }();
+    const int forced = g_opt_rowdecomp_min_n.load(std::memory_order_relaxed);
     if (forced >= 0) return n >= forced;
     return sizeof(T) == 4 ? n >= 9 : n >= 10;
 }
@@ -151,6 +163,12 @@ int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* o
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && n >= 2 && n <= 4 && m <= 4) {
         int rc = small_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    // n >= 9, one right-hand side, no LU output: speculative kernel + exact re-solve of the systems it hands back
+    // (gmb_rowfast.cuh); option "rowfast" = 0 switches it off (the exact kernels below then serve every system)
+    if (fast && m == 1 && n >= 9 && LU == nullptr && use_rowfast<T>(n)) {
+        int rc = rowfast_solve<T>(n, B, A, Bm, X, ok, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     if (fast && m == 1 && n >= 7 && use_row_kernel<T>(n, LU != nullptr)) {
@@ -215,11 +233,8 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
     }
     // The row-distributed kernel (gmb_rowinv.cuh) is 1.2x (7 x 7 double) to 3x (16 x 16 float) faster than the
     // column-distributed one from n = 8 (float) / n = 6 (double) on and slower below (profiles/r1j_row_inverse.md);
-    // GMB_ROWINV=0 / 1 forces the column / row kernel for every n >= 5 (tests).
-    static const int row_inv = [] {
-        const char* e = std::getenv("GMB_ROWINV");
-        return !e ? -1 : (e[0] == '0' ? 0 : 1);
-    }();
+    // option "rowinv" = 0 / 1 forces the column / row kernel for every n >= 5 (tests).
+    const int row_inv = g_opt_rowinv.load(std::memory_order_relaxed);
     const bool use_row_inv = row_inv >= 0 ? row_inv == 1 : n >= (sizeof(T) == 4 ? 8 : 6);
     if (fast && n >= 5 && use_row_inv) {
         int rc = rowinv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
@@ -526,6 +541,18 @@ int64_t gmb_soa_elems(int64_t B, int E, int elem_size) {
 }
 
 int64_t gmb_launch_count(void) { return g_launch_count.load(); }
+
+int gmb_set_option(const char* name, int value) {
+    if (!name) return GMB_ERR_INVALID_ARG;
+    std::atomic<int>* o = !std::strcmp(name, "rowplu_min_n")      ? &g_opt_rowplu_min_n
+                          : !std::strcmp(name, "rowdecomp_min_n") ? &g_opt_rowdecomp_min_n
+                          : !std::strcmp(name, "rowinv")          ? &g_opt_rowinv
+                          : !std::strcmp(name, "rowfast")         ? &g_opt_rowfast
+                                                                  : nullptr;
+    if (!o) return GMB_ERR_INVALID_ARG;
+    o->store(value);
+    return GMB_OK;
+}
 
 void* gmb_host_alloc(size_t bytes) {
     void* p = nullptr;

@@ -61,16 +61,12 @@ template <typename T> struct InfOf;
 template <> struct InfOf<float>  { __device__ static __forceinline__ float get()  { return __int_as_float(0x7f800000); } };
 template <> struct InfOf<double> { __device__ static __forceinline__ double get() { return __longlong_as_double(0x7ff0000000000000LL); } };
 
-// DECOMP = false: fused linear_solve (rider = right-hand side).
-// DECOMP = true : decomp_plu in place (LUDecomp.h:188): the rider carries the row's ORIGINAL index,
-//                 so after the exchanges slot p holds reorder[p]; no rider arithmetic, no backward sweep.
-//                 (A is then read and written through `LU`; perm / parity / degenerate counts are stored.)
-template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G = row_group(N, (int)sizeof(T) / 4), int MINB = GMB_ROW_MIN_BLOCKS,
-          bool WANT_LU = true, bool SHFLX = false, int THREADS = kRowThreads>
-__global__ void __launch_bounds__(THREADS, MINB)
-k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
-            uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
-            int64_t B) {
+// One system's solve / decomposition by the G lanes that own it (body of k_row_solve and k_row_solve_list).
+template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G, bool WANT_LU, bool SHFLX, int THREADS>
+__device__ __forceinline__ void
+row_solve_one(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
+              uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
+              int64_t B, int64_t s, const bool valid, const int64_t s_warp0) {
     constexpr int WORDS = (int)sizeof(T) / 4;
     constexpr int RL = row_rl(N, G);
     constexpr int NC = N + 1;                                  // augmented row: n columns + the rider
@@ -82,14 +78,11 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     constexpr int ST = SOA ? soa_w<T>() : 1;
     using VT = typename VecOf<T>::type;
 
-    __shared__ __align__(16) uint32_t bounce[(THREADS / G) * GS];
+    __shared__ __align__(16) uint32_t bounce[SHFLX ? 4 : (THREADS / G) * GS];   // only the bounce-buffer exchange uses it
 
     const int lane_g = (G == 1) ? 0 : (int)(threadIdx.x % G);
     const int group = (int)(threadIdx.x / G);
-    int64_t s = ((int64_t)blockIdx.x * THREADS + threadIdx.x) / G;
-    const bool valid = s < B;
-    if (!valid) s = B - 1;                                     // keep all lanes for the shuffles / syncwarp
-    T* buf0 = reinterpret_cast<T*>(bounce + group * GS);       // row i
+    T* buf0 = reinterpret_cast<T*>(bounce + (SHFLX ? 0 : group * GS));       // row i
     T* buf1 = buf0 + NCP;                                      // row pvt
 
     constexpr int W = soa_w<T>();
@@ -289,7 +282,6 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     extern __shared__ __align__(16) unsigned char gmb_dyn_smem[];
     constexpr int NSYS = 32 / G;
     constexpr int SA = stage_stride<N * N>();
-    const int64_t s_warp0 = ((int64_t)blockIdx.x * THREADS + (threadIdx.x & ~31u)) / G;
     if (WANT_LU && !SOA && LU != nullptr && s_warp0 + NSYS <= B) {
         T* smw = reinterpret_cast<T*>(gmb_dyn_smem) + (threadIdx.x >> 5) * (NSYS * SA);
         T* smd = smw + ((threadIdx.x & 31) / G) * SA;
@@ -356,6 +348,41 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
         if (lane_g == 0 && ok_out) ok_out[s] = good ? 1 : 0;
     }
     }   // !DECOMP
+}
+
+// DECOMP = false: fused linear_solve (rider = right-hand side).
+// DECOMP = true : decomp_plu in place (LUDecomp.h:188): the rider carries the row's ORIGINAL index,
+//                 so after the exchanges slot p holds reorder[p]; no rider arithmetic, no backward sweep.
+//                 (A is then read and written through `LU`; perm / parity / degenerate counts are stored.)
+template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G = row_group(N, (int)sizeof(T) / 4), int MINB = GMB_ROW_MIN_BLOCKS,
+          bool WANT_LU = true, bool SHFLX = false, int THREADS = kRowThreads>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
+            uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
+            int64_t B) {
+    int64_t s = ((int64_t)blockIdx.x * THREADS + threadIdx.x) / G;
+    const bool valid = s < B;
+    if (!valid) s = B - 1;                                     // keep all lanes for the shuffles / syncwarp
+    const int64_t s_warp0 = ((int64_t)blockIdx.x * THREADS + (threadIdx.x & ~31u)) / G;
+    row_solve_one<T, N, SOA, RM, DECOMP, G, WANT_LU, SHFLX, THREADS>(A, Bm, X, LU, ok_out, perm_out, parity_out, degen_out, skip, B, s,
+                                                                    valid, s_warp0);
+}
+
+// The same solve for the systems named in list[0 .. *count): the exact re-solve of the systems that the speculative
+// kernels (gmb_rowfast.cuh) could not finish on their fast path.  A small persistent grid walks the list.
+template <typename T, int N, bool SOA, bool RM, int G, int MINB, bool SHFLX, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB)
+k_row_solve_list(const T* __restrict__ A, const T* Bm, T* X, uint8_t* __restrict__ ok_out, int skip, int64_t B,
+                 const int32_t* __restrict__ list, const int* __restrict__ count) {
+    const int64_t cnt = *count;
+    const int64_t stride = (int64_t)gridDim.x * THREADS / G;
+    for (int64_t j = ((int64_t)blockIdx.x * THREADS + threadIdx.x) / G;; j += stride) {
+        const bool valid = j < cnt;
+        if (!__any_sync(0xffffffffu, valid)) break;
+        const int64_t s = valid ? (int64_t)list[j] : (B - 1);
+        row_solve_one<T, N, SOA, RM, false, G, false, SHFLX, THREADS>(A, Bm, X, nullptr, ok_out, nullptr, nullptr, nullptr, skip, B,
+                                                                     s, valid, B);
+    }
 }
 
 // dynamic shared memory of the AoS output staging: one buffer of 32/G systems per warp

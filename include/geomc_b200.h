@@ -288,6 +288,12 @@ int gmb_host_plu_decomp_f32(int rows, int cols, int64_t B, float* A_inout, uint8
                             uint8_t* degenerate, int row_major, int device);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t gmb_launch_count(void);
+/* Dispatch options for tests and tuning (the library never reads the environment).  value = -1 restores the measured
+ * per-(type, n) table.  "rowplu_min_n" / "rowdecomp_min_n": smallest n served by the row-distributed fused solve /
+ * decomposition (17 = never); "rowinv": 0 / 1 = column- / row-distributed inverse for every n >= 5; "rowfast": 0 / 1 =
+ * never / always use the speculative fused solve (n >= 9, one right-hand side, no LU output) with its exact re-solve.
+ * Every choice computes the same bits; only the time differs.  Returns GMB_ERR_INVALID_ARG for an unknown name. */
+int gmb_set_option(const char* name, int value);
 
 /* ---- device memory and streams for hosts that do not link the CUDA runtime themselves --------
  * (include/geomc_b200/batch.hpp builds with a plain C++ compiler on top of these). */

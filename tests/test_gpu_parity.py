@@ -335,12 +335,12 @@ def test_full_size_properties(gm):
 @pytest.mark.parametrize("force", ["9", "17"])
 def test_both_large_n_solve_kernels(force):
     """The dispatch table picks one of two fused-solve kernels per (type, n); force each of them for
-    every n = 9..16 (row-distributed with GMB_ROWPLU_MIN_N=9, column-distributed with =17) in a fresh
+    every n = 9..16 (row-distributed with option rowplu_min_n = 9, column-distributed with 17; speculative kernel off) in a fresh
     process and rerun the oracle comparison."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, GMB_ROWPLU_MIN_N=force)
+    env = dict(os.environ, GMB_OPT_ROWPLU_MIN_N=force, GMB_OPT_ROWFAST="0")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = " or ".join(f"{n}-" for n in range(9, 17))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
@@ -353,11 +353,11 @@ def test_both_large_n_solve_kernels(force):
 @pytest.mark.parametrize("force", ["0", "1"])
 def test_both_large_n_inverse_kernels(force):
     """inv for n >= 5 has a row-distributed (gmb_rowinv.cuh) and a column-distributed kernel; the dispatcher picks per
-    (type, n).  GMB_ROWINV=0 / 1 forces one for every n: rerun the oracle comparison for n = 5..16 in a fresh process."""
+    (type, n).  option rowinv = 0 / 1 forces one for every n: rerun the oracle comparison for n = 5..16 in a fresh process."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, GMB_ROWINV=force)
+    env = dict(os.environ, GMB_OPT_ROWINV=force)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = " or ".join(f"{n}-" for n in range(5, 17))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
@@ -402,7 +402,7 @@ def test_both_large_n_decomp_kernels(force):
     import os
     import subprocess
     import sys
-    env = dict(os.environ, GMB_ROWDECOMP_MIN_N=force)
+    env = dict(os.environ, GMB_OPT_ROWDECOMP_MIN_N=force)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sel = " or ".join(f"{n}-" for n in range(7, 17))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
