@@ -1,19 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- systems/sec of the batched 4x4 float PLU solve (geom::linear_solve) on B200.
+"""bench.py -- systems/sec of the batched small-matrix factorization / solve path (geomc/linalg) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1..C5] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step is ONE pass of the hot path over one batch of synthetic input: B = 2^24 independent
-4x4 float systems per GPU (A: 1 GiB, b: 256 MiB, x: 256 MiB -- far larger than the 126 MB L2, so
-no L2 flush is needed between steps), resident in HBM in the SoA-interleaved layout, solved by
-ONE launch of the fused PLU-solve kernel through the C ABI (gmb_plu_solve_f32).  Systems are
-sharded contiguously across GPUs (weak scaling: every rank owns its own 2^24 systems); the only
-collective is the final all-reduce of {residual sum, max, fail count, checksum} scalars.
+The headline (BASELINE.json `metric`) is config C1's shape: the fused 4x4 float PLU solve, 2^24 independent systems per
+GPU per step (A: 1 GiB, b: 256 MiB, x: 256 MiB -- far larger than the 126 MB L2, so no flush is needed between steps),
+resident in HBM in the SoA-interleaved container, ONE launch of gmb_plu_solve_f32 per step.  Systems are sharded
+contiguously across GPUs (geomc_b200.sharding.shard_range); the only collective is the final reduction of
+{residual sum, max, fail count, checksum, mismatch count} scalars (geomc_b200.sharding.reduce_stats).
 
-Prints one JSON line (see the driver contract): value, roofline, cpu_baseline, e2e, clocks, ...
-`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified
-geomc headers, OpenMP over all host threads; falls back to the C port if _ref is absent).
+Every other BASELINE config is measured in the same run, on every rank, at its stated size (`other_configs`):
+    C1s  the literal C1 size: 2^20 systems per launch, 24 launches rotating over 4 buffer sets (384 MB > L2)
+    C2   2^24 3x3 double SPD systems per GPU, fused Cholesky + solve
+    C3   2^25 4x4 float inverses per GPU from AoS SimpleMatrix<float,4,4> records (2^28 = 256 M over 8 GPUs)
+    C4   64 M double PLU decompositions, seven homogeneous sub-batches N = 2..8, sharded over the ranks (strong
+         scaling), pivots / parity / degenerate counts / factors of the WHOLE batch compared with the reference
+    C5   2^23 16x16 float fused PLU solves per GPU, AoS and SoA
+each with systems/s (whole job), the HBM fraction per GPU, `verified_systems` and `mismatches` (bit-level, against
+oracle/_ref = the unmodified reference compiled for the host, or the C port when _ref is absent).
+`--config Cx` makes that config the top-level line instead of C1.
+
+Prints ONE JSON line (see the driver contract): value, roofline, cpu_baseline, e2e, clocks, verify, other_configs.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, OpenMP over all host threads).
 """
 import argparse
 import json
@@ -28,10 +37,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_DIM = 4
-LOG2_B = 24                 # systems per GPU per step
+LOG2_B = 24                 # C1 systems per GPU per step
 ALG_BYTES = 96              # 64 (A) + 16 (b) read, 16 (x) written per system
 METRIC = "systems/sec (4x4 f32 PLU solve)"
 WORKLOAD = "C1-shape: random 4x4 float systems, fused PLU decompose + linear_solve, 2^24 systems per GPU per step"
+C4_TOTAL = 9586980          # systems per N (x 7 sizes = 67.1 M = "64 M"), whole job
 
 
 def read_peak():
@@ -48,10 +58,10 @@ def read_traffic():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("plu_solve_f32_soa_bytes_per_system")
+            return json.load(open(p))
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
 
 
 class ClockSampler:
@@ -103,10 +113,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def host_threads(lib):
-    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 for its workers; the
-    CPU reference arm is meant to use every core, so the OpenMP team size is set explicitly."""
-    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def host_threads(lib, share=1):
+    """Host cores this process may use (divided by `share` ranks).  torchrun exports OMP_NUM_THREADS=1 for its workers;
+    the CPU reference is meant to use every core, so the OpenMP team size is set explicitly."""
+    n = max(1, host_cores() // max(1, share))
     if lib.kind == "reference":
         lib.set_threads(n)
         return n
@@ -175,27 +189,6 @@ def run_reference(args, rank, world):
     emit(line)
 
 
-def side_config(gm, torch, name, fn, nbytes_per_system, B, peak, reps=5):
-    """Quick secondary measurement (other BASELINE configs): best-of-`reps` CUDA-event time of one launch."""
-    try:
-        fn()
-        torch.cuda.synchronize()
-        best = None
-        for _ in range(reps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            ms = e0.elapsed_time(e1)
-            best = ms if best is None else min(best, ms)
-        rate = B / (best * 1e-3)
-        return {"workload": name, "systems_per_s": rate, "ms": best, "alg_bytes_per_system": nbytes_per_system,
-                "hbm_frac": rate * nbytes_per_system / (peak * 1e9)}
-    except Exception as ex:     # a side config must never take the headline down
-        return {"workload": name, "error": repr(ex)[:200]}
-
-
 _REAL_STDOUT = None
 
 
@@ -218,6 +211,363 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+# ======================================================================================= the GPU arm
+class Ctx:
+    pass
+
+
+def grid_f(c, shape, dt, gen):
+    """Exact-grid values (20-bit integers times 2^-17, exact in float and double) generated on the device."""
+    t = c.torch
+    return t.randint(-(1 << 19), 1 << 19, shape, device=c.dev, generator=gen, dtype=t.int32).to(dt) * 2.0 ** -17
+
+
+def timed(c, fn, steps, warmup, before=None):
+    """CUDA-event time of `steps` launches of fn() on the current stream after `warmup` untimed ones -> per-step ms.
+    `before` (untimed, e.g. restoring an in-place input) runs ahead of every launch; without it the steps run back to back."""
+    t = c.torch
+    st = t.cuda.current_stream(c.dev)
+    for _ in range(warmup):
+        if before:
+            before()
+        fn()
+    t.cuda.synchronize()
+    ms = []
+    if before is None:
+        evs = [t.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        evs[0].record(st)
+        for i in range(steps):
+            fn()
+            evs[i + 1].record(st)
+        t.cuda.synchronize()
+        ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+    else:
+        for _ in range(steps):
+            before()
+            e0, e1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            e0.record(st)
+            fn()
+            e1.record(st)
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+    return ms
+
+
+def max_over_ranks(c, value):
+    if c.world == 1:
+        return float(value)
+    v = c.torch.tensor([float(value)], dtype=c.torch.float64, device=c.dev)
+    c.dist.all_reduce(v, op=c.dist.ReduceOp.MAX)
+    return float(v.item())
+
+
+def sum_over_ranks(c, value):
+    from geomc_b200.sharding import reduce_stats
+    return reduce_stats({"v": float(value)}, device=c.dev)["v"]
+
+
+def rows_differ(np, got, want):
+    """Per-system bit-level comparison (NaN == NaN regardless of payload): bool[B], True = mismatch."""
+    got, want = np.asarray(got), np.asarray(want)
+    if got.dtype.kind != "f":
+        d = got != want
+    else:
+        u = f"u{got.itemsize}"
+        d = (got.view(u) != want.view(u)) & ~(np.isnan(got) & np.isnan(want))
+    return d.reshape(d.shape[0], -1).any(axis=1) if d.ndim > 1 else d
+
+
+def row(c, name, cfg, per_gpu, total_ms_max, steps, nbytes, extra=None):
+    """One `other_configs` entry: whole-job systems/s (all ranks' systems / max-over-ranks time), HBM fraction per GPU."""
+    total_systems = sum_over_ranks(c, per_gpu)
+    rate = total_systems * steps / (total_ms_max * 1e-3)
+    out = {"config": cfg, "workload": name, "n_gpus": c.world, "systems_per_step": int(total_systems),
+           "systems_per_s": rate, "ms_per_step": total_ms_max / steps, "steps": steps, "alg_bytes_per_system": nbytes,
+           "hbm_frac": rate / c.world * nbytes / (c.peak * 1e9)}
+    if extra:
+        out.update(extra)
+    return out
+
+
+def oracle(c):
+    if getattr(c, "_orc", None) is None:
+        from oracle import pyoracle as po
+        c._orc = po.best()
+        c.cpu_threads = host_threads(c._orc, share=c.world)
+    return c._orc
+
+
+# ---------------------------------------------------------------------------------------- C1 (the metric)
+def make_c1(c, B, seed):
+    t, gm = c.torch, c.gm
+    g = t.Generator(device=c.dev).manual_seed(seed)
+    A = gm.BatchSoA(B, 16, t.float32, c.dev)
+    b = gm.BatchSoA(B, 4, t.float32, c.dev)
+    A.data.copy_(grid_f(c, A.data.shape, t.float32, g))
+    b.data.copy_(grid_f(c, b.data.shape, t.float32, g))
+    return A, b
+
+
+def verify_solve_sample(c, A, b, x, ok, n, count, dt):
+    """First `count` systems of this rank's shard against the oracle, bit for bit -> (#verified, #mismatching systems)."""
+    np, t, gm = c.np, c.torch, c.gm
+    orc = oracle(c)
+    count = min(count, A.B if hasattr(A, "B") else A.shape[0])
+
+    def head(v, E):
+        if hasattr(v, "to_aos"):
+            W = v.W
+            tiles = (count + W - 1) // W
+            sub = gm.BatchSoA(tiles * W, E, dt, c.dev, v.data[:tiles * E * W])
+            return sub.to_aos()[:count].cpu().numpy()
+        return v[:count].cpu().numpy()
+    with np.errstate(all="ignore"):
+        _, xe, oke = orc.linear_solve(head(A, n * n), head(b, n), n)
+    bad = rows_differ(np, head(x, n), xe) | (ok[:count].cpu().numpy() != oke)
+    return count, int(bad.sum())
+
+
+def config_c1_small(c, steps=24):
+    """The literal C1 size (SURVEY 8d timing protocol): 2^20 systems per launch, >= 20 launches over rotating buffer sets
+    larger than L2 -- shows what launch overhead and a short grid cost next to the 2^24 line."""
+    t, gm = c.torch, c.gm
+    B = 1 << 20
+    sets = [make_c1(c, B, 4000 + 17 * c.rank + i) for i in range(4)]          # 4 x 96 MB = 384 MB > 126 MB L2
+    xs = [gm.BatchSoA(B, 4, t.float32, c.dev) for _ in sets]
+    ok = t.zeros(B, dtype=t.uint8, device=c.dev)
+    k = [0]
+
+    def fn():
+        A, b = sets[k[0] % 4]
+        gm.linear_solve(A, b, 4, 1, 0, True, x_out=xs[k[0] % 4], ok_out=ok)
+        k[0] += 1
+    ms = timed(c, fn, steps, 4)
+    total = max_over_ranks(c, sum(ms))
+    nv, bad = verify_solve_sample(c, sets[(k[0] - 1) % 4][0], sets[(k[0] - 1) % 4][1], xs[(k[0] - 1) % 4], ok, 4, B, t.float32)
+    return row(c, "C1 literal: 4x4 f32 PLU solve, 2^20 systems per launch, 24 launches rotating over 4 buffer sets (384 MB > L2), SoA",
+               "C1s", B, total, steps, 96,
+               {"median_launch_ms": statistics.median(ms), "best_launch_ms": min(ms), "verified_systems": int(sum_over_ranks(c, nv)),
+                "mismatches": int(sum_over_ranks(c, bad)), "oracle": oracle(c).kind})
+
+
+# ---------------------------------------------------------------------------------------- C2
+def config_c2(c, steps=5):
+    t, gm, np = c.torch, c.gm, c.np
+    B = 1 << 24
+    g = t.Generator(device=c.dev).manual_seed(2000 + c.rank)
+    R = t.randint(-128, 128, (B, 3, 3), device=c.dev, generator=g).double() * 2.0 ** -5
+    S = (R @ R.transpose(1, 2) + t.eye(3, device=c.dev, dtype=t.float64)).reshape(B, 9).contiguous()
+    bs = grid_f(c, (B, 3), t.float64, g)
+    del R
+    Ss, bss = gm.BatchSoA.from_aos(S), gm.BatchSoA.from_aos(bs)
+    xs = bss.empty_like()
+    ok = t.zeros(B, dtype=t.uint8, device=c.dev)
+    out = []
+    # algorithmic bytes: the factorization reads only the LOWER triangle (Cholesky.h:42-44), so the SoA kernel never
+    # touches the 3 upper-triangle planes: 48 + 24 read, 24 written = 96 B; AoS pulls whole 72-byte records: 120 B
+    for name, fn, nbytes in (("SoA (96 B/system: lower triangle only)", lambda: gm.cholesky_solve(Ss, bss, 3, x_out=xs, ok_out=ok), 96),
+                             ("AoS (120 B/system: whole records)", None, 120)):
+        if fn is None:
+            xa = t.empty_like(bs)
+            fn = lambda: gm.cholesky_solve(S, bs, 3, x_out=xa, ok_out=ok)
+        total = max_over_ranks(c, sum(timed(c, fn, steps, 3)))
+        out.append([name, total, nbytes])
+    # verification of the SoA run: the factor against the reference's cholesky (pinned), the solve against the port's
+    # definition (the reference has no Cholesky solve: parity unpinned) and against a long-double host solve
+    count = 1 << 20
+    Sh, bh = S[:count].cpu().numpy(), bs[:count].cpu().numpy()
+    x_all, ok_all, L_all = gm.cholesky_solve(S[:count].contiguous(), bs[:count].contiguous(), 3, want_l=True)
+    xh = gm.BatchSoA(count, 3, t.float64, c.dev, xs.data[:count * 3]).to_aos().cpu().numpy()
+    orc = oracle(c)
+    from oracle import pyoracle as po
+    Le, oke = orc.cholesky(Sh, 3)
+    xe = po.port().cholesky_solve(Le, bh, 3)
+    bad = rows_differ(np, L_all.cpu().numpy(), Le) | (ok_all.cpu().numpy() != oke) | rows_differ(np, xh, xe) | \
+        rows_differ(np, x_all.cpu().numpy(), xe)
+    ld = np.longdouble
+    k = 1 << 14
+    xl = np.linalg.solve(Sh[:k].reshape(k, 3, 3).astype(np.float64), bh[:k].astype(np.float64)[..., None])[..., 0]   # f64 LAPACK as a first filter
+    Al, bl = Sh[:k].reshape(k, 3, 3).astype(ld), bh[:k].astype(ld)
+    res = np.abs(np.einsum("sij,sj->si", Al, xh[:k].astype(ld)) - bl).max(axis=1) / np.abs(bl).max(axis=1).clip(min=ld(1e-300))
+    extra = {"verified_systems": int(sum_over_ranks(c, count)), "mismatches": int(sum_over_ranks(c, int(bad.sum()))),
+             "oracle": f"{orc.kind} (factor L, ok) + port definition (x)",
+             "parity": "factor pinned to the reference; the SOLVE is parity-unpinned (the reference has no Cholesky solve)",
+             "max_rel_residual_long_double": float(max_over_ranks(c, float(res.max()))),
+             "max_abs_diff_vs_lapack_f64": float(np.abs(xl - xh[:k]).max())}
+    rows = []
+    for name, total, nbytes in out:
+        rows.append(row(c, f"C2: 3x3 f64 SPD cholesky + solve, 2^24 systems per GPU, {name}", "C2", B, total, steps, nbytes, extra))
+    return rows
+
+
+# ---------------------------------------------------------------------------------------- C3
+def config_c3(c, steps=5, log2_b=25):
+    """256 M 4x4 float projective-transform inverses over 8 GPUs = 2^25 AoS SimpleMatrix<float,4,4> records per GPU."""
+    t, gm, np = c.torch, c.gm, c.np
+    B = 1 << log2_b
+    g = t.Generator(device=c.dev).manual_seed(3000 + c.rank)
+    f32 = t.float32
+    # rotation(z) * rotation(x) * diag(scale) in the upper-left 3x3, a translation column, a non-trivial last row
+    M = t.empty((B, 4, 4), dtype=f32, device=c.dev)
+    ang = t.rand((B, 2), device=c.dev, generator=g, dtype=f32) * 6.2831853
+    sc = t.rand((B, 3), device=c.dev, generator=g, dtype=f32) * 1.5 + 0.25
+    cz, sz, cx, sx = ang[:, 0].cos(), ang[:, 0].sin(), ang[:, 1].cos(), ang[:, 1].sin()
+    M[:, 0, 0], M[:, 0, 1], M[:, 0, 2] = cz * sc[:, 0], -sz * cx * sc[:, 1], sz * sx * sc[:, 2]
+    M[:, 1, 0], M[:, 1, 1], M[:, 1, 2] = sz * sc[:, 0], cz * cx * sc[:, 1], -cz * sx * sc[:, 2]
+    M[:, 2, 0], M[:, 2, 1], M[:, 2, 2] = 0.0, sx * sc[:, 1], cx * sc[:, 2]
+    M[:, :3, 3] = t.rand((B, 3), device=c.dev, generator=g, dtype=f32) * 20 - 10
+    M[:, 3, :3] = t.rand((B, 3), device=c.dev, generator=g, dtype=f32) * 0.02 - 0.01
+    M[:, 3, 3] = 1.0
+    del ang, sc, cz, sz, cx, sx
+    A = M.reshape(B, 16)
+    out = t.empty_like(A)
+    ok = t.zeros(B, dtype=t.uint8, device=c.dev)
+    total = max_over_ranks(c, sum(timed(c, lambda: gm.inv(A, 4, out=out, ok_out=ok), steps, 3)))
+    count = 1 << 20
+    orc = oracle(c)
+    with np.errstate(all="ignore"):
+        ie, oke = orc.inv(A[:count].cpu().numpy(), 4, True, True, np.zeros((count, 16), np.float32))
+    got = out[:count].cpu().numpy()
+    okg = ok[:count].cpu().numpy()
+    got[okg == 0] = 0                                              # "out untouched" where singular: compare like with like
+    bad = rows_differ(np, got, ie) | (okg != oke)
+    # size-independent property over the whole shard: inv(inv(A)) ~ A
+    back = t.empty_like(A)
+    gm.inv(out, 4, out=back, ok_out=ok)
+    rel = ((back - A).abs().amax(dim=1) / A.abs().amax(dim=1))
+    extra = {"verified_systems": int(sum_over_ranks(c, count)), "mismatches": int(sum_over_ranks(c, int(bad.sum()))),
+             "oracle": orc.kind, "singular_systems": int(sum_over_ranks(c, int((ok == 0).sum().item()))),
+             "round_trip_rel_err_median": float(rel.median().item()), "round_trip_rel_err_max": max_over_ranks(c, float(rel.max().item()))}
+    del back, rel
+    r = [row(c, f"C3: 4x4 f32 projective-transform inverse, 2^{log2_b} AoS SimpleMatrix<float,4,4> records per GPU", "C3", B, total, steps, 128, extra)]
+    # the same through the host entry point (pinned host AoS in, host inverse out): the e2e number of this config
+    try:
+        Be = 1 << 24
+        hA = t.empty((Be, 16), dtype=f32).pin_memory()
+        hO = t.empty((Be, 16), dtype=f32).pin_memory()
+        hok = t.empty(Be, dtype=t.uint8).pin_memory()
+        hA.copy_(A[:Be])
+        t.cuda.synchronize()
+        gm.host_inv(hA, hO, hok, 4, device=c.local_rank)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            gm.host_inv(hA, hO, hok, 4, device=c.local_rank)
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        same = bool(t.equal(hO[:count].view(t.int32), out[:count].cpu().view(t.int32)))
+        r[0]["e2e"] = {"value": Be * c.world * reps / dt, "unit": "systems/s", "systems_per_gpu": Be, "h2d_bytes_per_step": Be * 64,
+                       "d2h_bytes_per_step": Be * 65, "api": "gmb_host_inv_f32 (pinned host AoS in, host inverse + ok out)",
+                       "matches_resident_path": same}
+        del hA, hO, hok
+    except Exception as ex:
+        r[0]["e2e"] = {"error": repr(ex)[:200]}
+    # the OBJECT form (geom::batch::inv on an array of SimpleMatrix<float,4,4> objects, include/geomc_b200/batch.hpp) beside
+    # the raw-pointer call on the same data: a C++ program (tests/cpp/bench_object_inv.cpp), rank 0 only
+    if c.rank == 0:
+        r[0]["object_form_e2e"] = object_form_e2e(c.local_rank)
+    if c.world > 1:
+        c.dist.barrier()
+    return r
+
+
+def object_form_e2e(device, log2_b=23):
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "oracle", "_ref", "bench_object_inv_geomc")        # built with the reference's real types where they exist
+    try:
+        if not os.path.exists(exe):
+            exe = os.path.join(tempfile.mkdtemp(), "bench_object_inv")
+            libdir = os.path.join(ROOT, "geomc_b200")
+            subprocess.run(["g++", "-std=c++17", "-O2", "-w", "-I", os.path.join(ROOT, "include"),
+                            os.path.join(ROOT, "tests", "cpp", "bench_object_inv.cpp"), "-L", libdir, "-lgeomc_b200",
+                            f"-Wl,-rpath,{libdir}", "-o", exe], check=True, capture_output=True, timeout=300)
+        out = subprocess.run([exe, str(log2_b), str(device), "3"], capture_output=True, text=True, timeout=600)
+        return json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception as ex:
+        return {"error": repr(ex)[:300]}
+
+
+# ---------------------------------------------------------------------------------------- C4
+def config_c4(c, steps=3, total_per_n=C4_TOTAL):
+    """64 M mixed N = 2..8 double PLU decompositions = seven homogeneous sub-batches, each sharded contiguously over the
+    ranks (strong scaling).  The WHOLE timed batch is verified: reorder[], parity, degenerate count and the packed LU of
+    every system against the reference's decomp_plu on the host (regression/linear_solve.cpp:71-101 checks LU = PM;
+    here the comparison is bit for bit)."""
+    from geomc_b200.sharding import shard_range
+    t, gm, np = c.torch, c.gm, c.np
+    f64 = t.float64
+    orc = oracle(c)
+    per_n, times, verified, bad_total, bytes_total, systems_total = [], 0.0, 0, 0, 0.0, 0
+    for n in range(2, 9):
+        lo, hi = shard_range(total_per_n, c.rank, c.world, align=64)      # 64 = SoA tile width of double: whole tiles per shard
+        Bc = hi - lo
+        g = t.Generator(device=c.dev).manual_seed(4000 + 100 * n + c.rank)
+        M0 = gm.BatchSoA(Bc, n * n, f64, c.dev)
+        M0.data.copy_(grid_f(c, M0.data.shape, f64, g))
+        M = M0.clone()
+        outs = (t.empty((Bc, n), dtype=t.uint8, device=c.dev), t.empty(Bc, dtype=t.uint8, device=c.dev),
+                t.empty(Bc, dtype=t.uint8, device=c.dev))
+        ms = timed(c, lambda: gm.decomp_plu(M, n, inplace=True, out=outs), steps, 3, before=lambda: M.data.copy_(M0.data))
+        tn = max_over_ranks(c, sum(ms))
+        nbytes = 16 * n * n + n + 2
+        cnt = sum_over_ranks(c, Bc)
+        per_n.append({"n": n, "systems_per_s": cnt * steps / (tn * 1e-3), "hbm_frac": cnt / c.world * steps / (tn * 1e-3) * nbytes / (c.peak * 1e9)})
+        times += tn
+        bytes_total += cnt * nbytes
+        systems_total += cnt
+        # whole-shard verification of the last timed launch's outputs, in chunks of 2^20 systems
+        A0, LU = M0.to_aos(), M.to_aos()
+        chunk = 1 << 20
+        for s0 in range(0, Bc, chunk):
+            s1 = min(Bc, s0 + chunk)
+            with np.errstate(all="ignore"):
+                lue, pe, pare, dge = orc.decomp_plu(A0[s0:s1].cpu().numpy(), n)
+            bad = (rows_differ(np, outs[0][s0:s1].cpu().numpy().astype(np.int64), pe) | (outs[1][s0:s1].cpu().numpy() != pare) |
+                   (outs[2][s0:s1].cpu().numpy().astype(np.int64) != dge) | rows_differ(np, LU[s0:s1].cpu().numpy(), lue))
+            bad_total += int(bad.sum())
+            verified += s1 - s0
+        del M0, M, A0, LU, outs
+    rate = systems_total * steps / (times * 1e-3)
+    return [{"config": "C4", "workload": f"C4: N x N f64 PLU decompose in place, N = 2..8, {total_per_n} systems per N (whole job), SoA, "
+                                         f"sharded over {c.world} rank(s)", "n_gpus": c.world, "systems_per_step": int(systems_total),
+             "systems_per_s": rate, "ms_per_step": times / steps, "steps": steps, "scaling": "strong",
+             "alg_bytes_per_system": bytes_total / systems_total, "hbm_frac": bytes_total / c.world * steps / (times * 1e-3) / (c.peak * 1e9),
+             "per_n": per_n, "verified_systems": int(sum_over_ranks(c, verified)), "mismatches": int(sum_over_ranks(c, bad_total)),
+             "verified": "reorder[], parity, degenerate count and packed LU of every system, bit for bit", "oracle": orc.kind,
+             "cpu_threads_per_rank": c.cpu_threads}]
+
+
+# ---------------------------------------------------------------------------------------- C5
+def config_c5(c, steps=3, log2_b=23):
+    t, gm, np = c.torch, c.gm, c.np
+    B = 1 << log2_b
+    g = t.Generator(device=c.dev).manual_seed(5000 + c.rank)
+    A = grid_f(c, (B, 256), t.float32, g)
+    b = grid_f(c, (B, 16), t.float32, g)
+    x = t.empty_like(b)
+    ok = t.zeros(B, dtype=t.uint8, device=c.dev)
+    rows = []
+    count = 1 << 18
+    orc = oracle(c)
+    with np.errstate(all="ignore"):
+        _, xe, oke = orc.linear_solve(A[:count].cpu().numpy(), b[:count].cpu().numpy(), 16)
+    total = max_over_ranks(c, sum(timed(c, lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok), steps, 3)))
+    bad = rows_differ(np, x[:count].cpu().numpy(), xe) | (ok[:count].cpu().numpy() != oke)
+    # issue-slot roofline next to the HBM fraction: the kernel is bound by instruction issue, not by bytes
+    rows.append(row(c, f"C5: 16x16 f32 fused PLU solve, 2^{log2_b} systems per GPU, AoS", "C5", B, total, steps, 1152,
+                    {"verified_systems": int(sum_over_ranks(c, count)), "mismatches": int(sum_over_ranks(c, int(bad.sum()))),
+                     "oracle": orc.kind, "failed_systems": int(sum_over_ranks(c, int((ok == 0).sum().item())))}))
+    As, bs_ = gm.BatchSoA.from_aos(A), gm.BatchSoA.from_aos(b)
+    del A
+    xs = bs_.empty_like()
+    total = max_over_ranks(c, sum(timed(c, lambda: gm.linear_solve(As, bs_, 16, x_out=xs, ok_out=ok), steps, 3)))
+    same = bool(t.equal(xs.to_aos().view(t.int32), x.view(t.int32)))
+    rows.append(row(c, f"C5: 16x16 f32 fused PLU solve, 2^{log2_b} systems per GPU, SoA container", "C5", B, total, steps, 1152,
+                    {"verified_systems": int(sum_over_ranks(c, B)), "mismatches": int(sum_over_ranks(c, 0 if same else 1)),
+                     "verified": "whole batch bit-identical to the AoS run (which is checked against the oracle)"}))
+    return rows
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -225,8 +575,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C1", choices=["C1", "C2", "C3", "C4", "C5"],
+                    help="which BASELINE config provides the top-level value (the others go to other_configs)")
     ap.add_argument("--log2-batch", type=int, default=LOG2_B)
-    ap.add_argument("--no-sides", action="store_true", help="skip the secondary configs")
+    ap.add_argument("--no-sides", action="store_true", help="skip the other configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -244,6 +596,7 @@ def main():
     import torch.distributed as dist
 
     import geomc_b200 as gm
+    from geomc_b200.sharding import checksum_word_offset, reduce_stats, shard_range
     L = gm.lib()                      # fails loudly if the CUDA library is missing
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: geomc_b200 has no CPU fallback")
@@ -252,18 +605,22 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner must not share stdout with the JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a rank that fails inside a side config must not leave the others waiting in a collective for NCCL's default 10 min
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=240))
 
+    c = Ctx()
+    c.torch, c.dist, c.gm, c.np, c.dev, c.rank, c.world, c.local_rank = torch, dist, gm, np, dev, rank, world, local_rank
+    c.peak, peak_src = read_peak()
+    c.cpu_threads = None
+    peak = c.peak
+
+    # ---- C1: this rank's contiguous shard of the global batch (weak scaling: 2^24 systems per rank) --------------------
     B = 1 << args.log2_batch
     n = N_DIM
-    peak, peak_src = read_peak()
-
-    # ---- synthetic inputs, generated on the device directly in the SoA-interleaved container ----
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    A = gm.BatchSoA(B, n * n, torch.float32, dev)
-    b = gm.BatchSoA(B, n, torch.float32, dev)
-    A.data.copy_(torch.randint(-(1 << 19), 1 << 19, A.data.shape, device=dev, generator=g, dtype=torch.int32).float() * 2.0 ** -17)
-    b.data.copy_(torch.randint(-(1 << 19), 1 << 19, b.data.shape, device=dev, generator=g, dtype=torch.int32).float() * 2.0 ** -17)
+    lo, hi = shard_range(B * world, rank, world, align=128)
+    assert hi - lo == B
+    A, b = make_c1(c, B, 1234 + rank)
     x = gm.BatchSoA(B, n, torch.float32, dev)
     ok = torch.zeros(B, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
@@ -294,10 +651,8 @@ def main():
     launches = L.gmb_launch_count() - launches0
     total_ms = evs[0].elapsed_time(evs[-1])
     per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = max_over_ranks(c, total_ms)
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end-to-end: host AoS buffers (pinned) -> C ABI host call -> host results -------------------
     e2e = None
@@ -318,13 +673,10 @@ def main():
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             gm.host_linear_solve(hA, hb, hx, hok, n, device=local_rank)
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": Be * world * e2e_steps / float(te.item()), "unit": "systems/s",
+        dt = max_over_ranks(c, time.perf_counter() - t0)
+        e2e = {"value": Be * world * e2e_steps / dt, "unit": "systems/s",
                "h2d_bytes_per_step": Be * (64 + 16), "d2h_bytes_per_step": Be * (16 + 1),
-               "steps": e2e_steps, "ms_per_step": 1e3 * float(te.item()) / e2e_steps,
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "api": "gmb_host_plu_solve_f32 (pinned host AoS in, host x/ok out; chunked H2D/kernel/D2H on 3 streams)"}
         # the host path and the resident SoA path must agree bit for bit
         same = bool(torch.equal(hx.cuda(dev).view(torch.int32), x.to_aos().view(torch.int32)))
@@ -333,109 +685,58 @@ def main():
     except Exception as ex:
         e2e = {"value": None, "unit": "systems/s", "error": repr(ex)[:300]}
 
-    # ---- verification of the timed run's outputs -----------------------------------------------------
+    # ---- verification of the timed run's outputs: device-side statistics of the whole shard, the first 2^20 systems of
+    # every shard against the oracle bit for bit; ONE reduction over the ranks (the only collective on the path) ----------
     stats = gm.solve_residual(A, x, b, ok, n)                       # [sum, max, fails, nonfinite]
-    csum = gm.checksum(ok, word_offset=rank * (B // 8))
-    red = torch.cat([stats[[0, 2, 3]], csum.double() * 0])         # sums
-    mx = stats[1:2].clone()
-    cs = csum.clone()
-    if world > 1:                                                   # the ONLY collective on the path
-        dist.all_reduce(red, op=dist.ReduceOp.SUM)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
-    verify = {"mean_residual": float(red[0].item()) / max(1.0, B * world - float(red[1].item())),
-              "max_residual": float(mx.item()), "failed_systems": int(red[1].item()),
-              "nonfinite_systems": int(red[2].item()), "ok_checksum": int(cs.item()) & ((1 << 64) - 1)}
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
-    clocks = sampler.stop()
-    # oracle check on a sample of the timed run's output (first 2 tiles + last tile)
+    csum = gm.checksum(ok, word_offset=checksum_word_offset(lo, 1))
+    verify = {}
     try:
-        from oracle import pyoracle as po
-        W = A.W
-        tiles = [0, 1, A.tiles - 1]
-        okc = True
-        orc = po.best()
-        for tl in tiles:
-            sub = lambda c, E: gm.BatchSoA(W, E, torch.float32, dev, c.data[tl * E * W:(tl + 1) * E * W]).to_aos().cpu().numpy()
-            _, xe, oke = orc.linear_solve(sub(A, 16), sub(b, 4), n)
-            xg = sub(x, 4)
-            okc &= bool(np.array_equal(xg.view(np.uint32), xe.view(np.uint32)))
-            okc &= bool(np.array_equal(ok[tl * W:(tl + 1) * W].cpu().numpy(), oke))
-        verify["oracle_sample_bit_exact"] = okc
-        verify["oracle"] = orc.kind
+        nv, nbad = verify_solve_sample(c, A, b, x, ok, n, 1 << 20, torch.float32)
+        verify["oracle"] = oracle(c).kind
     except Exception as ex:
-        verify["oracle_sample_bit_exact"] = None
+        nv, nbad = 0, 0
         verify["oracle_error"] = repr(ex)[:200]
+    red = reduce_stats({"residual_sum": float(stats[0]), "residual_max": float(stats[1]), "failed": float(stats[2]),
+                        "nonfinite": float(stats[3]), "verified": float(nv), "mismatches": float(nbad),
+                        "checksum": int(csum.item())}, device=dev)
+    solved = max(1.0, B * world - red["failed"])
+    # residual threshold: |Ax - b| <= c * eps * cond-like growth; for this generator (|a|,|b| < 4, n = 4) a solved system
+    # with max residual above 2^-4 of max|b| would be a wrong answer; ill-conditioned systems sit well below it
+    verify.update({"mean_residual": red["residual_sum"] / solved, "max_residual": red["residual_max"],
+                   "failed_systems": int(red["failed"]), "nonfinite_systems": int(red["nonfinite"]),
+                   "ok_checksum": int(red["checksum"]), "verified_systems": int(red["verified"]), "mismatches": int(red["mismatches"]),
+                   "oracle_sample_bit_exact": int(red["mismatches"]) == 0 and int(red["verified"]) > 0,
+                   "bit_exact_caveat": "oracle/_ref is geomc compiled by g++ 13 -ffp-contract=fast (+2 flags, DESIGN.md 4); the reference's own toolchain is clang"})
 
     value = B * world * args.steps / (total_ms_max * 1e-3)
     avg_launch_ms = statistics.mean(per_launch_ms)
     achieved = ALG_BYTES * B / (avg_launch_ms * 1e-3) / 1e9
     traffic = read_traffic()
+    tr = traffic.get("plu_solve_f32_soa_bytes_per_system")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None if traffic is None else traffic * B, "peak_source": peak_src,
+                "traffic": None if tr is None else tr * B, "traffic_source": traffic.get("source"), "peak_source": peak_src,
                 "kernel": "gmb::k_plu_solve<float,4,1,row_major,SoA>", "alg_bytes_per_system": ALG_BYTES,
                 "avg_launch_ms": avg_launch_ms, "min_launch_ms": min(per_launch_ms),
                 "frac_of_nominal_8TBs": achieved / 8000.0}
+    del A, b, x
 
     sides = []
-    if not args.no_sides and world == 1:
-        f32, f64 = torch.float32, torch.float64
-        # C1 from AoS (ingest included)
-        Aa, ba = A.to_aos(), b.to_aos()
-        xa = torch.empty_like(ba)
-        sides.append(side_config(gm, torch, "4x4 f32 PLU solve, AoS in/out (reference objects)",
-                                 lambda: gm.linear_solve(Aa, ba, 4, x_out=xa, ok_out=ok), 96, B, peak))
-        # C3: 4x4 f32 inverse (AoS SimpleMatrix<float,4,4> and SoA)
-        inv_out = torch.empty_like(Aa)
-        sides.append(side_config(gm, torch, "C3: 4x4 f32 inverse, AoS", lambda: gm.inv(Aa, 4, out=inv_out, ok_out=ok), 128, B, peak))
-        inv_soa = A.empty_like()
-        sides.append(side_config(gm, torch, "C3: 4x4 f32 inverse, SoA", lambda: gm.inv(A, 4, out=inv_soa, ok_out=ok), 128, B, peak))
-        del Aa, ba, xa, inv_out, inv_soa
-        # C2: 3x3 f64 SPD cholesky + solve, 2^24 systems
-        R = torch.randint(-128, 128, (B, 3, 3), device=dev, generator=g).double() * 2.0 ** -5
-        S = (R @ R.transpose(1, 2) + torch.eye(3, device=dev, dtype=f64)).reshape(B, 9).contiguous()
-        bs = torch.randint(-(1 << 19), 1 << 19, (B, 3), device=dev, generator=g).double() * 2.0 ** -17
-        Ss, bss = gm.BatchSoA.from_aos(S), gm.BatchSoA.from_aos(bs)
-        xs = bss.empty_like()
-        # algorithmic bytes: the factorization reads only the LOWER triangle (Cholesky.h:42-44), so the SoA
-        # kernel never touches the 3 upper-triangle planes: 48 + 24 read, 24 written = 96 B (the survey's
-        # 120 B counts the full 72-byte matrix, which the AoS path does pull in sector-wise).
-        sides.append(side_config(gm, torch, "C2: 3x3 f64 SPD cholesky + solve, SoA (96 B/system: lower triangle only)",
-                                 lambda: gm.cholesky_solve(Ss, bss, 3, x_out=xs, ok_out=ok), 96, B, peak))
-        xs_a = torch.empty_like(bs)
-        sides.append(side_config(gm, torch, "C2: 3x3 f64 SPD cholesky + solve, AoS (120 B/system: whole records)",
-                                 lambda: gm.cholesky_solve(S, bs, 3, x_out=xs_a, ok_out=ok), 120, B, peak))
-        del R, S, bs, Ss, bss, xs, xs_a
-        # C4: f64 PLU decompose N = 2..8 (one homogeneous sub-batch per N; working set >> L2 for every N)
-        for nn in range(2, 9):
-            Bc = 1 << (23 if nn <= 4 else 22)
-            M = gm.BatchSoA(Bc, nn * nn, f64, dev)
-            M.data.copy_(torch.randint(-(1 << 19), 1 << 19, M.data.shape, device=dev, generator=g).double() * 2.0 ** -17)
-            outs = (torch.empty((Bc, nn), dtype=torch.uint8, device=dev), torch.empty(Bc, dtype=torch.uint8, device=dev),
-                    torch.empty(Bc, dtype=torch.uint8, device=dev))
-            sides.append(side_config(gm, torch, f"C4: {nn}x{nn} f64 PLU decompose (in place), SoA, 2^{23 if nn <= 4 else 22} systems",
-                                     lambda: gm.decomp_plu(M, nn, inplace=True, out=outs), 16 * nn * nn + nn + 2, Bc, peak, reps=3))
-            del M, outs
-        # row (f)1: orthogonal<float,3> (cross product) and <float,4> (3x4 PLU + back-substitution), AoS Vec arrays
-        for nn in (3, 4):
-            Vn = torch.randint(-(1 << 19), 1 << 19, (B, (nn - 1) * nn), device=dev, generator=g).float() * 2.0 ** -17
-            sides.append(side_config(gm, torch, f"(f)1: orthogonal<float,{nn}>, AoS Vec arrays", lambda: gm.orthogonal(Vn, nn),
-                                     4 * ((nn - 1) * nn + nn), B, peak, reps=3))
-            del Vn
-        # C5: 16x16 f32 PLU solve, 2^21 systems
-        B5 = 1 << 21
-        A16 = torch.randint(-(1 << 19), 1 << 19, (B5, 256), device=dev, generator=g).float() * 2.0 ** -17
-        b16 = torch.randint(-(1 << 19), 1 << 19, (B5, 16), device=dev, generator=g).float() * 2.0 ** -17
-        x16 = torch.empty_like(b16)
-        ok16 = torch.zeros(B5, dtype=torch.uint8, device=dev)
-        sides.append(side_config(gm, torch, "C5: 16x16 f32 PLU solve, AoS",
-                                 lambda: gm.linear_solve(A16, b16, 16, x_out=x16, ok_out=ok16), 1152, B5, peak, reps=3))
-        del A16, b16, x16
+    if not args.no_sides:
+        for fn in (config_c1_small, config_c2, config_c3, config_c4, config_c5):
+            try:
+                torch.cuda.synchronize()
+                r = fn(c)
+                sides.extend(r if isinstance(r, list) else [r])
+            except Exception as ex:     # a side config must never take the headline down
+                import traceback
+                traceback.print_exc()
+                sides.append({"config": fn.__name__, "error": repr(ex)[:300]})
+            torch.cuda.empty_cache()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     cpu = None
     if not args.no_cpu and world == 1:
@@ -449,9 +750,20 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "n": n, "rhs": 1, "systems_per_gpu_per_step": B, "layout": "SoA-interleaved (resident in HBM)",
                        "l2": "inputs+outputs per step = 1.5 GiB per GPU >> 126 MB L2 (no flush needed)",
-                       "sharding": f"contiguous, {world} rank(s), no data-path collective"},
+                       "sharding": f"contiguous (shard_range), {world} rank(s), no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "verify": verify, "other_configs": sides}
+    if args.config != "C1":
+        pick = [s for s in sides if s.get("config") == args.config and "systems_per_s" in s]
+        if pick:
+            p = pick[0]
+            line.update({"metric": f"systems/sec ({p['workload']})", "value": p["systems_per_s"], "ms_per_step": p["ms_per_step"],
+                         "steps": p["steps"], "scaling": p.get("scaling", "weak"),
+                         "dtype": "f64" if args.config in ("C2", "C4") else "f32",
+                         "config": {"workload": p["workload"], "systems_per_step": p["systems_per_step"]},
+                         "roofline": {"bound": "hbm", "achieved": p["hbm_frac"] * peak, "peak": peak, "unit": "GB/s", "frac": p["hbm_frac"],
+                                      "traffic": None, "peak_source": peak_src, "alg_bytes_per_system": p["alg_bytes_per_system"]},
+                         "e2e": p.get("e2e", line["e2e"]), "c1": {"value": value, "roofline": roofline, "verify": verify}})
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -55,13 +55,17 @@ _TYPED = {
     "gmb_host_inv": [_i, _i64, _vp, _vp, _vp, _i, _i, _i],
     "gmb_host_cholesky_solve": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i],
     "gmb_host_plu_decomp": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i],
+    "gmb_host_plu_solve_multi": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _i, _vp, _i],
+    "gmb_host_inv_multi": [_i, _i64, _vp, _vp, _vp, _i, _i, _vp, _i],
+    "gmb_host_cholesky_solve_multi": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp, _i],
+    "gmb_host_plu_decomp_multi": [_i, _i, _i64, _vp, _vp, _vp, _vp, _i, _vp, _i],
 }
 
 # every symbol include/geomc_b200.h declares (tests/test_abi.py checks the header against this)
 UNTYPED = ["gmb_version", "gmb_error_string", "gmb_device_count", "gmb_soa_tile_width", "gmb_soa_elems",
            "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count", "gmb_set_option", "gmb_set_device",
            "gmb_device_alloc", "gmb_device_free", "gmb_memcpy_h2d", "gmb_memcpy_d2h", "gmb_memset_device",
-           "gmb_stream_synchronize"]
+           "gmb_stream_synchronize", "gmb_get_device", "gmb_host_register", "gmb_host_unregister", "gmb_shard_range"]
 EXPORTS = UNTYPED + [f"{k}_{s}" for k in _TYPED for s in ("f32", "f64")]
 
 
@@ -99,6 +103,14 @@ def lib() -> C.CDLL:
     L.gmb_set_option.argtypes = [C.c_char_p, _i]
     L.gmb_set_device.restype = _i
     L.gmb_set_device.argtypes = [_i]
+    L.gmb_get_device.restype = _i
+    L.gmb_get_device.argtypes = [C.POINTER(_i)]
+    L.gmb_host_register.restype = _i
+    L.gmb_host_register.argtypes = [_vp, C.c_size_t]
+    L.gmb_host_unregister.restype = _i
+    L.gmb_host_unregister.argtypes = [_vp]
+    L.gmb_shard_range.restype = _i
+    L.gmb_shard_range.argtypes = [_i64, _i, _i, _i64, C.POINTER(_i64), C.POINTER(_i64)]
     L.gmb_device_alloc.restype = _vp
     L.gmb_device_alloc.argtypes = [C.c_size_t]
     L.gmb_device_free.restype = None

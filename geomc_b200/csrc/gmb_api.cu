@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "gmb_common.cuh"
@@ -28,6 +29,9 @@ template <typename T> int small_backsolve(int, int, int, int64_t, const T*, cons
 template <typename T> int small_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
 template <typename T> int small_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int small_solve_vec(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, cudaStream_t);
+template <typename T> int small_inv_elem(int, int64_t, const T*, T*, uint8_t*, int, int, cudaStream_t);
+template <typename T> int small_solve_vec_elem(int, int, int64_t, const T*, const T*, T*, uint8_t*, cudaStream_t);
+template <typename T> int small_residual(int, int64_t, const T*, const T*, const T*, const uint8_t*, double*, int, int, cudaStream_t);
 // gmb_subwarp.cu
 template <typename T> int subwarp_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int subwarp_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
@@ -191,8 +195,10 @@ int linear_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X,
     cudaStream_t st = as_stream(stream);
     if (n < 5) {
         // inverse-then-multiply: LUDecomp.h:419-426 (skip is ignored on this path, as in the reference)
-        if (n >= 2 && m <= 4 && all_aligned16(bases, Bv, X)) return small_solve_vec<T>(n, m, B, bases, Bv, X, ok, layout, st);
-        return GMB_ERR_UNSUPPORTED;
+        if (n < 2 || m > 4) return GMB_ERR_UNSUPPORTED;
+        if (all_aligned16(bases, Bv, X)) return small_solve_vec<T>(n, m, B, bases, Bv, X, ok, layout, st);
+        if (layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;      // the container is aligned by construction
+        return small_solve_vec_elem<T>(n, m, B, bases, Bv, X, ok, st); // an array of Vec objects: element-aligned only
     }
     // n >= 5: column-major PLU + permutation + column-major back-substitution (:428-439)
     return plu_solve<T>(n, m, B, bases, Bv, X, ok, nullptr, skip, layout, /*row_major=*/0, stream);
@@ -211,7 +217,7 @@ int cholesky(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok
         int rc = small_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
-    if (n >= 5) {
+    if (fast && n >= 5) {
         int rc = subwarp_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
@@ -227,9 +233,10 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (n >= 5 && A == Ainv) return GMB_ERR_INVALID_ARG;   // invNxN: m must not alias out (MatrixInv.h:174)
     if (n >= 2 && n <= 4) {
-        // adjugate path only exists in the register kernels (the generic kernel is PLU-based and would
-        // change the arithmetic): an unaligned AoS batch is rejected rather than computed differently
-        return fast ? small_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st) : GMB_ERR_INVALID_ARG;
+        // adjugate (MatrixInv.h:49-165) in both cases: vectorised register kernel, or -- for an AoS batch that is only
+        // element-aligned, e.g. an offset into an array of objects -- the same arithmetic with scalar accesses
+        return fast ? small_inv<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st)
+                    : small_inv_elem<T>(n, B, A, Ainv, ok, src_rm, dst_rm, st);
     }
     // The row-distributed kernel (gmb_rowinv.cuh) is 1.2x (7 x 7 double) to 3x (16 x 16 float) faster than the
     // column-distributed one from n = 8 (float) / n = 6 (double) on and slower below (profiles/r1j_row_inverse.md);
@@ -311,6 +318,20 @@ int nullspace(int N, int nb, int64_t B, const T* bases, T* null, uint8_t* ok, in
 // AoS host batches are cut into chunks; each chunk goes H2D -> kernel -> D2H on its own stream
 // (3 slots round-robin) so uploads, kernels and downloads of neighbouring chunks overlap and both
 // PCIe directions stay busy.  Device staging buffers are cached per device.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        status = cudaSetDevice(device);
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 struct HostArg {
     const void* src;     // host source (inputs) or nullptr
     void* dst;           // host destination (outputs) or nullptr
@@ -348,9 +369,8 @@ static int run_host_pipeline(int device, int64_t B, std::vector<HostArg>& args, 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return GMB_ERR_NO_DEVICE;
     if (device < 0 || device >= ndev) return GMB_ERR_INVALID_ARG;
     if (B == 0) return GMB_OK;
-    int prev = 0;
-    cudaGetDevice(&prev);
-    cudaError_t e = cudaSetDevice(device);
+    DeviceGuard guard(device);                       // the caller's current device is restored on every return path
+    cudaError_t e = guard.status;
     if (e != cudaSuccess) return (int)e;
     HostCtx* ctx = host_ctx(device);
     std::lock_guard<std::mutex> g(ctx->mu);
@@ -409,8 +429,47 @@ static int run_host_pipeline(int device, int64_t B, std::vector<HostArg>& args, 
         e = cudaStreamSynchronize(s.stream);
         if (e != cudaSuccess && rc == GMB_OK) rc = (int)e;
     }
-    cudaSetDevice(prev);
     return rc;
+}
+
+// ------------------------------------------------------------------ several devices of one box
+// Independent systems: device k of `ndev` serves the contiguous shard shard_range(B, k, ndev, 1024) through its own
+// host pipeline on its own host thread.  No collective, no peer traffic; the shards of the host arrays are disjoint.
+static void shard_range(int64_t B, int rank, int world, int64_t align, int64_t* lo, int64_t* hi) {
+    const int64_t units = (B + align - 1) / align;
+    const int64_t per = units / world, extra = units % world;
+    const int64_t b = rank * per + (rank < extra ? rank : extra);
+    const int64_t e = b + per + (rank < extra ? 1 : 0);
+    *lo = b * align < B ? b * align : B;
+    *hi = e * align < B ? e * align : B;
+}
+
+template <class Shard>
+static int run_multi_device(int64_t B, const int* devices, int ndev, Shard&& shard) {
+    if (ndev < 1 || devices == nullptr || B < 0) return GMB_ERR_INVALID_ARG;
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have <= 0) return GMB_ERR_NO_DEVICE;
+    for (int k = 0; k < ndev; ++k) {
+        if (devices[k] < 0 || devices[k] >= have) return GMB_ERR_INVALID_ARG;
+        for (int j = 0; j < k; ++j)
+            if (devices[j] == devices[k]) return GMB_ERR_INVALID_ARG;
+    }
+    std::vector<int> rcs((size_t)ndev, GMB_OK);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < ndev; ++k) {
+        int64_t lo, hi;
+        shard_range(B, k, ndev, 1024, &lo, &hi);
+        if (hi <= lo) continue;
+        if (ndev == 1) {
+            rcs[0] = shard(lo, hi, devices[0]);
+        } else {
+            workers.emplace_back([&, k, lo, hi] { rcs[(size_t)k] = shard(lo, hi, devices[k]); });
+        }
+    }
+    for (auto& w : workers) w.join();
+    for (int rc : rcs)
+        if (rc != GMB_OK) return rc;
+    return GMB_OK;
 }
 
 template <typename T>
@@ -566,7 +625,29 @@ void gmb_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int gmb_host_register(void* p, size_t bytes) {
+    if (!p || bytes == 0) return GMB_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) cudaGetLastError();
+    return (int)e;
+}
+int gmb_host_unregister(void* p) {
+    if (!p) return GMB_ERR_INVALID_ARG;
+    const cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) cudaGetLastError();
+    return (int)e;
+}
+int gmb_shard_range(int64_t B, int rank, int world, int64_t align, int64_t* begin, int64_t* end) {
+    if (B < 0 || world < 1 || rank < 0 || rank >= world || align < 1 || !begin || !end) return GMB_ERR_INVALID_ARG;
+    shard_range(B, rank, world, align, begin, end);
+    return GMB_OK;
+}
+
 int gmb_set_device(int device) { return (int)cudaSetDevice(device); }
+int gmb_get_device(int* device) {
+    if (!device) return GMB_ERR_INVALID_ARG;
+    return (int)cudaGetDevice(device);
+}
 void* gmb_device_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
@@ -685,6 +766,10 @@ int gmb_stream_synchronize(void* stream) { return (int)cudaStreamSynchronize(as_
     int gmb_solve_residual_##SUF(int n, int64_t B, const T* A, const T* X, const T* Bm, const uint8_t* ok,            \
                                  double* stats4, int layout, int row_major, void* stream) {                           \
         if (B < 0 || n < 1 || (B > 0 && (!A || !X || !Bm || !stats4))) return GMB_ERR_INVALID_ARG;                    \
+        if (n >= 2 && n <= 4 && all_aligned16(A, X, Bm)) {                                                            \
+            int rc = small_residual<T>(n, B, A, X, Bm, ok, stats4, layout, row_major, as_stream(stream));             \
+            if (rc != GMB_ERR_UNSUPPORTED) return rc;                                                                 \
+        }                                                                                                             \
         return residual_stats<T>(n, B, A, X, Bm, ok, stats4, layout, row_major, as_stream(stream));                   \
     }                                                                                                                 \
     int gmb_host_plu_solve_##SUF(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, int skip,       \
@@ -702,6 +787,38 @@ int gmb_stream_synchronize(void* stream) { return (int)cudaStreamSynchronize(as_
     int gmb_host_plu_decomp_##SUF(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity,                \
                                   uint8_t* degen, int row_major, int device) {                                        \
         return host_plu_decomp<T>(rows, cols, B, A, perm, parity, degen, row_major, device);                          \
+    }                                                                                                                 \
+    int gmb_host_plu_solve_multi_##SUF(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, int skip, \
+                                       int row_major, const int* devices, int ndev) {                                 \
+        if (n < 1 || m < 1 || (B > 0 && (!A || !Bm || !X))) return GMB_ERR_INVALID_ARG;                               \
+        return run_multi_device(B, devices, ndev, [&](int64_t lo, int64_t hi, int dev) {                              \
+            return host_plu_solve<T>(n, m, hi - lo, A + lo * n * n, Bm + lo * n * m, X + lo * n * m,                  \
+                                     ok ? ok + lo : nullptr, skip, row_major, dev);                                   \
+        });                                                                                                           \
+    }                                                                                                                 \
+    int gmb_host_inv_multi_##SUF(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int src_row_major,               \
+                                 int dst_row_major, const int* devices, int ndev) {                                   \
+        if (n < 1 || (B > 0 && (!A || !Ainv))) return GMB_ERR_INVALID_ARG;                                            \
+        return run_multi_device(B, devices, ndev, [&](int64_t lo, int64_t hi, int dev) {                              \
+            return host_inv<T>(n, hi - lo, A + lo * n * n, Ainv + lo * n * n, ok ? ok + lo : nullptr, src_row_major,  \
+                               dst_row_major, dev);                                                                   \
+        });                                                                                                           \
+    }                                                                                                                 \
+    int gmb_host_cholesky_solve_multi_##SUF(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok,      \
+                                            int row_major, const int* devices, int ndev) {                            \
+        if (n < 1 || m < 1 || (B > 0 && (!A || !Bm || !X))) return GMB_ERR_INVALID_ARG;                               \
+        return run_multi_device(B, devices, ndev, [&](int64_t lo, int64_t hi, int dev) {                              \
+            return host_cholesky_solve<T>(n, m, hi - lo, A + lo * n * n, Bm + lo * n * m, X + lo * n * m,             \
+                                          ok ? ok + lo : nullptr, row_major, dev);                                    \
+        });                                                                                                           \
+    }                                                                                                                 \
+    int gmb_host_plu_decomp_multi_##SUF(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* parity,          \
+                                        uint8_t* degen, int row_major, const int* devices, int ndev) {                \
+        if (rows < 1 || cols < 1 || (B > 0 && !A)) return GMB_ERR_INVALID_ARG;                                        \
+        return run_multi_device(B, devices, ndev, [&](int64_t lo, int64_t hi, int dev) {                              \
+            return host_plu_decomp<T>(rows, cols, hi - lo, A + lo * rows * cols, perm ? perm + lo * rows : nullptr,   \
+                                      parity ? parity + lo : nullptr, degen ? degen + lo : nullptr, row_major, dev);  \
+        });                                                                                                           \
     }
 
 GMB_DEFINE(f32, float)

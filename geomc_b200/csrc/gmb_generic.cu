@@ -398,11 +398,13 @@ g_transpose(int E, int64_t B, const T* __restrict__ src, T* __restrict__ dst) {
     const int64_t nsys = (B - s_base) < W ? (B - s_base) : W;          // systems valid in this tile
     const int64_t aos_elems = nsys * E;
     const int tot = W * E;
+    // the AoS side may be an array of objects that is only element-aligned: scalar accesses there (warp-uniform test)
+    const bool al16 = (reinterpret_cast<uintptr_t>(TO_SOA ? src + s_base * E : dst + s_base * E) & 15) == 0;
     if (TO_SOA) {
         const T* a = src + s_base * E;
         for (int g = threadIdx.x * V; g < tot; g += 128 * V) {
             T t[V];
-            if (g + V <= aos_elems) {
+            if (al16 && g + V <= aos_elems) {
                 unpack(ldg_stream(reinterpret_cast<const VT*>(a + g)), t);
             } else {
 #pragma unroll
@@ -441,7 +443,7 @@ g_transpose(int E, int64_t B, const T* __restrict__ src, T* __restrict__ dst) {
                 const int sys = (g + v) / E, e = (g + v) - sys * E;
                 t[v] = sm[sys * EP + e];
             }
-            if (g + V <= aos_elems) {
+            if (al16 && g + V <= aos_elems) {
                 *reinterpret_cast<VT*>(d + g) = pack(t);
             } else {
 #pragma unroll
@@ -540,6 +542,7 @@ int checksum_bytes(const void* data, int64_t nbytes, int64_t word_offset, uint64
 template <typename T>
 int transpose_batch(bool to_soa, int E, int64_t B, const T* src, T* dst, cudaStream_t st) {
     if (E < 1 || E > 1024) return GMB_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(to_soa ? dst : src) % 16 != 0) return GMB_ERR_INVALID_ARG;   // the container is aligned by construction
     constexpr int W = soa_w<T>();
     const unsigned grid = (unsigned)ceil_div(B, W);
     if (grid == 0) return GMB_OK;

@@ -247,6 +247,55 @@ k_solve_vec_small(const T* __restrict__ bases, const T* Bv, T* X, uint8_t* __res
     store_bytes<V, 1>(ok, s0, B, okv);
 }
 
+// ============================================================ a10 / a7 for AoS batches that are only element-aligned
+// An array of the reference's objects is 4- or 8-byte aligned, not 16: these two kernels run the SAME arithmetic
+// (inv_flat, the fma product) with scalar loads and stores, one system per thread.  Slower than the vectorised kernels
+// (every 32-byte sector is touched by several instructions) but bit-identical, so the alignment of a batch never
+// changes its results.
+template <typename T, int N, bool TRANSPOSE_OUT>
+__global__ void __launch_bounds__(kThreads)
+k_inv_small_elem(const T* A, T* Ainv, uint8_t* __restrict__ ok, int64_t B) {
+    const int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (s >= B) return;
+    T qa[N * N], out[N * N];
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) qa[e] = A[s * (N * N) + e];
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) out[e] = qa[e];
+    const bool good = inv_flat<T>(out, qa);
+    if (ok != nullptr) ok[s] = good ? 1 : 0;
+    if (!good) return;                                        // "out is unchanged" (MatrixInv.h:45-46)
+#pragma unroll
+    for (int r = 0; r < N; ++r)
+#pragma unroll
+        for (int c = 0; c < N; ++c) Ainv[s * (N * N) + N * r + c] = out[TRANSPOSE_OUT ? N * c + r : N * r + c];
+}
+
+template <typename T, int N, int M>
+__global__ void __launch_bounds__(kThreads)
+k_solve_vec_small_elem(const T* __restrict__ bases, const T* Bv, T* X, uint8_t* __restrict__ ok, int64_t B) {
+    const int64_t s = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (s >= B) return;
+    T qa[N * N], qb[N * M], inv[N * N];
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) qa[e] = bases[s * (N * N) + e];
+#pragma unroll
+    for (int e = 0; e < N * M; ++e) qb[e] = Bv[s * (N * M) + e];
+#pragma unroll
+    for (int e = 0; e < N * N; ++e) inv[e] = (T)0;
+    const bool good = inv_flat<T>(inv, qa);
+    if (ok != nullptr) ok[s] = good ? 1 : 0;
+#pragma unroll
+    for (int c = 0; c < M; ++c)
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            T sum = (T)0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) sum = fma_rn(inv[N * k + r], qb[N * c + k], sum);
+            X[s * (N * M) + N * c + r] = good ? sum : qb[N * c + r];
+        }
+}
+
 // ============================================================ (f)1: orthogonal, N <= 4
 // Orthogonal.h:73-110: N = 2 left_perpendicular, N = 3 cross product (diff_of_products), N = 4
 // rectangular decomp_plu of the 3 x 4 matrix + back-substitution from o[3] = 1; the zero vector when
@@ -291,6 +340,90 @@ k_orthogonal_small(const T* __restrict__ Vin, T* __restrict__ Out, int64_t B) {
         }
     }
     store_elems<T, N, SOA>(Out, unit, lane, B, qo);
+}
+
+// ============================================================ batch statistics of a solve (test / verify path)
+// max_r |sum_c A(r,c) x(c) - b(r)| per system in double, then {sum, max, #ok == 0, #non-finite} over the batch.  Same
+// tile access as the solve it verifies (128-bit plane loads in the container): reads the same 96 bytes per 4 x 4 float
+// system and should run at the same HBM-bound rate (the element-wise generic kernel ran at 0.14 of the peak).
+template <typename T, int N, bool RM, bool SOA>
+__global__ void __launch_bounds__(kThreads)
+k_residual_small(const T* __restrict__ A, const T* __restrict__ X, const T* __restrict__ Bm, const uint8_t* __restrict__ ok,
+                 double* __restrict__ stats, int64_t B) {
+    using Wk = Work<T, SOA>;
+    constexpr int V = Wk::V;
+    int64_t unit, s0;
+    int lane;
+    double sum = 0.0, mx = 0.0, failed = 0.0, nonfinite = 0.0;
+    if (Wk::locate(B, unit, lane, s0)) {
+        T qa[V][N * N], qx[V][N], qb[V][N];
+        load_elems<T, N * N, SOA>(A, unit, lane, B, qa);
+        load_elems<T, N, SOA>(X, unit, lane, B, qx);
+        load_elems<T, N, SOA>(Bm, unit, lane, B, qb);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (s0 + v >= B) continue;
+            if (ok != nullptr && ok[s0 + v] == 0) {
+                failed += 1.0;
+                continue;
+            }
+            double res = 0.0;
+            bool fin = true;
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+                double acc = -(double)qb[v][r];
+#pragma unroll
+                for (int c = 0; c < N; ++c) acc = fma((double)qa[v][RM ? N * r + c : N * c + r], (double)qx[v][c], acc);
+                res = fmax(res, fabs(acc));
+                fin = fin && isfinite(acc);
+            }
+            if (fin) {
+                sum += res;
+                mx = fmax(mx, res);
+            } else {
+                nonfinite += 1.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        failed += __shfl_xor_sync(0xffffffffu, failed, o);
+        nonfinite += __shfl_xor_sync(0xffffffffu, nonfinite, o);
+    }
+    __shared__ double part[kThreads / 32][4];
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        part[w][0] = sum; part[w][1] = mx; part[w][2] = failed; part[w][3] = nonfinite;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 1; i < kThreads / 32; ++i) {
+            sum += part[i][0]; mx = fmax(mx, part[i][1]); failed += part[i][2]; nonfinite += part[i][3];
+        }
+        if (sum != 0.0) atomicAdd(&stats[0], sum);
+        if (mx != 0.0) atomicMax(reinterpret_cast<unsigned long long*>(&stats[1]), (unsigned long long)__double_as_longlong(mx));
+        if (failed != 0.0) atomicAdd(&stats[2], failed);
+        if (nonfinite != 0.0) atomicAdd(&stats[3], nonfinite);
+    }
+}
+
+template <typename T>
+int small_residual(int n, int64_t B, const T* A, const T* X, const T* Bm, const uint8_t* ok, double* stats, int layout,
+                   int rm, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+            dispatch_bool(rm != 0, [&](auto RM) {
+                const int64_t grid = Work<T, SOA.value>::grid(B);
+                if (grid > 0) k_residual_small<T, N.value, RM.value, SOA.value><<<(unsigned)grid, kThreads, 0, st>>>(A, X, Bm, ok, stats, B);
+                rc = grid > 0 ? after_launch() : GMB_OK;
+            });
+        });
+    });
+    return rc;
 }
 
 template <typename T>
@@ -409,6 +542,28 @@ int small_inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, in
 }
 
 template <typename T>
+int small_inv_elem(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int src_rm, int dst_rm, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_bool((src_rm != 0) != (dst_rm != 0), [&](auto TR) {
+            GMB_LAUNCH((k_inv_small_elem<T, N.value, TR.value>), (ceil_div(B, kThreads)), st, A, Ainv, ok, B);
+        });
+    });
+    return rc;
+}
+
+template <typename T>
+int small_solve_vec_elem(int n, int m, int64_t B, const T* bases, const T* Bv, T* X, uint8_t* ok, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<2, 3, 4>(n, [&](auto N) {
+        dispatch_int<1, 2, 3, 4>(m, [&](auto M) {
+            GMB_LAUNCH((k_solve_vec_small_elem<T, N.value, M.value>), (ceil_div(B, kThreads)), st, bases, Bv, X, ok, B);
+        });
+    });
+    return rc;
+}
+
+template <typename T>
 int small_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X, uint8_t* ok, int layout,
                     cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
@@ -433,7 +588,11 @@ int small_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X, 
                                    cudaStream_t);                                                                      \
     template int small_inv<T>(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);                      \
     template int small_solve_vec<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, cudaStream_t);          \
-    template int small_orthogonal<T>(int, int64_t, const T*, T*, int, cudaStream_t);
+    template int small_inv_elem<T>(int, int64_t, const T*, T*, uint8_t*, int, int, cudaStream_t);                      \
+    template int small_solve_vec_elem<T>(int, int, int64_t, const T*, const T*, T*, uint8_t*, cudaStream_t);           \
+    template int small_orthogonal<T>(int, int64_t, const T*, T*, int, cudaStream_t);                                   \
+    template int small_residual<T>(int, int64_t, const T*, const T*, const T*, const uint8_t*, double*, int, int,      \
+                                   cudaStream_t);
 
 INSTANTIATE(float)
 INSTANTIATE(double)

@@ -35,8 +35,45 @@ from ._lib import LAYOUT_AOS, LAYOUT_SOA
 _SUF = {torch.float32: "f32", torch.float64: "f64"}
 
 
-def _stream_ptr(device) -> int:
-    return torch.cuda.current_stream(device).cuda_stream
+class _Stream(int):
+    """The raw cudaStream_t of torch's current stream on `device`, remembering the device it belongs to."""
+    device = None
+
+
+def _stream_ptr(device) -> "_Stream":
+    st = _Stream(torch.cuda.current_stream(device).cuda_stream)
+    st.device = device
+    return st
+
+
+def _call(name: str, suf: str, *args) -> None:
+    """C ABI call whose last argument is a _Stream: the stream's device is made current for the duration of the call
+    (kernel launches and cudaFuncSetAttribute go to the CURRENT device, which need not be the tensors' device)."""
+    st = args[-1]
+    with torch.cuda.device(st.device):
+        _lib.call(name, suf, *args[:-1], int(st))
+
+
+def _same(a: "Batch", *others, what: str = "operands") -> None:
+    """dtype, device and layout of every operand must equal those of `a` (the C ABI takes raw pointers)."""
+    la, _, _, dta, deva, _ = _info(a)
+    for o in others:
+        if o is None:
+            continue
+        lo, _, _, dto, devo, _ = _info(o)
+        if (lo, dto, devo) != (la, dta, deva):
+            raise ValueError(f"{what}: layout / dtype / device differ ({lo}, {dto}, {devo}) vs ({la}, {dta}, {deva})")
+
+
+def _shape(x: "Batch", B: int, E: int, what: str) -> None:
+    _, Bx, Ex, _, _, _ = _info(x)
+    if (Bx, Ex) != (B, E):
+        raise ValueError(f"{what}: expected ({B}, {E}), got ({Bx}, {Ex})")
+
+
+def _flags(t: torch.Tensor, B: int, device, what: str) -> None:
+    if t.dtype != torch.uint8 or t.device != device or t.numel() < B or not t.is_contiguous():
+        raise ValueError(f"{what}: a contiguous uint8 tensor of {B} entries on {device} is required")
 
 
 class BatchSoA:
@@ -69,12 +106,12 @@ class BatchSoA:
         assert aos.is_cuda and aos.dim() == 2 and aos.is_contiguous()
         B, E = aos.shape
         out = cls(B, E, aos.dtype, aos.device)
-        _lib.call("gmb_aos_to_soa", _SUF[aos.dtype], E, B, aos.data_ptr(), out.data.data_ptr(), _stream_ptr(aos.device))
+        _call("gmb_aos_to_soa", _SUF[aos.dtype], E, B, aos.data_ptr(), out.data.data_ptr(), _stream_ptr(aos.device))
         return out
 
     def to_aos(self) -> torch.Tensor:
         out = torch.empty((self.B, self.E), dtype=self.dtype, device=self.device)
-        _lib.call("gmb_soa_to_aos", _SUF[self.dtype], self.E, self.B, self.data.data_ptr(), out.data_ptr(),
+        _call("gmb_soa_to_aos", _SUF[self.dtype], self.E, self.B, self.data.data_ptr(), out.data_ptr(),
                   _stream_ptr(self.device))
         return out
 
@@ -129,7 +166,7 @@ def decomp_plu(m: Batch, rows: int, cols: Optional[int] = None, row_major: bool 
         perm, parity, degen = out
     else:
         perm, parity, degen = _u8(B, rows, dev).reshape(B, rows), _u8(B, 1, dev), _u8(B, 1, dev)
-    _lib.call("gmb_plu_decomp", _SUF[dt], rows, cols, B, _ptr(lu), perm.data_ptr(), parity.data_ptr(), degen.data_ptr(),
+    _call("gmb_plu_decomp", _SUF[dt], rows, cols, B, _ptr(lu), perm.data_ptr(), parity.data_ptr(), degen.data_ptr(),
               layout, int(row_major), _stream_ptr(dev))
     return lu, perm, parity, degen
 
@@ -141,7 +178,7 @@ def decomp_lup(m: Batch, rows: int, cols: Optional[int] = None, row_major: bool 
     assert E == rows * cols
     lu = m if inplace else _clone(m)
     perm, parity, degen = _u8(B, cols, dev).reshape(B, cols), _u8(B, 1, dev), _u8(B, 1, dev)
-    _lib.call("gmb_lup_decomp", _SUF[dt], rows, cols, B, _ptr(lu), perm.data_ptr(), parity.data_ptr(), degen.data_ptr(),
+    _call("gmb_lup_decomp", _SUF[dt], rows, cols, B, _ptr(lu), perm.data_ptr(), parity.data_ptr(), degen.data_ptr(),
               layout, int(row_major), _stream_ptr(dev))
     return lu, perm, parity, degen
 
@@ -149,9 +186,11 @@ def decomp_lup(m: Batch, rows: int, cols: Optional[int] = None, row_major: bool 
 def backsolve_lu(lu: Batch, x: Batch, n: int, m: int = 1, skip: int = 0, row_major: bool = True, inplace: bool = False):
     """Solve L U X = X_in (X already permuted).  -> X."""
     layout, B, E, dt, dev, _ = _info(lu)
-    assert E == n * n and _info(x)[2] == n * m and _info(x)[0] == layout
+    assert E == n * n
+    _same(lu, x, what="backsolve_lu")
+    _shape(x, B, n * m, "backsolve_lu: x")
     out = x if inplace else _clone(x)
-    _lib.call("gmb_lu_backsolve", _SUF[dt], n, m, B, _ptr(lu), _ptr(out), skip, layout, int(row_major), _stream_ptr(dev))
+    _call("gmb_lu_backsolve", _SUF[dt], n, m, B, _ptr(lu), _ptr(out), skip, layout, int(row_major), _stream_ptr(dev))
     return out
 
 
@@ -159,8 +198,10 @@ def backsolve_plu(plu: Batch, p: torch.Tensor, b: Batch, n: int, m: int = 1, ski
     """Solve L U X = P B given the row-source array p (uint8[B,n]).  -> X."""
     layout, B, E, dt, dev, _ = _info(plu)
     assert E == n * n and p.dtype == torch.uint8 and p.is_contiguous()
+    _same(plu, b, what="backsolve_plu")
+    _shape(b, B, n * m, "backsolve_plu: b")
     x = _new_like(b)
-    _lib.call("gmb_plu_backsolve", _SUF[dt], n, m, B, _ptr(plu), p.data_ptr(), _ptr(x), _ptr(b), skip, layout,
+    _call("gmb_plu_backsolve", _SUF[dt], n, m, B, _ptr(plu), p.data_ptr(), _ptr(x), _ptr(b), skip, layout,
               int(row_major), _stream_ptr(dev))
     return x
 
@@ -170,7 +211,7 @@ def apply_permutation(p: torch.Tensor, a: Batch, n: int, m: int, row_major: bool
     layout, B, E, dt, dev, _ = _info(a)
     assert E == n * m and p.dtype == torch.uint8
     out = a if inplace else _clone(a)
-    _lib.call("gmb_apply_permutation", _SUF[dt], n, m, B, p.data_ptr(), _ptr(out), layout, int(row_major), _stream_ptr(dev))
+    _call("gmb_apply_permutation", _SUF[dt], n, m, B, p.data_ptr(), _ptr(out), layout, int(row_major), _stream_ptr(dev))
     return out
 
 
@@ -181,11 +222,15 @@ def linear_solve(a: Batch, b: Batch, n: int, m: int = 1, skip: int = 0, row_majo
     ok[s] == 0 iff the reference returns false; then x[s] == b[s] ("x untouched").
     """
     layout, B, E, dt, dev, _ = _info(a)
-    assert E == n * n and _info(b)[2] == n * m and _info(b)[0] == layout
+    assert E == n * n
+    _same(a, b, x_out, what="linear_solve")
+    _shape(b, B, n * m, "linear_solve: b")
     x = _new_like(b) if x_out is None else x_out
+    _shape(x, B, n * m, "linear_solve: x_out")
     ok = _u8(B, 1, dev) if ok_out is None else ok_out
+    _flags(ok, B, dev, "linear_solve: ok_out")
     lu = _new_like(a) if want_lu else None
-    _lib.call("gmb_plu_solve", _SUF[dt], n, m, B, _ptr(a), _ptr(b), _ptr(x), ok.data_ptr(), _ptr(lu), skip, layout,
+    _call("gmb_plu_solve", _SUF[dt], n, m, B, _ptr(a), _ptr(b), _ptr(x), ok.data_ptr(), _ptr(lu), skip, layout,
               int(row_major), _stream_ptr(dev))
     return (x, ok, lu) if want_lu else (x, ok)
 
@@ -193,10 +238,12 @@ def linear_solve(a: Batch, b: Batch, n: int, m: int = 1, skip: int = 0, row_majo
 def linear_solve_vec(bases: Batch, b: Batch, n: int, m: int = 1, skip: int = 0):
     """Vec-form linear_solve: bases = n column vectors; n < 5 is inverse-then-multiply.  -> (x, ok)."""
     layout, B, E, dt, dev, _ = _info(bases)
-    assert E == n * n and _info(b)[2] == n * m
+    assert E == n * n
+    _same(bases, b, what="linear_solve_vec")
+    _shape(b, B, n * m, "linear_solve_vec: b")
     x = _new_like(b)
     ok = _u8(B, 1, dev)
-    _lib.call("gmb_linear_solve_vec", _SUF[dt], n, m, B, _ptr(bases), _ptr(b), _ptr(x), ok.data_ptr(), skip, layout,
+    _call("gmb_linear_solve_vec", _SUF[dt], n, m, B, _ptr(bases), _ptr(b), _ptr(x), ok.data_ptr(), skip, layout,
               _stream_ptr(dev))
     return x, ok
 
@@ -207,7 +254,7 @@ def cholesky(a: Batch, n: int, row_major: bool = True, inplace: bool = False):
     assert E == n * n
     l = a if inplace else _clone(a)
     ok = _u8(B, 1, dev)
-    _lib.call("gmb_cholesky", _SUF[dt], n, B, _ptr(l), ok.data_ptr(), layout, int(row_major), _stream_ptr(dev))
+    _call("gmb_cholesky", _SUF[dt], n, B, _ptr(l), ok.data_ptr(), layout, int(row_major), _stream_ptr(dev))
     return l, ok
 
 
@@ -215,11 +262,15 @@ def cholesky_solve(a: Batch, b: Batch, n: int, m: int = 1, row_major: bool = Tru
                    ok_out: Optional[torch.Tensor] = None, want_l: bool = False):
     """Fused Cholesky factor + solve (framework-defined; the reference has no Cholesky solve).  -> (x, ok[, L])."""
     layout, B, E, dt, dev, _ = _info(a)
-    assert E == n * n and _info(b)[2] == n * m
+    assert E == n * n
+    _same(a, b, x_out, what="cholesky_solve")
+    _shape(b, B, n * m, "cholesky_solve: b")
     x = _new_like(b) if x_out is None else x_out
+    _shape(x, B, n * m, "cholesky_solve: x_out")
     ok = _u8(B, 1, dev) if ok_out is None else ok_out
+    _flags(ok, B, dev, "cholesky_solve: ok_out")
     l = _new_like(a) if want_l else None
-    _lib.call("gmb_cholesky_solve", _SUF[dt], n, m, B, _ptr(a), _ptr(b), _ptr(x), ok.data_ptr(), _ptr(l), layout,
+    _call("gmb_cholesky_solve", _SUF[dt], n, m, B, _ptr(a), _ptr(b), _ptr(x), ok.data_ptr(), _ptr(l), layout,
               int(row_major), _stream_ptr(dev))
     return (x, ok, l) if want_l else (x, ok)
 
@@ -232,8 +283,11 @@ def inv(a: Batch, n: int, src_row_major: bool = True, dst_row_major: bool = True
     if out is None:
         out = _new_like(a)
         (out.data if isinstance(out, BatchSoA) else out).zero_()
+    _same(a, out, what="inv")
+    _shape(out, B, n * n, "inv: out")
     ok = _u8(B, 1, dev) if ok_out is None else ok_out
-    _lib.call("gmb_inv", _SUF[dt], n, B, _ptr(a), _ptr(out), ok.data_ptr(), layout, int(src_row_major),
+    _flags(ok, B, dev, "inv: ok_out")
+    _call("gmb_inv", _SUF[dt], n, B, _ptr(a), _ptr(out), ok.data_ptr(), layout, int(src_row_major),
               int(dst_row_major), _stream_ptr(dev))
     return out, ok
 
@@ -243,7 +297,7 @@ def orthogonal(v: Batch, n: int) -> Batch:
     layout, B, E, dt, dev, _ = _info(v)
     assert E == (n - 1) * n
     out = _new_like(v, n)
-    _lib.call("gmb_orthogonal", _SUF[dt], n, B, _ptr(v), _ptr(out), layout, _stream_ptr(dev))
+    _call("gmb_orthogonal", _SUF[dt], n, B, _ptr(v), _ptr(out), layout, _stream_ptr(dev))
     return out
 
 
@@ -253,7 +307,7 @@ def nullspace(bases: Batch, N: int, nb: int):
     assert E == nb * N and 1 <= nb < N
     null = _new_like(bases, (N - nb) * N)
     ok = _u8(B, 1, dev)
-    _lib.call("gmb_nullspace", _SUF[dt], N, nb, B, _ptr(bases), _ptr(null), ok.data_ptr(), layout, _stream_ptr(dev))
+    _call("gmb_nullspace", _SUF[dt], N, nb, B, _ptr(bases), _ptr(null), ok.data_ptr(), layout, _stream_ptr(dev))
     return null, ok
 
 
@@ -264,7 +318,7 @@ def simplex_contains(verts: Batch, p: Batch, dim: int, nverts: Optional[torch.Te
     layout, B, E, dt, dev, _ = _info(verts)
     assert E == (dim + 1) * dim and _info(p)[2] == dim
     inside = _u8(B, 1, dev)
-    _lib.call("gmb_simplex_contains", _SUF[dt], dim, B, _ptr(verts), 0, None if nverts is None else nverts.data_ptr(),
+    _call("gmb_simplex_contains", _SUF[dt], dim, B, _ptr(verts), 0, None if nverts is None else nverts.data_ptr(),
               _ptr(p), inside.data_ptr(), layout, _stream_ptr(dev))
     return inside
 
@@ -281,7 +335,7 @@ def trace_simplex(verts: Batch, origin: Batch, direction: Batch, dim: int, want_
     if want_uv:
         uv = _new_like(verts, dim - 1)
         (uv.data if isinstance(uv, BatchSoA) else uv).zero_()
-    _lib.call("gmb_trace_simplex", _SUF[dt], dim, B, _ptr(verts), 0, _ptr(origin), _ptr(direction), 0, hit.data_ptr(),
+    _call("gmb_trace_simplex", _SUF[dt], dim, B, _ptr(verts), 0, _ptr(origin), _ptr(direction), 0, hit.data_ptr(),
               s.data_ptr(), _ptr(uv), layout, _stream_ptr(dev))
     return hit, s, uv
 
@@ -291,7 +345,7 @@ def simplex_intersect(verts: Batch, origin: Batch, direction: Batch, dim: int, n
     layout, B, E, dt, dev, _ = _info(verts)
     assert E == (dim + 1) * dim and _info(origin)[2] == dim and _info(direction)[2] == dim
     interval = _new_like(verts, 2)
-    _lib.call("gmb_simplex_intersect", _SUF[dt], dim, B, _ptr(verts), 0, None if nverts is None else nverts.data_ptr(),
+    _call("gmb_simplex_intersect", _SUF[dt], dim, B, _ptr(verts), 0, None if nverts is None else nverts.data_ptr(),
               _ptr(origin), _ptr(direction), 0, _ptr(interval), layout, _stream_ptr(dev))
     return interval
 
@@ -306,7 +360,7 @@ def mul(a: Batch, b: Batch, r: int, k: int, c: int, out: Optional[Batch] = None,
         assert not acc, "mul_acc needs the destination to accumulate into"
         out = _new_like(a, r * c)
     assert _info(out)[2] == r * c and _info(out)[0] == layout
-    _lib.call("gmb_mul", _SUF[dt], r, k, c, B, _ptr(a), _ptr(b), _ptr(out), int(acc), layout, int(a_row_major),
+    _call("gmb_mul", _SUF[dt], r, k, c, B, _ptr(a), _ptr(b), _ptr(out), int(acc), layout, int(a_row_major),
               int(b_row_major), int(d_row_major), _stream_ptr(dev))
     return out
 
@@ -321,7 +375,7 @@ def xf_from_matrix(m: Batch, dim: int, row_major: bool = True) -> Tuple[Batch, t
     assert E == dim * dim
     xf = _new_like(m, 2 * (dim + 1) ** 2)
     ok = _u8(B, 1, dev)
-    _lib.call("gmb_xf_from_matrix", _SUF[dt], dim, B, _ptr(m), _ptr(xf), ok.data_ptr(), layout, int(row_major),
+    _call("gmb_xf_from_matrix", _SUF[dt], dim, B, _ptr(m), _ptr(xf), ok.data_ptr(), layout, int(row_major),
               _stream_ptr(dev))
     return xf, ok
 
@@ -330,7 +384,7 @@ def _xf_from_vec(name: str, t: Batch, dim: int) -> Batch:
     layout, B, E, dt, dev, _ = _info(t)
     assert E == dim
     xf = _new_like(t, 2 * (dim + 1) ** 2)
-    _lib.call(name, _SUF[dt], dim, B, _ptr(t), _ptr(xf), layout, _stream_ptr(dev))
+    _call(name, _SUF[dt], dim, B, _ptr(t), _ptr(xf), layout, _stream_ptr(dev))
     return xf
 
 
@@ -349,7 +403,7 @@ def xf_compose(xf1: Batch, xf2: Batch, dim: int, inverse: bool = False) -> Batch
     layout, B, E, dt, dev, _ = _info(xf1)
     assert E == 2 * (dim + 1) ** 2 and _info(xf2)[2] == E and _info(xf2)[0] == layout
     out = _new_like(xf1)
-    _lib.call("gmb_xf_compose", _SUF[dt], dim, B, _ptr(xf1), _ptr(xf2), _ptr(out), int(inverse), layout, _stream_ptr(dev))
+    _call("gmb_xf_compose", _SUF[dt], dim, B, _ptr(xf1), _ptr(xf2), _ptr(out), int(inverse), layout, _stream_ptr(dev))
     return out
 
 
@@ -369,7 +423,7 @@ def xf_apply(xf, p: Batch, dim: int, mode: str = "apply") -> Batch:
         assert _info(xf)[0] == layout and _info(xf)[1] == B and _info(xf)[2] == E_xf
         count, pxf = B, _ptr(xf)
     out = _new_like(p)
-    _lib.call("gmb_xf_apply", _SUF[dt], dim, XF_MODES.index(mode), B, pxf, count, _ptr(p), _ptr(out), layout,
+    _call("gmb_xf_apply", _SUF[dt], dim, XF_MODES.index(mode), B, pxf, count, _ptr(p), _ptr(out), layout,
               _stream_ptr(dev))
     return out
 
@@ -378,7 +432,7 @@ def solve_residual(a: Batch, x: Batch, b: Batch, ok: Optional[torch.Tensor], n: 
     """Device-side batch statistics: [sum of per-system max|Ax-b|, max, #ok==0, #non-finite] (float64[4])."""
     layout, B, E, dt, dev, _ = _info(a)
     stats = torch.zeros(4, dtype=torch.float64, device=dev)
-    _lib.call("gmb_solve_residual", _SUF[dt], n, B, _ptr(a), _ptr(x), _ptr(b), None if ok is None else ok.data_ptr(),
+    _call("gmb_solve_residual", _SUF[dt], n, B, _ptr(a), _ptr(x), _ptr(b), None if ok is None else ok.data_ptr(),
               stats.data_ptr(), layout, int(row_major), _stream_ptr(dev))
     return stats
 
@@ -411,37 +465,76 @@ def checksum_host(buf) -> int:
 
 # ------------------------------------------------------------------------- host-buffer entry points
 def _host_ptr(t):
+    """(address, dtype name) of a contiguous numpy array or CPU torch tensor."""
     import numpy as np
     if isinstance(t, np.ndarray):
         assert t.flags["C_CONTIGUOUS"]
-        return t.ctypes.data, t.dtype.itemsize
+        return t.ctypes.data, t.dtype.name
     assert not t.is_cuda and t.is_contiguous()
-    return t.data_ptr(), t.element_size()
+    return t.data_ptr(), str(t.dtype).replace("torch.", "")
 
 
-def host_linear_solve(a, b, x, ok, n: int, m: int = 1, skip: int = 0, row_major: bool = True, device: int = 0) -> None:
-    """Host AoS buffers in, host buffers out (pipelined H2D / kernel / D2H).  numpy or CPU torch tensors."""
-    pa, sz = _host_ptr(a)
+def _host_suf(*arrays) -> str:
+    """f32 / f64 from the DTYPE of the floating-point operands (they must all agree; anything else is refused)."""
+    names = {_host_ptr(a)[1] for a in arrays}
+    if names == {"float32"}:
+        return "f32"
+    if names == {"float64"}:
+        return "f64"
+    raise TypeError(f"host batches must be all float32 or all float64, got {sorted(names)}")
+
+
+def _host_u8(t) -> int:
+    p, name = _host_ptr(t)
+    if name != "uint8":
+        raise TypeError(f"flag / index outputs are uint8 arrays, got {name}")
+    return p
+
+
+def host_linear_solve(a, b, x, ok, n: int, m: int = 1, skip: int = 0, row_major: bool = True, device=0) -> None:
+    """Host AoS buffers in, host buffers out (pipelined H2D / kernel / D2H).  numpy or CPU torch tensors.
+    `device` is one device index, or a sequence of them: the batch is then sharded contiguously over those GPUs
+    (gmb_host_plu_solve_multi_*: one pipeline and one host thread per device, no collective)."""
+    suf = _host_suf(a, b, x)
     B = a.shape[0]
-    _lib.call("gmb_host_plu_solve", "f32" if sz == 4 else "f64", n, m, B, pa, _host_ptr(b)[0], _host_ptr(x)[0],
-              _host_ptr(ok)[0], skip, int(row_major), device)
+    if isinstance(device, (list, tuple)):
+        devs = (C.c_int * len(device))(*device)
+        _lib.call("gmb_host_plu_solve_multi", suf, n, m, B, _host_ptr(a)[0], _host_ptr(b)[0], _host_ptr(x)[0], _host_u8(ok), skip,
+                  int(row_major), C.cast(devs, C.c_void_p), len(device))
+        return
+    _lib.call("gmb_host_plu_solve", suf, n, m, B, _host_ptr(a)[0], _host_ptr(b)[0], _host_ptr(x)[0], _host_u8(ok), skip,
+              int(row_major), device)
 
 
-def host_inv(a, out, ok, n: int, src_row_major: bool = True, dst_row_major: bool = True, device: int = 0) -> None:
-    pa, sz = _host_ptr(a)
-    _lib.call("gmb_host_inv", "f32" if sz == 4 else "f64", n, a.shape[0], pa, _host_ptr(out)[0], _host_ptr(ok)[0],
-              int(src_row_major), int(dst_row_major), device)
+def host_inv(a, out, ok, n: int, src_row_major: bool = True, dst_row_major: bool = True, device=0) -> None:
+    suf = _host_suf(a, out)
+    if isinstance(device, (list, tuple)):
+        devs = (C.c_int * len(device))(*device)
+        _lib.call("gmb_host_inv_multi", suf, n, a.shape[0], _host_ptr(a)[0], _host_ptr(out)[0], _host_u8(ok), int(src_row_major),
+                  int(dst_row_major), C.cast(devs, C.c_void_p), len(device))
+        return
+    _lib.call("gmb_host_inv", suf, n, a.shape[0], _host_ptr(a)[0], _host_ptr(out)[0], _host_u8(ok), int(src_row_major),
+              int(dst_row_major), device)
 
 
-def host_cholesky_solve(a, b, x, ok, n: int, m: int = 1, row_major: bool = True, device: int = 0) -> None:
-    pa, sz = _host_ptr(a)
-    _lib.call("gmb_host_cholesky_solve", "f32" if sz == 4 else "f64", n, m, a.shape[0], pa, _host_ptr(b)[0],
-              _host_ptr(x)[0], _host_ptr(ok)[0], int(row_major), device)
+def host_cholesky_solve(a, b, x, ok, n: int, m: int = 1, row_major: bool = True, device=0) -> None:
+    suf = _host_suf(a, b, x)
+    if isinstance(device, (list, tuple)):
+        devs = (C.c_int * len(device))(*device)
+        _lib.call("gmb_host_cholesky_solve_multi", suf, n, m, a.shape[0], _host_ptr(a)[0], _host_ptr(b)[0], _host_ptr(x)[0],
+                  _host_u8(ok), int(row_major), C.cast(devs, C.c_void_p), len(device))
+        return
+    _lib.call("gmb_host_cholesky_solve", suf, n, m, a.shape[0], _host_ptr(a)[0], _host_ptr(b)[0], _host_ptr(x)[0],
+              _host_u8(ok), int(row_major), device)
 
 
-def host_decomp_plu(a, perm, parity, degen, rows: int, cols: Optional[int] = None, row_major: bool = True,
-                    device: int = 0) -> None:
+def host_decomp_plu(a, perm, parity, degen, rows: int, cols: Optional[int] = None, row_major: bool = True, device=0) -> None:
     cols = rows if cols is None else cols
-    pa, sz = _host_ptr(a)
-    _lib.call("gmb_host_plu_decomp", "f32" if sz == 4 else "f64", rows, cols, a.shape[0], pa, _host_ptr(perm)[0],
-              _host_ptr(parity)[0], _host_ptr(degen)[0], int(row_major), device)
+    suf = _host_suf(a)
+    if isinstance(device, (list, tuple)):
+        devs = (C.c_int * len(device))(*device)
+        _lib.call("gmb_host_plu_decomp_multi", suf, rows, cols, a.shape[0], _host_ptr(a)[0], _host_u8(perm), _host_u8(parity),
+                  _host_u8(degen), int(row_major), C.cast(devs, C.c_void_p), len(device))
+        return
+    _lib.call("gmb_host_plu_decomp", suf, rows, cols, a.shape[0], _host_ptr(a)[0], _host_u8(perm), _host_u8(parity),
+              _host_u8(degen), int(row_major), device)

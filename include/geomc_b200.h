@@ -270,6 +270,11 @@ int gmb_checksum_bytes(const void* data, int64_t nbytes, int64_t word_offset, ui
  * Pinned buffers (gmb_host_alloc, or cudaHostRegister'ed memory) give full PCIe bandwidth. */
 void* gmb_host_alloc(size_t bytes);
 void gmb_host_free(void* p);
+/* Pin / unpin memory the application already owns (an array of SimpleMatrix objects, a std::vector's storage) so that
+ * the host entry points reach full PCIe bandwidth on it without a copy into a pinned staging buffer.  Returns a
+ * cudaError_t (> 0) when the range cannot be registered; the host entry points still work on pageable memory. */
+int gmb_host_register(void* p, size_t bytes);
+int gmb_host_unregister(void* p);
 int gmb_host_plu_solve_f32(int n, int m, int64_t B, const float* A, const float* Bm, float* X, uint8_t* ok,
                            int skip, int row_major, int device);
 int gmb_host_plu_solve_f64(int n, int m, int64_t B, const double* A, const double* Bm, double* X, uint8_t* ok,
@@ -286,6 +291,28 @@ int gmb_host_plu_decomp_f64(int rows, int cols, int64_t B, double* A_inout, uint
                             uint8_t* degenerate, int row_major, int device);
 int gmb_host_plu_decomp_f32(int rows, int cols, int64_t B, float* A_inout, uint8_t* perm, uint8_t* parity,
                             uint8_t* degenerate, int row_major, int device);
+/* ---- several GPUs of one box -------------------------------------------------------------------
+ * The systems of a batch are independent, so a batch is sharded CONTIGUOUSLY over devices[0..ndev): device k serves
+ * systems [begin, end) = gmb_shard_range(B, k, ndev, 1024) of every host array through its own host pipeline, driven
+ * by its own host thread.  There is no collective and no peer traffic on the data path; the call returns when every
+ * shard's results are in the host buffers.  ndev = 1 is the single-device call.  Devices must be distinct. */
+int gmb_shard_range(int64_t B, int rank, int world, int64_t align, int64_t* begin, int64_t* end);
+int gmb_host_plu_solve_multi_f32(int n, int m, int64_t B, const float* A, const float* Bm, float* X, uint8_t* ok,
+                                 int skip, int row_major, const int* devices, int ndev);
+int gmb_host_plu_solve_multi_f64(int n, int m, int64_t B, const double* A, const double* Bm, double* X, uint8_t* ok,
+                                 int skip, int row_major, const int* devices, int ndev);
+int gmb_host_inv_multi_f32(int n, int64_t B, const float* A, float* Ainv, uint8_t* ok, int src_row_major,
+                           int dst_row_major, const int* devices, int ndev);
+int gmb_host_inv_multi_f64(int n, int64_t B, const double* A, double* Ainv, uint8_t* ok, int src_row_major,
+                           int dst_row_major, const int* devices, int ndev);
+int gmb_host_cholesky_solve_multi_f32(int n, int m, int64_t B, const float* A, const float* Bm, float* X,
+                                      uint8_t* ok, int row_major, const int* devices, int ndev);
+int gmb_host_cholesky_solve_multi_f64(int n, int m, int64_t B, const double* A, const double* Bm, double* X,
+                                      uint8_t* ok, int row_major, const int* devices, int ndev);
+int gmb_host_plu_decomp_multi_f32(int rows, int cols, int64_t B, float* A_inout, uint8_t* perm, uint8_t* parity,
+                                  uint8_t* degenerate, int row_major, const int* devices, int ndev);
+int gmb_host_plu_decomp_multi_f64(int rows, int cols, int64_t B, double* A_inout, uint8_t* perm, uint8_t* parity,
+                                  uint8_t* degenerate, int row_major, const int* devices, int ndev);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t gmb_launch_count(void);
 /* Dispatch options for tests and tuning (the library never reads the environment).  value = -1 restores the measured
@@ -298,6 +325,7 @@ int gmb_set_option(const char* name, int value);
 /* ---- device memory and streams for hosts that do not link the CUDA runtime themselves --------
  * (include/geomc_b200/batch.hpp builds with a plain C++ compiler on top of these). */
 int gmb_set_device(int device);
+int gmb_get_device(int* device);
 void* gmb_device_alloc(size_t bytes);                 /* NULL on failure */
 void gmb_device_free(void* p);
 int gmb_memcpy_h2d(void* dst_device, const void* src_host, size_t bytes, void* stream);

@@ -226,16 +226,56 @@ inline index_t count_false(const std::uint8_t* ok, index_t B) {
     for (index_t i = 0; i < B; ++i) n += ok[i] ? 0 : 1;
     return n;
 }
+// Makes `device` current for a scope and restores the caller's device on every exit path (exceptions included).
+class DeviceScope {
+public:
+    explicit DeviceScope(int device) {
+        if (gmb_get_device(&prev_) != GMB_OK) prev_ = -1;
+        detail::DeviceScope scope(device);
+    }
+    ~DeviceScope() {
+        if (prev_ >= 0) gmb_set_device(prev_);
+    }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+private:
+    int prev_ = -1;
+};
+// The reference's bool results: a bool is one byte holding 0 or 1, which is exactly what the kernels write, so a
+// caller's bool[B] receives the flags directly; a scratch array stands in when the caller passes nullptr.
+static_assert(sizeof(bool) == 1, "bool[B] is used as the uint8 flag array of the C ABI");
+struct OkFlags {
+    std::vector<std::uint8_t> scratch;
+    std::uint8_t* p;
+    OkFlags(bool* ok, index_t B) : scratch(ok ? 0 : (std::size_t)B), p(ok ? reinterpret_cast<std::uint8_t*>(ok) : scratch.data()) {}
+};
 }  // namespace detail
+
+// Pins an application-owned host range for the lifetime of the object (gmb_host_register): the host and object forms
+// then move it over PCIe at full speed with no staging copy.  Registration failure is not an error (`pinned()` tells).
+class PinnedScope {
+public:
+    PinnedScope(const void* p, std::size_t bytes) : p_(const_cast<void*>(p)) {
+        ok_ = p_ && bytes && gmb_host_register(p_, bytes) == GMB_OK;
+    }
+    ~PinnedScope() {
+        if (ok_) gmb_host_unregister(p_);
+    }
+    PinnedScope(const PinnedScope&) = delete;
+    PinnedScope& operator=(const PinnedScope&) = delete;
+    bool pinned() const { return ok_; }
+private:
+    void* p_;
+    bool ok_ = false;
+};
 
 // for (s < B) ok[s] = geom::linear_solve<T,RowMajor>(a + s*n*n, n, m, x + s*n*m, skip);
 // Difference from the reference: `a` is left intact (the reference leaves the LU factors in it).
 template <typename T, bool RowMajor = true>
 index_t linear_solve(const T* a, index_t n, index_t m, T* x, index_t B, bool* ok = nullptr, index_t skip = 0, int device = 0) {
-    std::vector<std::uint8_t> okb((std::size_t)B);
-    check(Abi<T>::host_plu_solve((int)n, (int)m, B, a, x, x, okb.data(), (int)skip, RowMajor ? 1 : 0, device), "linear_solve");
-    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
-    return detail::count_false(okb.data(), B);
+    detail::OkFlags okb(ok, B);
+    check(Abi<T>::host_plu_solve((int)n, (int)m, B, a, x, x, okb.p, (int)skip, RowMajor ? 1 : 0, device), "linear_solve");
+    return detail::count_false(okb.p, B);
 }
 
 // for (s < B) degenerate[s] = geom::decomp_plu<T,RowMajor>(m + s*rows*cols, rows, cols, reorder + s*rows, parity + s);
@@ -252,40 +292,72 @@ void decomp_plu(T* m, index_t rows, index_t cols, index_t B, index_t* reorder, b
 // for (s < B) ok[s] = geom::cholesky<T,RowMajor>(...) followed by the L L^T solve of x (new).
 template <typename T, bool RowMajor = true>
 index_t cholesky_solve(const T* a, index_t n, index_t m, T* x, index_t B, bool* ok = nullptr, int device = 0) {
-    std::vector<std::uint8_t> okb((std::size_t)B);
-    check(Abi<T>::host_cholesky_solve((int)n, (int)m, B, a, x, x, okb.data(), RowMajor ? 1 : 0, device), "cholesky_solve");
-    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
-    return detail::count_false(okb.data(), B);
+    detail::OkFlags okb(ok, B);
+    check(Abi<T>::host_cholesky_solve((int)n, (int)m, B, a, x, x, okb.p, RowMajor ? 1 : 0, device), "cholesky_solve");
+    return detail::count_false(okb.p, B);
 }
 
 // for (s < B) ok[s] = inv2x2/3x3/4x4/invNxN on flat arrays; `out` untouched where ok == false.
 template <typename T>
 index_t inv(T* out, const T* src, index_t n, index_t B, bool* ok = nullptr, bool src_row_major = true,
             bool dst_row_major = true, int device = 0) {
-    std::vector<std::uint8_t> okb((std::size_t)B);
-    check(Abi<T>::host_inv((int)n, B, src, out, okb.data(), src_row_major ? 1 : 0, dst_row_major ? 1 : 0, device), "inv");
-    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
-    return detail::count_false(okb.data(), B);
+    detail::OkFlags okb(ok, B);
+    check(Abi<T>::host_inv((int)n, B, src, out, okb.p, src_row_major ? 1 : 0, dst_row_major ? 1 : 0, device), "inv");
+    return detail::count_false(okb.p, B);
 }
 
 // ================================================================= (3) object forms
 // Arrays of the reference's own objects, duck-typed: Mx needs `elem_t`, static `ROWDIM`, `COLDIM`,
 // `Layout` (0 = ROW_MAJOR, 1 = COL_MAJOR: LinalgTypes.h:36-39) and `data_begin()`; Vec needs
-// `begin()`.  Objects whose size is not N*N*sizeof(T) (SimpleMatrix<float,3,3> is 40 bytes) are
-// packed into a temporary.
+// `begin()`.  An array of objects that ARE their elements (sizeof(Mx) == E * sizeof(T), data_begin() == this:
+// SimpleMatrix<float,4,4> is 64 packed bytes) goes to the host entry points AS IT IS -- no repacking, no staging copy;
+// only objects with alignment padding (SimpleMatrix<float,3,3> is 40 bytes) are packed into a temporary.
 namespace detail {
 template <typename Mx> using elem_of = typename Mx::elem_t;
-template <typename Mx>
-std::vector<elem_of<Mx>> pack(const Mx* m, index_t B, int E) {
-    std::vector<elem_of<Mx>> v((std::size_t)(B * E));
-    for (index_t s = 0; s < B; ++s) std::memcpy(v.data() + s * E, m[s].data_begin(), sizeof(elem_of<Mx>) * (std::size_t)E);
-    return v;
+template <typename Mx, int E>
+bool is_packed_array(const Mx* m, index_t B) {
+    if (sizeof(Mx) != sizeof(elem_of<Mx>) * (std::size_t)E) return false;
+    return B <= 0 || reinterpret_cast<const char*>(m[0].data_begin()) == reinterpret_cast<const char*>(&m[0]);
 }
-template <typename Mx>
-void unpack(Mx* m, const std::vector<elem_of<Mx>>& v, index_t B, int E, const std::uint8_t* only_where) {
-    for (index_t s = 0; s < B; ++s)
-        if (!only_where || only_where[s]) std::memcpy(m[s].data_begin(), v.data() + s * E, sizeof(elem_of<Mx>) * (std::size_t)E);
-}
+// Read-only / read-write view of an object array as the flat T[B][E] the C ABI takes.
+template <typename Mx, int E>
+struct FlatIn {
+    std::vector<elem_of<Mx>> tmp;
+    const elem_of<Mx>* p;
+    FlatIn(const Mx* m, index_t B) {
+        if (is_packed_array<Mx, E>(m, B)) {
+            p = reinterpret_cast<const elem_of<Mx>*>(m);
+        } else {
+            tmp.resize((std::size_t)(B * E));
+            for (index_t s = 0; s < B; ++s) std::memcpy(tmp.data() + s * E, m[s].data_begin(), sizeof(elem_of<Mx>) * (std::size_t)E);
+            p = tmp.data();
+        }
+    }
+};
+template <typename Mx, int E>
+struct FlatOut {
+    Mx* m;
+    index_t B;
+    bool direct;
+    std::vector<elem_of<Mx>> tmp;
+    elem_of<Mx>* p;
+    // load_current: the objects' present contents matter (accumulation, "untouched on failure")
+    FlatOut(Mx* m_, index_t B_, bool load_current) : m(m_), B(B_), direct(is_packed_array<Mx, E>(m_, B_)) {
+        if (direct) {
+            p = reinterpret_cast<elem_of<Mx>*>(m);
+        } else {
+            tmp.resize((std::size_t)(B * E));
+            if (load_current)
+                for (index_t s = 0; s < B; ++s) std::memcpy(tmp.data() + s * E, m[s].data_begin(), sizeof(elem_of<Mx>) * (std::size_t)E);
+            p = tmp.data();
+        }
+    }
+    void commit(const std::uint8_t* only_where = nullptr) {
+        if (direct) return;
+        for (index_t s = 0; s < B; ++s)
+            if (!only_where || only_where[s]) std::memcpy(m[s].data_begin(), tmp.data() + s * E, sizeof(elem_of<Mx>) * (std::size_t)E);
+    }
+};
 }  // namespace detail
 
 // for (s < B) ok[s] = geom::inv(&into[s], src[s]);          Matrix.h:717 (static N = 2..16)
@@ -295,13 +367,12 @@ index_t inv(Md* into, const Mx* src, index_t B, bool* ok = nullptr, int device =
     constexpr int N = (int)(Mx::ROWDIM > Mx::COLDIM ? Mx::ROWDIM : Mx::COLDIM);
     static_assert(N >= 2 && N <= GMB_MAX_N, "static dimension 2..16 required");
     static_assert(std::is_same<T, detail::elem_of<Md>>::value, "element types must agree");
-    auto a = detail::pack(src, B, N * N);
-    auto o = detail::pack(into, B, N * N);                  // current contents: "untouched on failure"
-    std::vector<std::uint8_t> okb((std::size_t)B);
-    check(Abi<T>::host_inv(N, B, a.data(), o.data(), okb.data(), (int)Mx::Layout == 0 ? 1 : 0, (int)Md::Layout == 0 ? 1 : 0, device), "inv");
-    detail::unpack(into, o, B, N * N, okb.data());
-    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
-    return detail::count_false(okb.data(), B);
+    detail::FlatIn<Mx, N * N> a(src, B);
+    detail::FlatOut<Md, N * N> o(into, B, /*load_current=*/true);      // current contents: "untouched on failure"
+    detail::OkFlags okb(ok, B);
+    check(Abi<T>::host_inv(N, B, a.p, o.p, okb.p, (int)Mx::Layout == 0 ? 1 : 0, (int)Md::Layout == 0 ? 1 : 0, device), "inv");
+    o.commit(okb.p);
+    return detail::count_false(okb.p, B);
 }
 
 // for (s < B) ok[s] = geom::cholesky(&m[s]);                Cholesky.h:83 (row-major arithmetic on begin())
@@ -314,19 +385,18 @@ index_t cholesky(Mx* m, index_t B, bool* ok = nullptr, int device = 0) {
     // whatever the storage layout; a symmetric input makes the two coincide for reading, and the
     // factor is written to logical (r,c).
     const bool rm = (int)Mx::Layout == 0;
-    auto a = detail::pack(m, B, N * N);
-    std::vector<std::uint8_t> okb((std::size_t)B);
+    detail::DeviceScope scope(device);                       // before any allocation: the buffers must live on `device`
+    detail::FlatOut<Mx, N * N> a(m, B, /*load_current=*/true);
+    detail::OkFlags okb(ok, B);
     DeviceBatch<T> d(B, N * N, Layout::AoS);
     DeviceArray<std::uint8_t> dok((std::size_t)B);
-    check(gmb_set_device(device), "set_device");
-    d.upload_aos(a.data());
+    d.upload_aos(a.p);
     check(Abi<T>::cholesky(N, B, d.data(), dok.get(), GMB_LAYOUT_AOS, rm ? 1 : 0, nullptr), "cholesky");
-    d.download_aos(a.data());
-    dok.download(okb.data(), (std::size_t)B);
+    d.download_aos(a.p);
+    dok.download(okb.p, (std::size_t)B);
     check(gmb_stream_synchronize(nullptr), "sync");
-    detail::unpack(m, a, B, N * N, nullptr);
-    if (ok) for (index_t i = 0; i < B; ++i) ok[i] = okb[(std::size_t)i] != 0;
-    return detail::count_false(okb.data(), B);
+    a.commit();
+    return detail::count_false(okb.p, B);
 }
 
 // for (s < B) ok[s] = geom::linear_solve<T,N>(bases[s], 1, &x[s], skip);      LUDecomp.h:417
@@ -336,7 +406,7 @@ template <typename V>
 index_t linear_solve_vec(const V* bases, V* x, index_t N, index_t B, bool* ok = nullptr, index_t skip = 0, int device = 0) {
     using T = typename std::remove_cv<typename std::remove_reference<decltype(*std::declval<V&>().begin())>::type>::type;
     static_assert(sizeof(V) % sizeof(T) == 0, "packed vectors expected (VecBase.h:112)");
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     DeviceBatch<T> dA(B, (int)(N * N), Layout::AoS), dX(B, (int)N, Layout::AoS);
     DeviceArray<std::uint8_t> dok((std::size_t)B);
     dA.upload_aos(reinterpret_cast<const T*>(bases));
@@ -361,7 +431,7 @@ using vec_elem = typename std::remove_cv<typename std::remove_reference<decltype
 template <typename V>
 void orthogonal(const V* v, V* out, index_t N, index_t B, int device = 0) {
     using T = detail::vec_elem<V>;
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     DeviceBatch<T> dV(B, (int)((N - 1) * N), Layout::AoS), dO(B, (int)N, Layout::AoS);
     dV.upload_aos(reinterpret_cast<const T*>(v));
     check(Abi<T>::orthogonal((int)N, B, dV.data(), dO.data(), GMB_LAYOUT_AOS, nullptr), "orthogonal");
@@ -372,7 +442,7 @@ void orthogonal(const V* v, V* out, index_t N, index_t B, int device = 0) {
 template <typename V>
 index_t nullspace(const V* bases, index_t n, V* null_basis, index_t N, index_t B, bool* ok = nullptr, int device = 0) {
     using T = detail::vec_elem<V>;
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     DeviceBatch<T> dB(B, (int)(n * N), Layout::AoS), dN(B, (int)((N - n) * N), Layout::AoS);
     DeviceArray<std::uint8_t> dok((std::size_t)B);
     dB.upload_aos(reinterpret_cast<const T*>(bases));
@@ -423,7 +493,7 @@ template <typename S, typename V>
 index_t contains(const S* simplexes, const V* p, index_t B, bool* inside, int device = 0) {
     using T = detail::simplex_elem<S>;
     constexpr int N = (int)(sizeof(V) / sizeof(T));
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return 0;
     const std::size_t voff = detail::member_offset<T>(simplexes, simplexes[0].pts[0].begin(), "Simplex layout");
     DeviceArray<T> dS = detail::upload_objects<T>(simplexes, B), dP = detail::upload_objects<T>(p, B);
@@ -448,7 +518,7 @@ template <typename V, typename R, typename VU, typename T>
 index_t trace_simplex(const V* verts, const R* rays, VU* uv, T* t, index_t B, bool* hit, int device = 0) {
     static_assert(std::is_same<T, detail::vec_elem<V>>::value, "ray parameter type must be the vertices' element type");
     constexpr int N = (int)(sizeof(V) / sizeof(T));
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return 0;
     const std::size_t ooff = detail::member_offset<T>(rays, rays[0].origin.begin(), "Ray layout");
     const std::size_t doff = detail::member_offset<T>(rays, rays[0].direction.begin(), "Ray layout");
@@ -480,7 +550,7 @@ template <typename S, typename R, typename I>
 index_t intersect(const S* simplexes, const R* rays, index_t B, I* intervals, int device = 0) {
     using T = detail::simplex_elem<S>;
     constexpr int N = (int)(sizeof(R) / sizeof(T) / 2);
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return 0;
     const std::size_t voff = detail::member_offset<T>(simplexes, simplexes[0].pts[0].begin(), "Simplex layout");
     const std::size_t ooff = detail::member_offset<T>(rays, rays[0].origin.begin(), "Ray layout");
@@ -512,25 +582,20 @@ void mul(Md* into, const Ma* a, const Mb* b, index_t B, bool accumulate = false,
     constexpr int R = (int)Ma::ROWDIM, K = (int)Ma::COLDIM, C = (int)Mb::COLDIM;
     static_assert((int)Mb::ROWDIM == K && (int)Md::ROWDIM == R && (int)Md::COLDIM == C, "dimension mismatch");
     static_assert(std::is_same<T, detail::elem_of<Mb>>::value && std::is_same<T, detail::elem_of<Md>>::value, "element types must agree");
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return;
-    auto ha = detail::pack(a, B, R * K);
-    auto hb = detail::pack(b, B, K * C);
+    detail::FlatIn<Ma, R * K> ha(a, B);
+    detail::FlatIn<Mb, K * C> hb(b, B);
+    detail::FlatOut<Md, R * C> hd(into, B, /*load_current=*/accumulate);
     DeviceBatch<T> dA(B, R * K, Layout::AoS), dB(B, K * C, Layout::AoS), dD(B, R * C, Layout::AoS);
-    dA.upload_aos(ha.data());
-    dB.upload_aos(hb.data());
-    std::vector<T> hd;
-    if (accumulate) {
-        hd = detail::pack(into, B, R * C);
-        dD.upload_aos(hd.data());
-    } else {
-        hd.resize((std::size_t)(B * R * C));
-    }
+    dA.upload_aos(ha.p);
+    dB.upload_aos(hb.p);
+    if (accumulate) dD.upload_aos(hd.p);
     check(Abi<T>::mul(R, K, C, B, dA.data(), dB.data(), dD.data(), accumulate ? 1 : 0, GMB_LAYOUT_AOS, (int)Ma::Layout == 0 ? 1 : 0,
                       (int)Mb::Layout == 0 ? 1 : 0, (int)Md::Layout == 0 ? 1 : 0, nullptr), "mul");
-    dD.download_aos(hd.data());
+    dD.download_aos(hd.p);
     check(gmb_stream_synchronize(nullptr), "sync");
-    detail::unpack(into, hd, B, R * C, nullptr);
+    hd.commit();
 }
 template <typename Md, typename Ma, typename Mb>
 void mul_acc(Md* into, const Ma* a, const Mb* b, index_t B, int device = 0) { mul(into, a, b, B, true, device); }
@@ -572,12 +637,12 @@ index_t transformation(X* out, const Mx* m, index_t B, int device = 0) {
     using T = detail::elem_of<Mx>;
     constexpr int N = (int)Mx::ROWDIM, E = 2 * (N + 1) * (N + 1);
     static_assert(detail::xf_K<X>() == N + 1 && (int)Mx::COLDIM == N, "AffineTransform<T,N> from an N x N matrix");
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return 0;
-    auto hm = detail::pack(m, B, N * N);
+    detail::FlatIn<Mx, N * N> hm(m, B);
     DeviceBatch<T> dM(B, N * N, Layout::AoS), dX(B, E, Layout::AoS);
     DeviceArray<std::uint8_t> dok((std::size_t)B);
-    dM.upload_aos(hm.data());
+    dM.upload_aos(hm.p);
     check(Abi<T>::xf_from_matrix(N, B, dM.data(), dX.data(), dok.get(), GMB_LAYOUT_AOS, (int)Mx::Layout == 0 ? 1 : 0, nullptr),
           "transformation");
     std::vector<T> hx((std::size_t)(B * E));
@@ -595,7 +660,7 @@ void xf_from_vectors(X* out, const V* v, index_t B, bool is_scale, int device) {
     using T = xf_elem<X>;
     constexpr int N = xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
     static_assert(sizeof(V) == sizeof(T) * N, "packed Vec<T,N> expected");
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return;
     DeviceBatch<T> dV(B, N, Layout::AoS), dX(B, E, Layout::AoS);
     dV.upload_aos(reinterpret_cast<const T*>(v));
@@ -619,7 +684,7 @@ template <typename X>
 void compose(X* out, const X* xf1, const X* xf2, index_t B, bool inverse = false, int device = 0) {
     using T = detail::xf_elem<X>;
     constexpr int N = detail::xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return;
     auto h1 = detail::pack_xf(xf1, B), h2 = detail::pack_xf(xf2, B);
     DeviceBatch<T> d1(B, E, Layout::AoS), d2(B, E, Layout::AoS), dO(B, E, Layout::AoS);
@@ -638,7 +703,7 @@ void apply(const X& xf, const V* p, V* out, index_t B, int mode = GMB_XF_APPLY, 
     using T = detail::xf_elem<X>;
     constexpr int N = detail::xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
     static_assert(sizeof(V) == sizeof(T) * N, "packed Vec<T,N> expected");
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return;
     auto hx = detail::pack_xf(&xf, 1);
     DeviceArray<T> dX((std::size_t)E);
@@ -655,7 +720,7 @@ void apply(const X* xf, const V* p, V* out, index_t B, int mode = GMB_XF_APPLY, 
     using T = detail::xf_elem<X>;
     constexpr int N = detail::xf_K<X>() - 1, E = 2 * (N + 1) * (N + 1);
     static_assert(sizeof(V) == sizeof(T) * N, "packed Vec<T,N> expected");
-    check(gmb_set_device(device), "set_device");
+    detail::DeviceScope scope(device);
     if (B <= 0) return;
     auto hx = detail::pack_xf(xf, B);
     DeviceBatch<T> dX(B, E, Layout::AoS), dP(B, N, Layout::AoS), dO(B, N, Layout::AoS);

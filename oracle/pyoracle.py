@@ -377,6 +377,24 @@ def best() -> CpuLinalg:
     return ref() if ref_available() else port()
 
 
+class Checker:
+    """What the GPU parity tests compare with: every function of best() -- the compiled reference when oracle/_ref is
+    on the box -- except the one the reference does not have (cholesky_solve, defined by the port: parity unpinned)."""
+
+    def __init__(self):
+        self._best, self._port = best(), port()
+        self.kind = self._best.kind
+
+    def __getattr__(self, name):
+        return getattr(self._port if name == "cholesky_solve" else self._best, name)
+
+
+def checker() -> Checker:
+    if "checker" not in _cache:
+        _cache["checker"] = Checker()
+    return _cache["checker"]
+
+
 # ---------------------------------------------------------------------- shared input generators
 def exact_grid(rng: np.random.Generator, shape, dtype, bits: int = 20, scale_log2: int = -17):
     """Contraction-proof inputs: `bits`-bit signed integers times 2**scale_log2 (exact in f32 and f64).

@@ -61,6 +61,14 @@ def ref():
     return po.ref()
 
 
+@pytest.fixture(scope="session")
+def orc():
+    """The checker of the GPU parity tests: oracle/_ref (the unmodified reference, compiled; it travels to the GPU box)
+    when present, else the C port -- no indirection through the port when the reference itself can answer."""
+    from oracle import pyoracle as po
+    return po.checker()
+
+
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_SIZES = (2, 3, 4, 5, 7, 8, 11, 16)
 

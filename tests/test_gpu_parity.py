@@ -1,7 +1,8 @@
 """GPU suite: the CUDA path, called through the C ABI, against the CPU oracle.
 
 * the committed golden fixtures (outputs of the reference itself, tests/golden/),
-* seeded random batches against oracle.c (which test_oracle_vs_ref.py pins to the reference),
+* seeded random batches against oracle/_ref = the compiled reference itself (conftest.orc; the C port only when
+  _ref is absent -- test_oracle_vs_ref.py pins the two to each other),
 for every hot-path function, float and double, AoS and SoA-interleaved layouts, row- and
 column-major, N = 2..16, including singular / non-SPD / non-finite systems.
 
@@ -44,29 +45,29 @@ def check(got, want, what):
     assert bits_equal(got, want), f"{what}: {first_diff(got, want)}"
 
 
-def run_all(gm, port, n, A, b1, b3, S, soa, expect=None):
-    """Run every entry point on one input set and compare with `expect` (golden dict) or the port."""
+def run_all(gm, orc, n, A, b1, b3, S, soa, expect=None):
+    """Run every entry point on one input set and compare with `expect` (golden dict) or the checker (conftest.orc)."""
     with np.errstate(all="ignore"):
         for rm, r in ((True, "rm"), (False, "cm")):
             tag = f"n={n} soa={soa} {r}"
             dA, db1, db3, dS = up(gm, A, soa), up(gm, b1, soa), up(gm, b3, soa), up(gm, S, soa)
             # a1 decomp_plu
             lu, p, par, dg = gm.decomp_plu(dA, n, n, rm)
-            e = (expect[f"plu_{r}_lu"], expect[f"plu_{r}_p"], expect[f"plu_{r}_parity"], expect[f"plu_{r}_degen"]) if expect is not None else port.decomp_plu(A, n, n, rm)
+            e = (expect[f"plu_{r}_lu"], expect[f"plu_{r}_p"], expect[f"plu_{r}_parity"], expect[f"plu_{r}_degen"]) if expect is not None else orc.decomp_plu(A, n, n, rm)
             check(down(lu), e[0], f"decomp_plu lu {tag}")
             check(down(p).astype(np.int64), e[1], f"decomp_plu reorder {tag}")
             check(down(par), e[2], f"decomp_plu parity {tag}")
             check(down(dg).astype(np.int64), e[3], f"decomp_plu degenerate {tag}")
             # a2 decomp_lup
             lu2, p2, par2, dg2 = gm.decomp_lup(dA, n, n, rm)
-            e = (expect[f"lup_{r}_lu"], expect[f"lup_{r}_p"], expect[f"lup_{r}_parity"], expect[f"lup_{r}_degen"]) if expect is not None else port.decomp_lup(A, n, n, rm)
+            e = (expect[f"lup_{r}_lu"], expect[f"lup_{r}_p"], expect[f"lup_{r}_parity"], expect[f"lup_{r}_degen"]) if expect is not None else orc.decomp_lup(A, n, n, rm)
             check(down(lu2), e[0], f"decomp_lup lu {tag}")
             check(down(p2).astype(np.int64), e[1], f"decomp_lup reorder {tag}")
             check(down(par2), e[2], f"decomp_lup parity {tag}")
             check(down(dg2).astype(np.int64), e[3], f"decomp_lup degenerate {tag}")
             # a6 linear_solve (fused), m = 1 and m = 3 / skip = 1, plus the LU it leaves in `a`
             x, ok, lua = gm.linear_solve(dA, db1, n, 1, 0, rm, want_lu=True)
-            e = (expect[f"solve_{r}_a"], expect[f"solve_{r}_x"], expect[f"solve_{r}_ok"]) if expect is not None else port.linear_solve(A, b1, n, 1, 0, rm)
+            e = (expect[f"solve_{r}_a"], expect[f"solve_{r}_x"], expect[f"solve_{r}_ok"]) if expect is not None else orc.linear_solve(A, b1, n, 1, 0, rm)
             check(down(x), e[1], f"linear_solve x {tag}")
             check(down(ok), e[2], f"linear_solve ok {tag}")
             check(down(lua), e[0], f"linear_solve a (LU) {tag}")
@@ -75,38 +76,38 @@ def run_all(gm, port, n, A, b1, b3, S, soa, expect=None):
             check(down(x_nolu), e[1], f"linear_solve (no LU output) x {tag}")
             check(down(ok_nolu), e[2], f"linear_solve (no LU output) ok {tag}")
             x3, ok3 = gm.linear_solve(dA, db3, n, 3, 1, rm)
-            e = (None, expect[f"solve3s1_{r}_x"], expect[f"solve3s1_{r}_ok"]) if expect is not None else port.linear_solve(A, b3, n, 3, 1, rm)
+            e = (None, expect[f"solve3s1_{r}_x"], expect[f"solve3s1_{r}_ok"]) if expect is not None else orc.linear_solve(A, b3, n, 3, 1, rm)
             check(down(x3), e[1], f"linear_solve m=3 skip=1 x {tag}")
             check(down(ok3), e[2], f"linear_solve m=3 skip=1 ok {tag}")
             # a3 / a4 / a5 on the reference LU
             lu_np, p_np = down(lu), down(p)
-            e = expect[f"bslu_{r}_x"] if expect is not None else port.backsolve_lu(lu_np, b3, n, 3, 0, rm)
+            e = expect[f"bslu_{r}_x"] if expect is not None else orc.backsolve_lu(lu_np, b3, n, 3, 0, rm)
             check(down(gm.backsolve_lu(lu, db3, n, 3, 0, rm)), e, f"backsolve_lu {tag}")
-            e = expect[f"bsplu_{r}_x"] if expect is not None else port.backsolve_plu(lu_np, p_np.astype(np.int64), b3, n, 3, 0, rm)
+            e = expect[f"bsplu_{r}_x"] if expect is not None else orc.backsolve_plu(lu_np, p_np.astype(np.int64), b3, n, 3, 0, rm)
             check(down(gm.backsolve_plu(lu, p, db3, n, 3, 0, rm)), e, f"backsolve_plu {tag}")
-            e = expect[f"perm_{r}_a"] if expect is not None else port.apply_perm(p_np.astype(np.int64), b3, n, 3, rm)[0]
+            e = expect[f"perm_{r}_a"] if expect is not None else orc.apply_perm(p_np.astype(np.int64), b3, n, 3, rm)[0]
             check(down(gm.apply_permutation(p, db3, n, 3, rm)), e, f"apply_permutation {tag}")
             # a8 cholesky
             L, okc = gm.cholesky(dS, n, rm)
-            e = (expect[f"chol_{r}_l"], expect[f"chol_{r}_ok"]) if expect is not None else port.cholesky(S, n, rm)
+            e = (expect[f"chol_{r}_l"], expect[f"chol_{r}_ok"]) if expect is not None else orc.cholesky(S, n, rm)
             check(down(L), e[0], f"cholesky L {tag}")
             check(down(okc), e[1], f"cholesky ok {tag}")
             # new: cholesky_solve against the port's definition
-            Lp, okp = port.cholesky(S, n, rm)
+            Lp, okp = orc.cholesky(S, n, rm)
             xs, oks, Ls = gm.cholesky_solve(dS, db1, n, 1, rm, want_l=True)
             check(down(Ls), Lp, f"cholesky_solve L {tag}")
             check(down(oks), okp, f"cholesky_solve ok {tag}")
-            check(down(xs), port.cholesky_solve(Lp, b1, n, 1, rm), f"cholesky_solve x {tag}")
+            check(down(xs), orc.cholesky_solve(Lp, b1, n, 1, rm), f"cholesky_solve x {tag}")
             # a13 inv, all four layout combinations, destination pre-filled with 7
             for drm, q in ((True, "rm"), (False, "cm")):
                 init = np.full_like(A, 7)
                 out, oki = gm.inv(dA, n, rm, drm, out=up(gm, init, soa))
-                e = (expect[f"inv_{r}_{q}"], expect[f"inv_{r}_{q}_ok"]) if expect is not None else port.inv(A, n, rm, drm, init)
+                e = (expect[f"inv_{r}_{q}"], expect[f"inv_{r}_{q}_ok"]) if expect is not None else orc.inv(A, n, rm, drm, init)
                 check(down(out), e[0], f"inv {r}->{q} {tag}")
                 check(down(oki), e[1], f"inv ok {r}->{q} {tag}")
         # a7 Vec-form linear_solve
         xv, okv = gm.linear_solve_vec(up(gm, A, soa), up(gm, b1, soa), n, 1, 0)
-        e = (None, expect["solvevec_x"], expect["solvevec_ok"]) if expect is not None else port.linear_solve_vec(A, b1, n, 1, 0)
+        e = (None, expect["solvevec_x"], expect["solvevec_ok"]) if expect is not None else orc.linear_solve_vec(A, b1, n, 1, 0)
         check(down(xv), e[1], f"linear_solve(Vec) x n={n} soa={soa}")
         check(down(okv), e[2], f"linear_solve(Vec) ok n={n} soa={soa}")
 
@@ -114,9 +115,9 @@ def run_all(gm, port, n, A, b1, b3, S, soa, expect=None):
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("tag", ["f32", "f64"])
 @pytest.mark.parametrize("n", GOLDEN_SIZES)
-def test_golden(gm, port, tag, n, soa):
+def test_golden(gm, orc, tag, n, soa):
     g = load_golden(tag, n)
-    run_all(gm, port, n, g["A"], g["b1"], g["b3"], g["S"], soa, expect=g)
+    run_all(gm, orc, n, g["A"], g["b1"], g["b3"], g["S"], soa, expect=g)
     # rectangular decomp_plu ((n-1) x n), as used by nullspace / orthogonal
     lur, pr, parr, dgr = gm.decomp_plu(up(gm, g["rect_m"], soa), n - 1, n, True)
     check(down(lur), g["rect_lu"], "rect lu")
@@ -128,7 +129,7 @@ def test_golden(gm, port, tag, n, soa):
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", list(range(2, 17)))
-def test_random_vs_oracle(gm, port, dt, n, soa):
+def test_random_vs_oracle(gm, orc, dt, n, soa):
     """Seeded random batches whose size is NOT a multiple of the tile width (ragged last tile)."""
     from oracle import pyoracle as po
     rng = np.random.default_rng(4242 + 100 * n + np.dtype(dt).itemsize)
@@ -140,13 +141,13 @@ def test_random_vs_oracle(gm, port, dt, n, soa):
     b3 = rng.standard_normal((B, n * 3)).astype(dt)
     S = po.spd_exact(rng, B, n, dt)
     S[::53, 0] = -1
-    run_all(gm, port, n, A, b1, b3, S, soa)
+    run_all(gm, orc, n, A, b1, b3, S, soa)
 
 
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [3, 4, 5, 6, 8, 9, 12, 13, 16])
-def test_extreme_magnitudes_vs_oracle(gm, port, dt, n, soa):
+def test_extreme_magnitudes_vs_oracle(gm, orc, dt, n, soa):
     """Rows scaled by powers of two far outside the fast domain of the shared-reciprocal division (RcpOf, gmb_math.cuh:
     float operands beyond 2^+-57, double quotients near the ends of the exponent range), subnormal and zero entries,
     overflowing multipliers: every quotient must still be the correctly rounded one (= the oracle's)."""
@@ -168,7 +169,7 @@ def test_extreme_magnitudes_vs_oracle(gm, port, dt, n, soa):
         S = po.spd_exact(rng, B, n, np.float64).reshape(B, n, n)
         k = rng.integers(-kmax // 3, kmax // 3 + 1, size=(B, n))
         S = np.ldexp(S, k[:, :, None] + k[:, None, :]).astype(dt).reshape(B, n * n)   # D S D stays symmetric positive definite
-    run_all(gm, port, n, A, b1, b3, S, soa)
+    run_all(gm, orc, n, A, b1, b3, S, soa)
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
@@ -201,34 +202,72 @@ def test_aos_soa_round_trip(gm, dt, E):
             assert flat[((s // W) * E + e) * W + s % W] == a[s, e]
 
 
-@pytest.mark.parametrize("n", [3, 4, 6, 16])
-def test_unaligned_aos_batches_take_the_elementwise_kernels(gm, port, n):
-    """The reference's objects are only 4/8-byte aligned: an AoS batch at an odd offset must still be
-    solved (generic element-wise kernels), bit-identically."""
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [2, 3, 4, 6, 8, 12, 16])
+def test_unaligned_aos_batches_take_the_elementwise_kernels(gm, orc, n, dt):
+    """The reference's objects are only 4/8-byte aligned: an AoS batch at an odd offset must still be served -- by
+    element-wise kernels, bit-identically -- by EVERY entry point (include/geomc_b200.h, "Alignment")."""
+    from oracle import pyoracle as po
     rng = np.random.default_rng(n)
     B = 777
-    A = rng.standard_normal((B, n * n)).astype(np.float32)
-    b = rng.standard_normal((B, n)).astype(np.float32)
-    buf_a = torch.zeros(B * n * n + 1, dtype=torch.float32, device="cuda")
-    buf_b = torch.zeros(B * n + 1, dtype=torch.float32, device="cuda")
-    dA = buf_a[1:].view(B, n * n)
-    db = buf_b[1:].view(B, n)
-    dA.copy_(torch.from_numpy(A))
-    db.copy_(torch.from_numpy(b))
-    assert dA.data_ptr() % 16 != 0
-    x, ok = gm.linear_solve(dA, db, n)
-    _, xe, oke = port.linear_solve(A, b, n)
-    check(down(x), xe, f"unaligned linear_solve n={n}")
-    check(down(ok), oke, "unaligned ok")
-    lu, p, par, dg = gm.decomp_plu(dA, n)
-    e = port.decomp_plu(A, n)
-    check(down(lu), e[0], "unaligned decomp lu")
-    check(down(p).astype(np.int64), e[1], "unaligned decomp perm")
+    tdt = torch.float32 if dt == np.float32 else torch.float64
+    A = rng.standard_normal((B, n * n)).astype(dt)
+    A[::59] = 0
+    b = rng.standard_normal((B, n)).astype(dt)
+    S = po.spd_exact(rng, B, n, dt)
+    S[::41, 0] = -1
+
+    def odd(h):
+        buf = torch.zeros(h.size + 1, dtype=tdt, device="cuda")
+        v = buf[1:].view(*h.shape)
+        v.copy_(torch.from_numpy(h))
+        assert v.data_ptr() % 16 != 0
+        return v
+    dA, db, dS = odd(A), odd(b), odd(S)
+    with np.errstate(all="ignore"):
+        x, ok = gm.linear_solve(dA, db, n)
+        _, xe, oke = orc.linear_solve(A, b, n)
+        check(down(x), xe, f"unaligned linear_solve n={n}")
+        check(down(ok), oke, "unaligned ok")
+        lu, p, par, dg = gm.decomp_plu(dA, n)
+        e = orc.decomp_plu(A, n)
+        check(down(lu), e[0], "unaligned decomp lu")
+        check(down(p).astype(np.int64), e[1], "unaligned decomp perm")
+        # inverse: adjugate for n <= 4 (element-wise kernel), PLU above; all four layout combinations
+        for srm in (True, False):
+            for drm in (True, False):
+                init = np.full_like(A, 7)
+                out, oki = gm.inv(dA, n, srm, drm, out=odd(init))
+                e = orc.inv(A, n, srm, drm, init)
+                check(down(out), e[0], f"unaligned inv n={n} {srm}->{drm}")
+                check(down(oki), e[1], f"unaligned inv ok n={n}")
+        # Vec form (inverse-then-multiply below 5 unknowns)
+        xv, okv = gm.linear_solve_vec(dA, db, n)
+        e = orc.linear_solve_vec(A, b, n, 1, 0)
+        check(down(xv), e[1], f"unaligned linear_solve(Vec) n={n}")
+        check(down(okv), e[2], f"unaligned linear_solve(Vec) ok n={n}")
+        # Cholesky and the fused Cholesky solve
+        L, okc = gm.cholesky(dS, n)
+        Le, okce = orc.cholesky(S, n, True)
+        check(down(L), Le, f"unaligned cholesky n={n}")
+        check(down(okc), okce, "unaligned cholesky ok")
+        xs, oks = gm.cholesky_solve(dS, db, n)
+        check(down(oks), okce, "unaligned cholesky_solve ok")
+        check(down(xs), orc.cholesky_solve(Le, b, n, 1, True), f"unaligned cholesky_solve n={n}")
+    # container ingest / egress with an element-aligned AoS side
+    soa = gm.BatchSoA.from_aos(dA)
+    check(down(soa), A, "aos_to_soa from an unaligned AoS batch")
+    back = odd(np.zeros_like(A))
+    gm.lib()  # (the C ABI directly: to_aos() would allocate an aligned destination)
+    from geomc_b200 import _lib
+    _lib.call("gmb_soa_to_aos", "f32" if dt == np.float32 else "f64", n * n, B, soa.data.data_ptr(), back.data_ptr(),
+              torch.cuda.current_stream().cuda_stream)
+    check(down(back), A, "soa_to_aos into an unaligned AoS batch")
 
 
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [8, 12, 16])
-def test_batches_aligned_to_16_but_not_32_bytes(gm, port, dt, n):
+def test_batches_aligned_to_16_but_not_32_bytes(gm, orc, dt, n):
     """The row kernels read AoS rows with 256-bit loads when the batch is 32-byte aligned and with 128-bit loads when
     it is only 16-byte aligned (ldg_row, gmb_io.cuh): same results either way."""
     rng = np.random.default_rng(31 * n)
@@ -248,19 +287,19 @@ def test_batches_aligned_to_16_but_not_32_bytes(gm, port, dt, n):
         bufs.append(v)
     dA, db, dS = bufs
     x, ok = gm.linear_solve(dA, db, n)
-    _, xe, oke = port.linear_solve(A, b, n)
+    _, xe, oke = orc.linear_solve(A, b, n)
     check(down(x), xe, f"16-byte aligned linear_solve n={n}")
     check(down(ok), oke, "16-byte aligned ok")
     out, oki = gm.inv(dA, n)
-    e = port.inv(A, n, True, True, np.zeros_like(A))
+    e = orc.inv(A, n, True, True, np.zeros_like(A))
     check(down(out)[down(oki) != 0], e[0][e[1] != 0], f"16-byte aligned inv n={n}")
-    Lp, okp = port.cholesky(S, n, True)
+    Lp, okp = orc.cholesky(S, n, True)
     xs, oks = gm.cholesky_solve(dS, db, n)
     check(down(oks), okp, "16-byte aligned cholesky ok")
-    check(down(xs), port.cholesky_solve(Lp, b, n, 1, True), f"16-byte aligned cholesky_solve n={n}")
+    check(down(xs), orc.cholesky_solve(Lp, b, n, 1, True), f"16-byte aligned cholesky_solve n={n}")
 
 
-def test_host_api_matches_device_api(gm, port):
+def test_host_api_matches_device_api(gm, orc):
     rng = np.random.default_rng(9)
     B, n = 70001, 4
     A = rng.standard_normal((B, n * n)).astype(np.float32)
@@ -269,12 +308,12 @@ def test_host_api_matches_device_api(gm, port):
     x = np.zeros_like(b)
     ok = np.zeros(B, np.uint8)
     gm.host_linear_solve(A, b, x, ok, n)
-    _, xe, oke = port.linear_solve(A, b, n)
+    _, xe, oke = orc.linear_solve(A, b, n)
     check(x, xe, "host linear_solve x")
     check(ok, oke, "host linear_solve ok")
     out = np.full_like(A, 3)
     gm.host_inv(A, out, ok, n)
-    oe, oke = port.inv(A, n, True, True, np.full_like(A, 3))
+    oe, oke = orc.inv(A, n, True, True, np.full_like(A, 3))
     check(out, oe, "host inv")
     check(ok, oke, "host inv ok")
     from oracle import pyoracle as po
@@ -282,8 +321,8 @@ def test_host_api_matches_device_api(gm, port):
     b3 = po.exact_grid(rng, (B, 3), np.float64)
     x3 = np.zeros_like(b3)
     gm.host_cholesky_solve(S, b3, x3, ok, 3)
-    L, okc = port.cholesky(S, 3)
-    check(x3, port.cholesky_solve(L, b3, 3), "host cholesky_solve")
+    L, okc = orc.cholesky(S, 3)
+    check(x3, orc.cholesky_solve(L, b3, 3), "host cholesky_solve")
     check(ok, okc, "host cholesky ok")
     A8 = rng.standard_normal((B // 7, 64))
     lu = A8.copy()
@@ -291,7 +330,7 @@ def test_host_api_matches_device_api(gm, port):
     par = np.zeros(B // 7, np.uint8)
     dg = np.zeros(B // 7, np.uint8)
     gm.host_decomp_plu(lu, p, par, dg, 8)
-    e = port.decomp_plu(A8, 8)
+    e = orc.decomp_plu(A8, 8)
     check(lu, e[0], "host decomp lu")
     check(p.astype(np.int64), e[1], "host decomp perm")
     check(par, e[2], "host decomp parity")
@@ -370,7 +409,7 @@ def test_both_large_n_inverse_kernels(force):
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [2, 4, 6, 7, 8, 9, 12, 15, 16])
-def test_skip_rows_single_rhs(gm, port, dt, n, soa):
+def test_skip_rows_single_rhs(gm, orc, dt, n, soa):
     """`skip` > 0 with ONE right-hand side goes through the register / column / row kernels (the m = 3
     cases above take the generic path): rows < skip keep their forward-substituted values
     (LUDecomp.h:356), bit for bit, in both layouts and both matrix orders."""
@@ -384,13 +423,13 @@ def test_skip_rows_single_rhs(gm, port, dt, n, soa):
             continue
         for rm in (True, False):
             x, ok = gm.linear_solve(up(gm, A, soa), up(gm, b, soa), n, 1, skip, rm)
-            _, xe, oke = port.linear_solve(A, b, n, 1, skip, rm)
+            _, xe, oke = orc.linear_solve(A, b, n, 1, skip, rm)
             check(down(x), xe, f"skip={skip} n={n} rm={rm} soa={soa}")
             check(down(ok), oke, f"skip={skip} ok")
     # and through the Vec-form entry point for n >= 5 (column-major PLU, LUDecomp.h:428-439)
     if n >= 5:
         xv, okv = gm.linear_solve_vec(up(gm, A, soa), up(gm, b, soa), n, 1, 1)
-        _, xe, oke = port.linear_solve_vec(A, b, n, 1, 1)
+        _, xe, oke = orc.linear_solve_vec(A, b, n, 1, 1)
         check(down(xv), xe, f"Vec-form skip=1 n={n}")
         check(down(okv), oke, "Vec-form ok")
 
@@ -470,7 +509,7 @@ def test_no_out_of_bounds_writes(gm, dt, n, soa):
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
 @pytest.mark.parametrize("n", [3, 5, 6, 9, 12, 16])
-def test_backsolve_single_rhs(gm, port, dt, n, soa):
+def test_backsolve_single_rhs(gm, orc, dt, n, soa):
     """backsolve_lu / backsolve_plu with ONE right-hand side (n >= 5: the row-distributed kernel; the
     m = 3 cases in run_all go through the generic path), skip = 0 and skip > 0, both matrix orders."""
     rng = np.random.default_rng(77 * n + np.dtype(dt).itemsize)
@@ -478,11 +517,11 @@ def test_backsolve_single_rhs(gm, port, dt, n, soa):
     A = rng.standard_normal((B, n * n)).astype(dt)
     b = rng.standard_normal((B, n)).astype(dt)
     for rm in (True, False):
-        lu_np, p_np, _, _ = port.decomp_plu(A, n, n, rm)
+        lu_np, p_np, _, _ = orc.decomp_plu(A, n, n, rm)
         lu, p = up(gm, lu_np, soa), torch.from_numpy(p_np.astype(np.uint8)).cuda()
         for skip in (0, 1, n - 1):
             with np.errstate(all="ignore"):
-                check(down(gm.backsolve_lu(lu, up(gm, b, soa), n, 1, skip, rm)), port.backsolve_lu(lu_np, b, n, 1, skip, rm),
+                check(down(gm.backsolve_lu(lu, up(gm, b, soa), n, 1, skip, rm)), orc.backsolve_lu(lu_np, b, n, 1, skip, rm),
                       f"backsolve_lu n={n} rm={rm} skip={skip} soa={soa}")
                 check(down(gm.backsolve_plu(lu, p, up(gm, b, soa), n, 1, skip, rm)),
-                      port.backsolve_plu(lu_np, p_np, b, n, 1, skip, rm), f"backsolve_plu n={n} rm={rm} skip={skip} soa={soa}")
+                      orc.backsolve_plu(lu_np, p_np, b, n, 1, skip, rm), f"backsolve_plu n={n} rm={rm} skip={skip} soa={soa}")
