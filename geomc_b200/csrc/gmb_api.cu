@@ -21,6 +21,9 @@ std::atomic<int> g_opt_rowplu_min_n{-1};     // fused solve: row-distributed ker
 std::atomic<int> g_opt_rowdecomp_min_n{-1};  // decomp_plu: row-distributed kernel from this n on
 std::atomic<int> g_opt_rowinv{-1};           // inverse n >= 5: 0 = column-distributed kernel, 1 = row-distributed
 std::atomic<int> g_opt_rowfast{-1};          // speculative solve (gmb_rowfast.cuh): 0 = off, 1 = wherever it exists
+std::atomic<int> g_opt_invd{-1};             // deferred-rider inverse (k_sub_plu MODE_INVD): 0 = off, 1 = wherever it exists
+std::atomic<int> g_opt_lanesolve{-1};        // one-thread-per-system speculative solve, n = 5..8 (gmb_lane.cuh): 0 = off, 1 = on
+std::atomic<int> g_opt_lanechol{-1};         // one-thread-per-system Cholesky with staged ingest, n = 5..8: 0 = off, 1 = on
 
 // gmb_small.cu
 template <typename T> int small_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
@@ -34,16 +37,22 @@ template <typename T> int small_solve_vec_elem(int, int, int64_t, const T*, cons
 template <typename T> int small_residual(int, int64_t, const T*, const T*, const T*, const uint8_t*, double*, int, int, cudaStream_t);
 // gmb_subwarp.cu
 template <typename T> int subwarp_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
+template <typename T, int XC> int subwarp_plu_solve_m(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int subwarp_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
+template <typename T> int subwarp_invd(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
+template <typename T> int subwarp_lup(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int subwarp_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
 // gmb_rowplu_*.cu
 template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int rowinv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
-template <typename T> int row_backsolve(int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
+template <typename T> int row_backsolve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
 // gmb_rowfast_*.cu
 template <typename T> int rowfast_solve(int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
+// gmb_lane_*.cu
+template <typename T> int lane_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
+template <typename T> int lane_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
 // gmb_generic.cu
 template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
 template <typename T> int generic_solve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
@@ -91,6 +100,28 @@ static bool use_rowfast(int n) {
     return sizeof(T) == 4 && (n == 13 || n >= 15);
 }
 
+// One thread per system (gmb_lane.cuh): float n = 5..8, double n = 5..6.
+template <typename T>
+static bool use_lane_solve(int n, int m) {
+    if (n < 5 || n > (sizeof(T) == 4 ? 8 : 6) || m > 4) return false;
+    const int forced = g_opt_lanesolve.load(std::memory_order_relaxed);
+    if (forced >= 0) return forced != 0;
+    return false;
+}
+// Cholesky: the row kernel (one lane per system for these sizes, staged AoS ingest) serves one right-hand side; the
+// lane kernel serves 2..4 of them (the row kernel carries one rider).  Option "lanechol": 1 = lane kernel for m = 1 too
+// (tests), 0 = never (m > 1 then falls to the generic kernel).
+// Measured (profiles/r2c_lane_ab.md): from AoS records the lane kernel wins (float n = 5..8: 0.60 / 0.53 / 0.56 / 0.43 of
+// the peak against 0.55 / 0.44 / 0.43 / 0.38 for the row kernel with the same staged ingest), in the SoA container the
+// row kernel's right-looking order wins (0.82 / 0.71 / 0.78 / 0.67 against 0.77 / 0.65 / 0.69 / 0.58).
+template <typename T>
+static bool use_lane_chol(int n, int m, bool solve, int layout) {
+    if (n < 5 || n > (sizeof(T) == 4 ? 8 : 6) || (solve && m > 4)) return false;
+    const int forced = g_opt_lanechol.load(std::memory_order_relaxed);
+    if (forced >= 0) return forced != 0;
+    return (solve && m >= 2) || layout == GMB_LAYOUT_AOS;
+}
+
 static bool bad_layout(int layout) { return layout != GMB_LAYOUT_AOS && layout != GMB_LAYOUT_SOA; }
 
 // The register and sub-warp kernels use 128-bit accesses and need 16-byte aligned batches (any
@@ -132,6 +163,10 @@ int plu_decomp(int rows, int cols, int64_t B, T* A, uint8_t* perm, uint8_t* pari
         int rc = subwarp_decomp<T>(rows, B, A, perm, parity, degen, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
+    if (fast && colpiv && rows == cols && rows >= 5) {
+        int rc = subwarp_lup<T>(rows, B, A, perm, parity, degen, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
     return generic_decomp<T>(rows, cols, B, A, perm, parity, degen, layout, rm, colpiv, st);
 }
 
@@ -149,8 +184,8 @@ int lu_backsolve(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* 
         int rc = small_backsolve<T>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
-    if (fast && n >= 5 && m == 1 && mode != 2) {
-        int rc = row_backsolve<T>(mode, n, B, LU, perm, Bm, X, skip, layout, rm, st);
+    if (fast && n >= 5) {                                    // any number of right-hand sides: the LU rows are loaded once
+        int rc = row_backsolve<T>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     return generic_solve<T>(mode, n, m, B, LU, perm, Bm, X, nullptr, nullptr, skip, layout, rm, st);
@@ -169,6 +204,12 @@ int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* o
         int rc = small_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
+    // n = 5..8 (double: 5, 6), up to four right-hand sides, no LU output: one thread per system, speculative, with the
+    // exact re-solve of the systems it hands back (gmb_lane.cuh)
+    if (fast && LU == nullptr && use_lane_solve<T>(n, m)) {
+        int rc = lane_solve<T>(n, m, B, A, Bm, X, ok, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
     // n >= 9, one right-hand side, no LU output: speculative kernel + exact re-solve of the systems it hands back
     // (gmb_rowfast.cuh); option "rowfast" = 0 switches it off (the exact kernels below then serve every system)
     if (fast && m == 1 && n >= 9 && LU == nullptr && use_rowfast<T>(n)) {
@@ -180,7 +221,11 @@ int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* o
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     if (fast && n >= 5) {
-        int rc = subwarp_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
+        int rc = m == 1   ? subwarp_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st)
+                 : m == 2 ? subwarp_plu_solve_m<T, 2>(n, B, A, Bm, X, ok, LU, skip, layout, rm, st)
+                 : m == 3 ? subwarp_plu_solve_m<T, 3>(n, B, A, Bm, X, ok, LU, skip, layout, rm, st)
+                 : m == 4 ? subwarp_plu_solve_m<T, 4>(n, B, A, Bm, X, ok, LU, skip, layout, rm, st)
+                          : GMB_ERR_UNSUPPORTED;
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     return generic_solve<T>(3, n, m, B, A, nullptr, Bm, X, ok, LU, skip, layout, rm, st);
@@ -217,6 +262,10 @@ int cholesky(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok
         int rc = small_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
+    if (fast && use_lane_chol<T>(n, m, solve, layout)) {
+        int rc = lane_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
     if (fast && n >= 5) {
         int rc = subwarp_cholesky<T>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
@@ -241,6 +290,12 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
     // The row-distributed kernel (gmb_rowinv.cuh) is 1.2x (7 x 7 double) to 3x (16 x 16 float) faster than the
     // column-distributed one from n = 8 (float) / n = 6 (double) on and slower below (profiles/r1j_row_inverse.md);
     // option "rowinv" = 0 / 1 forces the column / row kernel for every n >= 5 (tests).
+    // one lane per system with deferred riders (float n <= 10, double n <= 7): option "invd" = 0 switches it off
+    if (fast && n >= 5 && n <= (sizeof(T) == 4 ? 10 : 7) && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
+        g_opt_rowinv.load(std::memory_order_relaxed) < 0) {
+        int rc = subwarp_invd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
     const int row_inv = g_opt_rowinv.load(std::memory_order_relaxed);
     const bool use_row_inv = row_inv >= 0 ? row_inv == 1 : n >= (sizeof(T) == 4 ? 8 : 6);
     if (fast && n >= 5 && use_row_inv) {
@@ -607,6 +662,9 @@ int gmb_set_option(const char* name, int value) {
                           : !std::strcmp(name, "rowdecomp_min_n") ? &g_opt_rowdecomp_min_n
                           : !std::strcmp(name, "rowinv")          ? &g_opt_rowinv
                           : !std::strcmp(name, "rowfast")         ? &g_opt_rowfast
+                          : !std::strcmp(name, "invd")            ? &g_opt_invd
+                          : !std::strcmp(name, "lanesolve")       ? &g_opt_lanesolve
+                          : !std::strcmp(name, "lanechol")        ? &g_opt_lanechol
                                                                   : nullptr;
     if (!o) return GMB_ERR_INVALID_ARG;
     o->store(value);

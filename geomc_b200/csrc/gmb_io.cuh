@@ -204,11 +204,12 @@ template <int R>
 struct StageCfg {
     static constexpr bool vec16 = (R % 16 == 0);
     static constexpr int CH = R / 16;                        // 16-byte chunks per record (if vec16)
-    static constexpr bool swz = vec16 && (CH == 2 || CH == 4 || CH == 8);
+    static constexpr bool swz = vec16 && (CH == 2 || CH == 4 || CH == 8 || CH == 16 || CH == 32);
     static constexpr bool use = R >= 32;
     static constexpr int warp_bytes = 32 * R;
     __device__ static __forceinline__ int chunk(int t, int j) {           // position of chunk j of record t
-        if constexpr (swz) return t * CH + (j ^ ((t / (8 / CH)) & (CH - 1)));
+        if constexpr (swz && CH <= 8) return t * CH + (j ^ ((t / (8 / CH)) & (CH - 1)));
+        else if constexpr (swz) return t * CH + (j ^ (t & 7));            // records of 256 / 512 bytes: rotate inside groups of 8 chunks
         else return t * CH + j;
     }
 };
@@ -222,10 +223,10 @@ __device__ __forceinline__ unsigned char* stage_buffer() {
 
 // all 32 lanes of the warp call this; record t = lane; `full` = all 32 records exist
 template <typename T, int E>
-__device__ __forceinline__ void aos_load_staged(const T* __restrict__ base, int64_t s_warp0, int lane, T (&q)[E]) {
+__device__ __forceinline__ void aos_load_staged(const T* __restrict__ base, int64_t s_warp0, int lane, T (&q)[E],
+                                                unsigned char* sm = stage_buffer<T, E>()) {
     constexpr int R = E * (int)sizeof(T);
     using Cfg = StageCfg<R>;
-    unsigned char* sm = stage_buffer<T, E>();
     const uint4* g = reinterpret_cast<const uint4*>(base + s_warp0 * (int64_t)E);
     constexpr int NCH = 2 * R;                               // 32 * R / 16
 #pragma unroll
@@ -259,10 +260,10 @@ __device__ __forceinline__ void aos_load_staged(const T* __restrict__ base, int6
 }
 
 template <typename T, int E>
-__device__ __forceinline__ void aos_store_staged(T* __restrict__ base, int64_t s_warp0, int lane, const T (&q)[E]) {
+__device__ __forceinline__ void aos_store_staged(T* __restrict__ base, int64_t s_warp0, int lane, const T (&q)[E],
+                                                 unsigned char* sm = stage_buffer<T, E>()) {
     constexpr int R = E * (int)sizeof(T);
     using Cfg = StageCfg<R>;
-    unsigned char* sm = stage_buffer<T, E>();
     if constexpr (Cfg::vec16) {
         using VT = typename VecOf<T>::type;
         constexpr int V = soa_v<T>();

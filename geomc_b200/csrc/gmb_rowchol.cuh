@@ -40,6 +40,39 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
     // ---- load the lower triangle of this lane's rows (and b) ------------------------------------
     T a[RL][N];
     T y[RL];
+    // One lane per system on an AoS batch: the warp's 32 records travel as one contiguous range through a warp-private
+    // shared-memory transpose (coalesced 128-bit accesses on both sides, gmb_io.cuh) -- records whose rows are not
+    // multiples of 16 bytes (n = 5, 6, 7, 9, ...) used to be read with scalar loads at a stride of one record.
+    constexpr bool LANE_IO = (G == 1) && !SOA;
+    extern __shared__ __align__(16) unsigned char gmb_dyn_smem[];
+    unsigned char* lane_sm = gmb_dyn_smem + (size_t)(threadIdx.x >> 5) * (32 * N * N * sizeof(T));
+    const int64_t s_raw = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
+    const bool lane_full = LANE_IO && ((s_raw - (threadIdx.x & 31)) + 32 <= B);
+    if constexpr (LANE_IO) {
+        T qa[N * N];
+        if (StageCfg<N * N * (int)sizeof(T)>::use && lane_full) {
+            aos_load_staged<T, N * N>(A, s_raw - (threadIdx.x & 31), threadIdx.x & 31, qa, lane_sm);
+        } else {
+            aos_load<T, N * N>(A, s, qa);
+        }
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) a[r][c] = (c <= r) ? qa[RM ? N * r + c : N * c + r] : (T)0;
+        if (SOLVE) {
+            T qb[N];
+            if (StageCfg<N * (int)sizeof(T)>::use && lane_full) {
+                aos_load_staged<T, N>(Bm, s_raw - (threadIdx.x & 31), threadIdx.x & 31, qb, lane_sm);
+            } else {
+                aos_load<T, N>(Bm, s, qb);
+            }
+#pragma unroll
+            for (int r = 0; r < N; ++r) y[r] = qb[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < N; ++r) y[r] = (T)0;
+        }
+    } else
 #pragma unroll
     for (int k = 0; k < RL; ++k) {
         const int p = k * G + lane_g;
@@ -138,6 +171,20 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
     }
 
     // ---- L with the strict upper triangle zeroed (Cholesky.h:52) ---------------------------------
+    if constexpr (LANE_IO) {
+        if (L_out != nullptr) {
+            T ql[N * N];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) ql[RM ? N * r + c : N * c + r] = (c <= r) ? a[r][c] : (T)0;
+            if (StageCfg<N * N * (int)sizeof(T)>::use && lane_full) {
+                aos_store_staged<T, N * N>(L_out, s_raw - (threadIdx.x & 31), threadIdx.x & 31, ql, lane_sm);
+            } else if (valid) {
+                aos_store<T, N * N>(L_out, s, ql);
+            }
+        }
+    } else
     if (L_out != nullptr && valid) {
 #pragma unroll
         for (int k = 0; k < RL; ++k) {
@@ -168,6 +215,16 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
                 }
             }
         }
+        if constexpr (LANE_IO) {
+            T qx[N];
+#pragma unroll
+            for (int r = 0; r < N; ++r) qx[r] = y[r];
+            if (StageCfg<N * (int)sizeof(T)>::use && lane_full) {
+                aos_store_staged<T, N>(X, s_raw - (threadIdx.x & 31), threadIdx.x & 31, qx, lane_sm);
+            } else if (valid) {
+                aos_store<T, N>(X, s, qx);
+            }
+        } else
         if (valid) {
 #pragma unroll
             for (int k = 0; k < RL; ++k) {
@@ -194,7 +251,14 @@ int rowchol_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t
         dispatch_bool(solve, [&](auto SOLVE) {
             dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
                 dispatch_bool(rm != 0, [&](auto RM) {
-                    k_row_chol<T, N.value, SOLVE.value, SOA.value, RM.value><<<grid, kRowThreads, 0, st>>>(A, Bm, X, L_out, ok, B);
+                    auto kern = k_row_chol<T, N.value, SOLVE.value, SOA.value, RM.value>;
+                    // one lane per system on an AoS batch: one staging buffer of 32 records per warp
+                    const size_t smem = (G == 1 && !SOA.value) ? (size_t)(kRowThreads / 32) * 32 * N.value * N.value * sizeof(T) : 0;
+                    if (smem > 48 * 1024) {
+                        static std::atomic<uint64_t> raised{0};
+                        raise_dyn_smem(kern, smem, raised);
+                    }
+                    kern<<<grid, kRowThreads, smem, st>>>(A, Bm, X, L_out, ok, B);
                 });
             });
         });
@@ -212,9 +276,13 @@ namespace gmb {
 // distributed as above.  PLU = true gathers y(r) = b(perm[r]) first (:294).  Forward sweep column by
 // column (c ascending: x(r) = fma(-x(c), lu(r,c), x(r)) for r > c -- for every row the terms arrive in
 // the reference's order), backward sweep as in k_row_solve (c descending, then divide by u(c,c)).
-template <typename T, int N, bool PLU, bool SOA, bool RM>
+template <typename T, int N, int MODE, bool SOA, bool RM>
 __global__ void __launch_bounds__(kRowThreads, GMB_ROW_MIN_BLOCKS)
-k_row_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, const T* Bm, T* X, int skip, int64_t B) {
+k_row_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, const T* Bm, T* X, int skip, int m, int64_t B) {
+    // MODE 0 = backsolve_lu, 1 = backsolve_plu (gathers b(perm[r]) first), 2 = destructive_apply_permutation (gather only).
+    // m right-hand sides: the LU rows are loaded once, the columns of X go through the sweeps one after the other; element
+    // (r, j) of the n x m block sits at RM ? m*r + j : n*j + r (MatrixGlue.h:28-58).
+    constexpr bool PLU = MODE != 0;
     constexpr int WORDS = (int)sizeof(T) / 4;
     constexpr int G = row_group(N, WORDS);
     constexpr int RL = row_rl(N, G);
@@ -225,67 +293,76 @@ k_row_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, con
     const bool valid = s < B;
     if (!valid) s = B - 1;
     const int64_t baseA = SOA ? (s / W) * (int64_t)(N * N) * W + (s % W) : s * (int64_t)(N * N);
-    const int64_t baseX = SOA ? (s / W) * (int64_t)N * W + (s % W) : s * (int64_t)N;
+    const int64_t baseX = SOA ? (s / W) * (int64_t)(N * m) * W + (s % W) : s * (int64_t)(N * m);
 
     T a[RL][N];
-    T x[RL];
+    int src[RL];
 #pragma unroll
     for (int k = 0; k < RL; ++k) {
         const int p = k * G + lane_g;
         const int pr = p < N ? p : 0;
-        if constexpr (!SOA && RM && (N * (int)sizeof(T)) % 16 == 0) {
-            ldg_row<T, N>(LUm + baseA + (int64_t)pr * N, a[k], (reinterpret_cast<uintptr_t>(LUm) & 31) == 0);   // whole row, 128 / 256 bit
-        } else {
+        if constexpr (MODE != 2) {
+            if constexpr (!SOA && RM && (N * (int)sizeof(T)) % 16 == 0) {
+                ldg_row<T, N>(LUm + baseA + (int64_t)pr * N, a[k], (reinterpret_cast<uintptr_t>(LUm) & 31) == 0);   // whole row, 128 / 256 bit
+            } else {
 #pragma unroll
-            for (int c = 0; c < N; ++c) a[k][c] = LUm[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
-        }
-        const int src = PLU ? (int)perm[s * N + pr] : pr;
-        x[k] = Bm[baseX + (int64_t)src * ST];
-    }
-    // forward: L y = b (unit diagonal)
-#pragma unroll
-    for (int c = 0; c < N - 1; ++c) {
-        const T xc = (G == 1) ? x[c / G] : __shfl_sync(0xffffffffu, x[c / G], c % G, G);
-#pragma unroll
-        for (int sl = 0; sl < RL; ++sl) {
-            if (sl >= c / G) {                                 // static
-                const int p = sl * G + lane_g;
-                const T v = fma_rn(-xc, a[sl][c], x[sl]);
-                if (p > c && p < N) x[sl] = v;
+                for (int c = 0; c < N; ++c) a[k][c] = LUm[baseA + (int64_t)(RM ? N * pr + c : N * c + pr) * ST];
             }
         }
+        src[k] = PLU ? (int)perm[s * N + pr] : pr;
     }
-    // backward: U x = y
+    for (int j = 0; j < m; ++j) {
+        T x[RL];
 #pragma unroll
-    for (int c = N - 1; c >= 0; --c) {
-        const int oc_lane = c % G, oc_slot = c / G;            // static
-        const bool on = c >= skip;
-        const T q = div_rn(x[oc_slot], a[oc_slot][c]);
-        const T xc = (G == 1) ? q : __shfl_sync(0xffffffffu, q, oc_lane, G);
-        if (on && lane_g == oc_lane) x[oc_slot] = q;
+        for (int k = 0; k < RL; ++k) x[k] = Bm[baseX + (int64_t)(RM ? m * src[k] + j : N * j + src[k]) * ST];
+        if constexpr (MODE == 2) __syncwarp();                 // in place: every source row is read before any is written
+        if constexpr (MODE != 2) {
+            // forward: L y = b (unit diagonal)
 #pragma unroll
-        for (int sl = 0; sl < RL; ++sl) {
-            if (sl <= oc_slot) {                               // static
-                const int p = sl * G + lane_g;
-                const T v = fma_rn(-xc, a[sl][c], x[sl]);
-                if (on && p < c && p >= skip) x[sl] = v;
+            for (int c = 0; c < N - 1; ++c) {
+                const T xc = (G == 1) ? x[c / G] : __shfl_sync(0xffffffffu, x[c / G], c % G, G);
+#pragma unroll
+                for (int sl = 0; sl < RL; ++sl) {
+                    if (sl >= c / G) {                                 // static
+                        const int p = sl * G + lane_g;
+                        const T v = fma_rn(-xc, a[sl][c], x[sl]);
+                        if (p > c && p < N) x[sl] = v;
+                    }
+                }
+            }
+            // backward: U x = y
+#pragma unroll
+            for (int c = N - 1; c >= 0; --c) {
+                const int oc_lane = c % G, oc_slot = c / G;            // static
+                const bool on = c >= skip;
+                const T q = div_rn(x[oc_slot], a[oc_slot][c]);
+                const T xc = (G == 1) ? q : __shfl_sync(0xffffffffu, q, oc_lane, G);
+                if (on && lane_g == oc_lane) x[oc_slot] = q;
+#pragma unroll
+                for (int sl = 0; sl < RL; ++sl) {
+                    if (sl <= oc_slot) {                               // static
+                        const int p = sl * G + lane_g;
+                        const T v = fma_rn(-xc, a[sl][c], x[sl]);
+                        if (on && p < c && p >= skip) x[sl] = v;
+                    }
+                }
             }
         }
-    }
-    if (valid) {
+        if (valid) {
 #pragma unroll
-        for (int k = 0; k < RL; ++k) {
-            const int p = k * G + lane_g;
-            if (p < N) X[baseX + (int64_t)p * ST] = x[k];
+            for (int k = 0; k < RL; ++k) {
+                const int p = k * G + lane_g;
+                if (p < N) X[baseX + (int64_t)(RM ? m * p + j : N * j + p) * ST] = x[k];
+            }
         }
     }
 }
 
 template <typename T>
-int rowbacksolve_impl(int mode, int n, int64_t B, const T* LU, const uint8_t* perm, const T* Bm, T* X, int skip, int layout,
+int rowbacksolve_impl(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* perm, const T* Bm, T* X, int skip, int layout,
                       int rm, cudaStream_t st) {
-    if (mode != 0 && mode != 1) return GMB_ERR_UNSUPPORTED;
-    if (mode == 1 && X == Bm) return GMB_ERR_UNSUPPORTED;        // the gather needs distinct buffers
+    if (mode < 0 || mode > 2 || m < 1) return GMB_ERR_UNSUPPORTED;
+    if (mode == 1 && X == Bm) return GMB_ERR_UNSUPPORTED;        // the gather of backsolve_plu needs distinct buffers (as in the reference)
     int rc = GMB_ERR_UNSUPPORTED;
     dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
         constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
@@ -294,10 +371,10 @@ int rowbacksolve_impl(int mode, int n, int64_t B, const T* LU, const uint8_t* pe
             rc = GMB_OK;
             return;
         }
-        dispatch_bool(mode == 1, [&](auto PLU) {
+        dispatch_int<0, 1, 2>(mode, [&](auto MODE) {
             dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
                 dispatch_bool(rm != 0, [&](auto RM) {
-                    k_row_backsolve<T, N.value, PLU.value, SOA.value, RM.value><<<grid, kRowThreads, 0, st>>>(LU, perm, Bm, X, skip, B);
+                    k_row_backsolve<T, N.value, MODE.value, SOA.value, RM.value><<<grid, kRowThreads, 0, st>>>(LU, perm, Bm, X, skip, m, B);
                 });
             });
         });

@@ -6,9 +6,9 @@ template <> int subwarp_cholesky<double>(int n, int m, int64_t B, const double* 
                                       int layout, int rm, bool solve, cudaStream_t st) {
     return rowchol_impl<double>(n, m, B, A, Bm, X, ok, L_out, layout, rm, solve, st);
 }
-template <typename T> int row_backsolve(int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
-template <> int row_backsolve<double>(int mode, int n, int64_t B, const double* LU, const uint8_t* perm, const double* Bm, double* X, int skip,
+template <typename T> int row_backsolve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
+template <> int row_backsolve<double>(int mode, int n, int m, int64_t B, const double* LU, const uint8_t* perm, const double* Bm, double* X, int skip,
                                    int layout, int rm, cudaStream_t st) {
-    return rowbacksolve_impl<double>(mode, n, B, LU, perm, Bm, X, skip, layout, rm, st);
+    return rowbacksolve_impl<double>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
 }
 }  // namespace gmb

@@ -38,6 +38,7 @@ constexpr int kRegBudgetWords = 100;      // register words for the local block
 constexpr int MODE_SOLVE = 0;   // A, Bm -> X, ok (, LU)
 constexpr int MODE_DECOMP = 1;  // A in place, perm, parity, degenerate
 constexpr int MODE_INV = 2;     // A -> Ainv, ok
+constexpr int MODE_INVD = 3;    // A -> Ainv, ok: one lane per system, riders deferred (see k_sub_plu)
 
 constexpr int sub_lc(int n, int xc, int g) { return (n + xc + g - 1) / g; }
 // does ANY lane of the group hold a rider column / a column beyond `i` at local index j?  (static)
@@ -86,7 +87,51 @@ struct BatchAddr {
     }
 };
 
-template <typename T, int N, int XC, int MODE, bool SOA, bool A_RM, bool X_RM>
+// One lane per system (G == 1) on an AoS batch: the warp's 32 records are one contiguous range, moved with coalesced
+// 128-bit accesses through a warp-private, swizzled shared-memory transpose (aos_load_staged / aos_store_staged,
+// gmb_io.cuh) instead of 32 lanes walking 32 records at a stride of one record.  `sm` = the warp's staging buffer.
+template <typename T, int E>
+__device__ __forceinline__ void sub_lane_load(const T* __restrict__ base, int64_t s, int lane, bool full, bool valid, T (&q)[E],
+                                              unsigned char* sm) {
+    if (StageCfg<E * (int)sizeof(T)>::use && full) {
+        aos_load_staged<T, E>(base, s - lane, lane, q, sm);
+    } else if (valid) {
+        aos_load<T, E>(base, s, q);
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) q[e] = (T)0;
+    }
+}
+template <typename T, int E>
+__device__ __forceinline__ void sub_lane_store(T* __restrict__ base, int64_t s, int lane, bool full, bool valid, const T (&q)[E],
+                                               unsigned char* sm) {
+    if (StageCfg<E * (int)sizeof(T)>::use && full) {
+        aos_store_staged<T, E>(base, s - lane, lane, q, sm);
+    } else if (valid) {
+        aos_store<T, E>(base, s, q);
+    }
+}
+// elements of the largest record a G == 1 AoS kernel moves (matrix, or the rider block)
+constexpr int sub_lane_emax(int n, int xc) { return n * (n > xc ? n : xc); }
+
+// MODE_INVD (XC = 0, G = 1): invNxN (MatrixInv.h:219-231) without carrying the identity through the elimination.  The
+// reference decomposes, sets out(i, p[i]) = 1 and runs backsolve_lu on the n columns of `out`.  Column p[i] of that
+// right-hand side is e_i, so its forward sweep (LUDecomp.h:345-353) is y(r) = 0 for r < i, y(i) = 1 and the reference's
+// chain from c = i on for r > i -- the terms with c < i multiply an exact zero: with finite multipliers they leave the
+// accumulator at +0, bit for bit.  The kernel therefore factors [A] alone (half the columns to exchange, the
+// decomposition runs at the HBM roofline for these sizes), then produces the inverse ONE COLUMN AT A TIME in i-space
+// -- forward chain on the statically known non-zero part, dense backward sweep (:356-365), one reciprocal per
+// diagonal entry shared by all columns -- and stores column i at its dynamic position p[i] through a per-thread,
+// bank-conflict-free shared-memory scratch (a register file cannot be indexed at run time; memory can).  A system
+// whose multipliers are not all finite (0 * inf = NaN in the skipped terms) takes the dense forward sweep instead,
+// in the same kernel: same bits as the reference for every input.
+// COLPIV = true: decomp_lup (LUDecomp.h:102-165, column pivoting) on the TRANSPOSED view of the matrix -- the launcher
+// flips A_RM, so "row p" below is column p of M: the search then runs along row i of M (:124-131), the exchange swaps
+// columns of M (:140-145), and only the elimination differs from decomp_plu: the multipliers b_r = M(r,i) / M(i,i)
+// (:152) sit in ROW i of the view (one per column, computed by the lane that owns the column, pivot broadcast with one
+// shuffle) and the unscaled M(i,c) (:157) is COLUMN i of the view, broadcast from its owner with n-1-i shuffles --
+// the same number of shuffles as decomp_plu, with the roles of the two factors exchanged.
+template <typename T, int N, int XC, int MODE, bool SOA, bool A_RM, bool X_RM, bool COLPIV = false>
 __global__ void __launch_bounds__(kSubThreads, GMB_SUB_MIN_BLOCKS)
 k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ perm_out,
           uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B) {
@@ -114,13 +159,39 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     // Measured (profiles/r1e_*): per-lane strided LOADS go through L1 and every fetched line is consumed,
     // so staging them only pays where the record stride is a power of two (f32 N=8) or nearly so;
     // per-lane strided STORES write partial sectors, so matrix outputs are always staged.
-    constexpr bool STAGE_IN = sub_stage_in<T>(N, MODE, SOA), STAGE_OUT = sub_stage_out(MODE, SOA);
+    constexpr bool LANE_IO = (G == 1) && !SOA;                             // one lane per system: staged record I/O
+    constexpr bool STAGE_IN = !LANE_IO && sub_stage_in<T>(N, MODE, SOA), STAGE_OUT = !LANE_IO && sub_stage_out(MODE, SOA);
     const bool stage = (STAGE_IN || STAGE_OUT) && (s_warp0 + NSYS <= B);   // warp-uniform
+    const int64_t s_raw = (int64_t)blockIdx.x * kSubThreads + threadIdx.x; // LANE_IO: this thread's system before clamping
+    const bool lane_full = LANE_IO && (s_warp0 + 32 <= B);                 // warp-uniform
+    unsigned char* lane_sm = gmb_dyn_smem + (size_t)(threadIdx.x >> 5) * (32 * (sub_lane_emax(N, XC) + 1) * sizeof(T));
     const T* sms = smw + ((threadIdx.x & 31) / G) * SA + (A_RM ? c0 : N * c0);   // this lane's system, first local column
     if (STAGE_IN && stage) warp_stage_in<T, N * N, NSYS>(A + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
 
     // ---- load the local block -------------------------------------------------------------
     T a[N][LC];
+    if constexpr (LANE_IO) {
+        T qa[N * N];
+        sub_lane_load<T, N * N>(A, s_raw, threadIdx.x & 31, lane_full, valid, qa, lane_sm);
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) a[r][c] = qa[A_RM ? N * r + c : N * c + r];
+        if constexpr (MODE == MODE_SOLVE) {
+            T qb[N * XC];
+            sub_lane_load<T, N * XC>(Bm, s_raw, threadIdx.x & 31, lane_full, valid, qb, lane_sm);
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < XC; ++j) a[r][N + j] = qb[X_RM ? XC * r + j : N * j + r];
+        }
+        if constexpr (MODE == MODE_INV) {
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < XC; ++j) a[r][N + j] = (r == j) ? (T)1 : (T)0;
+        }
+    } else
 #pragma unroll
     for (int r = 0; r < N; ++r)
 #pragma unroll
@@ -137,7 +208,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
         }
 
     uint8_t perm[N];
-    if (MODE == MODE_DECOMP) {
+    if (MODE == MODE_DECOMP || MODE == MODE_INVD) {
 #pragma unroll
         for (int r = 0; r < N; ++r) perm[r] = (uint8_t)r;
     }
@@ -180,7 +251,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
                 a[i][j] = sw ? a[p][j] : t;
                 a[p][j] = sw ? t : a[p][j];
             }
-            if (MODE == MODE_DECOMP) {
+            if (MODE == MODE_DECOMP || MODE == MODE_INVD) {
                 const uint8_t t = perm[i];
                 perm[i] = sw ? perm[p] : t;
                 perm[p] = sw ? t : perm[p];
@@ -189,6 +260,43 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
         // multipliers from the owner lane, then the rank-1 update of the local columns
         const T piv = a[i][k];
         const bool mine = (G == 1) || (lane_g == owner);
+        if constexpr (COLPIV) {
+            const T pv = shfl_t<G>(piv, owner);
+            const RcpOf<T> rc(pv);
+            T bq[LC];
+            bool all_ok = true;
+#pragma unroll
+            for (int j = 0; j < LC; ++j) {
+                bq[j] = (T)0;
+                if ((G - 1) * LC + j > i) {                       // static: some lane's column at j is right of i
+                    bool ok;
+                    bq[j] = rc.fast(a[i][j], ok);
+                    all_ok = all_ok && (ok || !(c0 + j > i && c0 + j < N));
+                }
+            }
+            if (!all_ok) {
+#pragma unroll
+                for (int j = 0; j < LC; ++j)
+                    if ((G - 1) * LC + j > i) bq[j] = div_rn(a[i][j], pv);
+            }
+            bool on[LC];
+#pragma unroll
+            for (int j = 0; j < LC; ++j) {
+                on[j] = !dead && (c0 + j > i) && (c0 + j < N);
+                if ((G - 1) * LC + j > i) a[i][j] = on[j] ? bq[j] : a[i][j];       // M(r,i) = b (:163)
+                on[j] = on[j] && (bq[j] != (T)0);                                    // `if (b != 0)` (:153)
+            }
+#pragma unroll
+            for (int r = i + 1; r < N; ++r) {
+                const T t = shfl_t<G>(a[r][k], owner);           // M(i, r): row i of M is not touched by this step
+#pragma unroll
+                for (int j = 0; j < LC; ++j) {
+                    if ((G - 1) * LC + j > i) {
+                        if (on[j]) a[r][j] = fma_rn(-bq[j], t, a[r][j]);
+                    }
+                }
+            }
+        } else {
         // one reciprocal per pivot, three operations per quotient (RcpOf, gmb_math.cuh); the owner lane redoes its
         // quotients with div_rn when an operand leaves the fast domain -- same bits either way
         T bq[N];
@@ -221,15 +329,127 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
                 }
             }
         }
+        }
     }
 
     const bool good = degenerate == 0;
+
+    if constexpr (MODE == MODE_INVD) {
+        static_assert(G == 1 && XC == 0, "deferred-rider inverse: one lane per system");
+        const int lane = threadIdx.x & 31;
+        // per-thread scratch for the dynamically placed columns: SoA [element][lane] (bank = lane: conflict-free for any
+        // index), AoS [record][element] at an odd stride (the layout warp_stage_out flushes with coalesced stores)
+        T* scr = reinterpret_cast<T*>(lane_sm);
+        constexpr int SA2 = stage_stride<N * N>();
+        auto slot = [&](int e) -> T& { return SOA ? scr[e * 32 + lane] : scr[lane * SA2 + e]; };
+        // are all multipliers finite?  (0 * l accumulates to 0 unless some l is Inf / NaN; FMA pipe, no compares)
+        T fin = (T)0;
+#pragma unroll
+        for (int r = 1; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < r; ++c) fin = fma_rn(a[r][c], (T)0, fin);
+        const bool sparse_ok = fin == (T)0;
+        // one reciprocal per diagonal entry of U, shared by the n columns (RcpOf, gmb_math.cuh)
+        T ry[N];
+        bool rs[N];
+#pragma unroll
+        for (int r = 0; r < N; ++r) {
+            const RcpOf<T> rc(a[r][r]);
+            ry[r] = rc.y;
+            rs[r] = rc.safe;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            T y[N];
+            if (sparse_ok) {
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    if (r < i) y[r] = (T)0;
+                    else if (r == i) y[r] = (T)1;
+                    else {
+                        T v = (T)0;
+#pragma unroll
+                        for (int c = i; c < r; ++c) v = fma_rn(-y[c], a[r][c], v);
+                        y[r] = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    T v = (r == i) ? (T)1 : (T)0;
+#pragma unroll
+                    for (int c = 0; c < r; ++c) v = fma_rn(-y[c], a[r][c], v);
+                    y[r] = v;
+                }
+            }
+            // backward sweep (:356-365): x(r) = (y(r) - sum_{c = n-1 .. r+1} u(r,c) x(c)) / u(r,r)
+            T x[N];
+            bool all_ok = true;
+#pragma unroll
+            for (int r = N - 1; r >= 0; --r) {
+                T v = y[r];
+#pragma unroll
+                for (int c = N - 1; c > r; --c) v = fma_rn(-x[c], a[r][c], v);
+                y[r] = v;                                       // the dividend, kept for the exact redo
+                bool okq;
+                x[r] = RcpOf<T>(a[r][r], ry[r], rs[r]).fast(v, okq);
+                all_ok = all_ok && okq;
+            }
+            if (!all_ok) {                                      // some operand outside the fast division window: IEEE divisions
+                // redo the whole column with div_rn (the quotients feed the rows above them)
+                T yy[N];
+#pragma unroll
+                for (int r = 0; r < N; ++r) {
+                    T v = (r == i) ? (T)1 : (T)0;
+#pragma unroll
+                    for (int c = 0; c < r; ++c) v = fma_rn(-yy[c], a[r][c], v);
+                    yy[r] = v;
+                }
+#pragma unroll
+                for (int r = N - 1; r >= 0; --r) {
+                    T v = yy[r];
+#pragma unroll
+                    for (int c = N - 1; c > r; --c) v = fma_rn(-x[c], a[r][c], v);
+                    x[r] = div_rn(v, a[r][r]);
+                }
+            }
+            const int pc = perm[i];                             // out(r, p[i]) = x(r): row-major flat index n*r + p[i] (:192)
+#pragma unroll
+            for (int r = 0; r < N; ++r) slot(N * r + pc) = x[r];
+        }
+        // ---- egress
+        if constexpr (SOA) {
+            if (valid && good) {
+                T* dst = X + baseA;
+#pragma unroll
+                for (int e = 0; e < N * N; ++e) dst[e * ST] = slot(e);
+            }
+        } else {
+            const bool staged = lane_full && __all_sync(0xffffffffu, good);
+            if (staged) {
+                warp_stage_out<T, N * N, 32>(X + s_warp0 * (int64_t)(N * N), scr, lane);
+            } else if (valid && good) {
+                T* dst = X + baseA;
+#pragma unroll
+                for (int e = 0; e < N * N; ++e) dst[e] = slot(e);
+            }
+        }
+        if (valid && ok_out) ok_out[s] = good ? 1 : 0;
+        return;
+    }
 
     // ---- outputs that need no backward sweep ------------------------------------------------
     if (MODE == MODE_DECOMP || (MODE == MODE_SOLVE && LU != nullptr)) {
         T* dstb = (MODE == MODE_DECOMP) ? const_cast<T*>(A) : LU;
         T* dst = dstb + baseA + (int64_t)c0 * (A_RM ? ST : N * ST);
-        if (STAGE_OUT && stage) {
+        if constexpr (LANE_IO) {
+            T ql[N * N];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) ql[A_RM ? N * r + c : N * c + r] = a[r][c];
+            sub_lane_store<T, N * N>(dstb, s_raw, threadIdx.x & 31, lane_full, valid, ql, lane_sm);
+        } else if (STAGE_OUT && stage) {
             __syncwarp();                                              // every lane is done reading the staged input
             T* smd = smw + ((threadIdx.x & 31) / G) * SA + (A_RM ? c0 : N * c0);
 #pragma unroll
@@ -313,6 +533,20 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
             warp_stage_out<T, N * N, NSYS>(X + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
         }
     }
+    if constexpr (LANE_IO && (MODE == MODE_SOLVE || MODE == MODE_INV)) {
+        // a warp whose systems are all regular stores through the staging buffer; one with a failed system stores per
+        // thread below, so that the failed system's destination keeps what it must keep (x = b / `out` untouched)
+        if (__all_sync(0xffffffffu, good || !valid)) {
+            T qx[N * XC];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < XC; ++j) qx[(MODE == MODE_INV || X_RM) ? XC * r + j : N * j + r] = a[r][N + j];
+            sub_lane_store<T, N * XC>(X, s_raw, threadIdx.x & 31, lane_full, valid, qx, lane_sm);
+            if (valid && ok_out) ok_out[s] = 1;
+            return;
+        }
+    }
     if (valid) {
         if (MODE == MODE_SOLVE) {
 #pragma unroll
@@ -340,7 +574,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
 }
 
 // ---------------------------------------------------------------- launchers
-template <typename T, int N, int XC, int MODE>
+template <typename T, int N, int XC, int MODE, bool COLPIV = false>
 static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t* perm, uint8_t* parity, uint8_t* degen,
                       int skip, int64_t B, int layout, int a_rm, int x_rm, cudaStream_t st) {
     constexpr int G = sub_group(N, XC, (int)sizeof(T) / 4);
@@ -350,11 +584,13 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
     dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
         dispatch_bool(a_rm != 0, [&](auto ARM) {
             // riders: linear_solve uses the matrix' own layout flag; invNxN always writes row-major
-            constexpr bool XRM = (MODE == MODE_INV) ? true : ARM.value;
+            constexpr bool XRM = (MODE == MODE_INV || MODE == MODE_INVD) ? true : ARM.value;
             (void)x_rm;
-            auto kern = k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM>;
+            auto kern = k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM, COLPIV>;
             // AoS: one staging buffer of 32/G systems per warp (dynamic shared memory)
-            const size_t smem = !(sub_stage_in<T>(N, MODE, SOA.value) || sub_stage_out(MODE, SOA.value))
+            const size_t smem = (G == 1 && (!SOA.value || MODE == MODE_INVD))
+                                    ? (size_t)(kSubThreads / 32) * 32 * (sub_lane_emax(N, XC) + 1) * sizeof(T)
+                                : !(sub_stage_in<T>(N, MODE, SOA.value) || sub_stage_out(MODE, SOA.value))
                                     ? 0
                                     : (size_t)(kSubThreads / 32) * (32 / G) * stage_stride<N * N>() * sizeof(T);
             if (smem > 48 * 1024) {
@@ -378,6 +614,17 @@ int subwarp_plu_solve_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* 
     return rc;
 }
 
+// m = 2..4 right-hand sides: the same kernel with XC = m rider columns (instantiated in their own translation units)
+template <typename T, int XC>
+int subwarp_plu_solve_m_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* LU, int skip, int layout, int rm,
+                             cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        rc = launch_sub<T, N.value, XC, MODE_SOLVE>(A, Bm, X, LU, ok, nullptr, nullptr, nullptr, skip, B, layout, rm, rm, st);
+    });
+    return rc;
+}
+
 template <typename T>
 int subwarp_decomp_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
                         cudaStream_t st) {
@@ -389,9 +636,36 @@ int subwarp_decomp_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, 
     return rc;
 }
 
+// decomp_lup for n >= 5: the column-pivot variant runs on the transposed view (a_rm flipped)
+template <typename T>
+int subwarp_lup_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uint8_t* degen, int layout, int rm,
+                     cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
+        rc = launch_sub<T, N.value, 0, MODE_DECOMP, true>(A, nullptr, nullptr, nullptr, nullptr, perm, parity, degen, 0, B, layout,
+                                                          rm ? 0 : 1, rm ? 0 : 1, st);
+    });
+    return rc;
+}
+
 // inv for n >= 5 (MatrixInv.h:243-249 + 219-231): the working copy has the DESTINATION's layout and
 // is then treated as row-major, i.e. the kernel reads A with a_rm = (src layout == dst layout)
 // and writes the result flat row-major into the destination buffer.
+// deferred-rider inverse (MODE_INVD): the sizes whose matrix alone fits one lane (float n <= 10, double n <= 7)
+template <typename T>
+int subwarp_invd_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm,
+                      cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    const int a_rm = ((src_rm != 0) == (dst_rm != 0)) ? 1 : 0;
+    dispatch_int<5, 6, 7, 8, 9, 10>(n, [&](auto N) {
+        if constexpr (sub_group(N.value, 0, (int)sizeof(T) / 4) == 1) {
+            rc = launch_sub<T, N.value, 0, MODE_INVD>(A, nullptr, Ainv, nullptr, ok, nullptr, nullptr, nullptr, 0, B, layout,
+                                                      a_rm, 1, st);
+        }
+    });
+    return rc;
+}
+
 template <typename T>
 int subwarp_inv_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm,
                      cudaStream_t st) {

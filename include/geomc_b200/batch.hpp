@@ -231,7 +231,7 @@ class DeviceScope {
 public:
     explicit DeviceScope(int device) {
         if (gmb_get_device(&prev_) != GMB_OK) prev_ = -1;
-        detail::DeviceScope scope(device);
+        check(gmb_set_device(device), "set_device");
     }
     ~DeviceScope() {
         if (prev_ >= 0) gmb_set_device(prev_);

@@ -82,6 +82,13 @@ def run(case):
         A, b = grid((B, n * n), dt), grid((B, n), dt)
         x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, n, x_out=x, ok_out=ok)
+    if case.startswith("ssolve"):         # ssolve<f|d><n>: fused PLU solve, SoA container, n x n
+        dt = f32 if case[6] == "f" else f64
+        n = int(case[7:])
+        B = int(os.environ.get("PROF_B", 1 << 20))
+        A, b = gm.BatchSoA.from_aos(grid((B, n * n), dt)), gm.BatchSoA.from_aos(grid((B, n), dt))
+        x, ok = b.empty_like(), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.linear_solve(A, b, n, x_out=x, ok_out=ok)
     if case == "c5soa":
         B = 1 << 19
         A, b = gm.BatchSoA.from_aos(grid((B, 256), f32)), gm.BatchSoA.from_aos(grid((B, 16), f32))

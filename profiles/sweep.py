@@ -2,8 +2,9 @@
 in HBM, working set of every case > 2 x L2), and print systems/s and the fraction of the measured HBM peak.
     python profiles/sweep.py [nmin nmax] > gpurun_out/sweep.md
 
-Algorithmic bytes per system: solve  E*n*n + 2*E*n (+1);  decomp (in place) 2*E*n*n + n + 2;
-inverse 2*E*n*n (+1);  cholesky+solve E*n*(n+1)/2 (lower triangle) + 2*E*n (+1).   E = sizeof(T).
+Algorithmic bytes per system: solve  E*n*n + 2*E*n*m (+1);  decomp (in place) 2*E*n*n + n + 2;
+inverse 2*E*n*n (+1);  cholesky+solve: SoA E*n*(n+1)/2 (only the lower-triangle planes are read) + 2*E*n (+1), AoS E*n*n +
+2*E*n (+1) (records are contiguous: the upper triangle travels too);  backsolve_plu (m = 3) E*n*n + n + 2*E*n*3.   E = sizeof(T).
 """
 import json
 import os
@@ -42,8 +43,8 @@ def restore(dst, src):
     (dst.data if hasattr(dst, "data") and not torch.is_tensor(dst) else dst).copy_(src.data if not torch.is_tensor(src) else src)
 
 
-print("| n | type | layout | solve sys/s (of peak) | decomp_plu | inv | cholesky+solve |")
-print("|---|---|---|---|---|---|---|")
+print("| n | type | layout | solve sys/s (of peak) | decomp_plu | inv | cholesky+solve | solve m=3 | decomp_lup | backsolve_plu m=3 |")
+print("|---|---|---|---|---|---|---|---|---|---|")
 NMIN, NMAX = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2, 16)
 for n in range(NMIN, NMAX + 1):
     for dt, name, E in ((torch.float32, "f32", 4), (torch.float64, "f64", 8)):
@@ -62,14 +63,23 @@ for n in range(NMIN, NMAX + 1):
             x = b.clone()
             out = A.clone()
             M = A.clone()
+            b3 = grid((B, 3 * n), dt)
+            if lay == "SoA":
+                b3 = gm.BatchSoA.from_aos(b3)
+            x3 = b3.clone()
+            lu, perm, _, _ = gm.decomp_plu(A, n)
+            chol_bytes = (E * n * (n + 1) // 2 if lay == "SoA" else E * n * n) + 2 * E * n + 1
             cells = []
             for fn, nbytes, before in ((lambda: gm.linear_solve(A, b, n, x_out=x, ok_out=ok), E * n * n + 2 * E * n + 1, None),
                                        (lambda: gm.decomp_plu(M, n, inplace=True, out=outs), 2 * E * n * n + n + 2, lambda: restore(M, A)),
                                        (lambda: gm.inv(A, n, out=out, ok_out=ok), 2 * E * n * n + 1, None),
-                                       (lambda: gm.cholesky_solve(S, b, n, x_out=x, ok_out=ok), E * n * (n + 1) // 2 + 2 * E * n + 1, None)):
+                                       (lambda: gm.cholesky_solve(S, b, n, x_out=x, ok_out=ok), chol_bytes, None),
+                                       (lambda: gm.linear_solve(A, b3, n, 3, x_out=x3, ok_out=ok), E * n * n + 6 * E * n + 1, None),
+                                       (lambda: gm.decomp_lup(M, n, inplace=True), 2 * E * n * n + n + 2, lambda: restore(M, A)),
+                                       (lambda: gm.backsolve_plu(lu, perm, b3, n, 3), E * n * n + n + 6 * E * n, None)):
                 ms = timeit(fn, before=before)
                 rate = B / (ms * 1e-3)
                 cells.append(f"{rate:.3g} ({rate * nbytes / (peak * 1e9):.2f})")
             print(f"| {n} | {name} | {lay} | " + " | ".join(cells) + " |", flush=True)
-            del x, out, M
+            del x, out, M, b3, x3, lu, perm
         del A, b, ok, S, outs

@@ -13,6 +13,9 @@
 #include <geomc/shape/Simplex.h>
 #include <geomc/linalg/AffineTransform.h>
 #endif
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -338,7 +341,33 @@ static void test_affine(long B) {
     EXPECT(std::fabs((double)prod[0](0, 0) - 2.0) < tol * 100 && std::fabs((double)prod[0](0, 1)) < tol * 100, "mul_acc accumulates");
 }
 
+// a crash prints where it happened (build with -g -rdynamic for symbol names)
+static void on_crash(int sig) {
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "fatal signal; backtrace:\n";
+    (void)!write(2, msg, sizeof(msg) - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
+#define STAGE(call) do { std::printf("  %s\n", #call); call; } while (0)
+
 int main() {
+    std::setvbuf(stdout, nullptr, _IONBF, 0);              // a crash must not swallow the progress lines
+    {   // handlers on an alternate stack, so that a stack overflow is reported too
+        static char alt[1 << 16];
+        stack_t ss{};
+        ss.ss_sp = alt;
+        ss.ss_size = sizeof(alt);
+        sigaltstack(&ss, nullptr);
+        struct sigaction sa{};
+        sa.sa_handler = on_crash;
+        sa.sa_flags = SA_ONSTACK;
+        sigaction(SIGSEGV, &sa, nullptr);
+        sigaction(SIGBUS, &sa, nullptr);
+        sigaction(SIGABRT, &sa, nullptr);
+    }
     if (gmb_device_count() == 0) {
         // no CPU fallback: the call must fail loudly
         float a[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, x[4] = {1, 2, 3, 4};
@@ -352,29 +381,29 @@ int main() {
         }
     }
     for (long n : {2L, 3L, 4L, 5L, 8L, 16L}) {
-        test_pointer_linear_solve<float>(n, 3001);
-        test_pointer_linear_solve<double>(n, 1777);
+        STAGE((test_pointer_linear_solve<float>(n, 3001)));
+        STAGE((test_pointer_linear_solve<double>(n, 1777)));
     }
-    test_object_inv<float, 4, geom::ROW_MAJOR, geom::ROW_MAJOR>(2049);
-    test_object_inv<double, 4, geom::ROW_MAJOR, geom::COL_MAJOR>(1000);
-    test_object_inv<float, 3, geom::COL_MAJOR, geom::ROW_MAJOR>(1000);     // 40-byte objects: packed path
-    test_object_inv<double, 6, geom::ROW_MAJOR, geom::ROW_MAJOR>(500);
-    test_vec_linear_solve<double, 3>(1000);
-    test_vec_linear_solve<double, 4>(1000);
-    test_vec_linear_solve<double, 7>(1000);
-    test_decomp_and_cholesky(999);
-    test_orthogonal_nullspace<double, 3>(500);
-    test_orthogonal_nullspace<double, 4>(500);
-    test_orthogonal_nullspace<float, 4>(500);
-    test_orthogonal_nullspace<double, 7>(300);
-    test_simplex_queries<float, 3>(2000);
-    test_simplex_queries<double, 2>(1000);
-    test_simplex_queries<double, 3>(1000);
-    test_simplex_queries<double, 5>(500);
-    test_affine<float, 3>(3000);
-    test_affine<double, 2>(1000);
-    test_affine<double, 3>(1000);
-    test_affine<double, 6>(400);
+    STAGE((test_object_inv<float, 4, geom::ROW_MAJOR, geom::ROW_MAJOR>(2049)));
+    STAGE((test_object_inv<double, 4, geom::ROW_MAJOR, geom::COL_MAJOR>(1000)));
+    STAGE((test_object_inv<float, 3, geom::COL_MAJOR, geom::ROW_MAJOR>(1000)));     // 40-byte objects: packed path
+    STAGE((test_object_inv<double, 6, geom::ROW_MAJOR, geom::ROW_MAJOR>(500)));
+    STAGE((test_vec_linear_solve<double, 3>(1000)));
+    STAGE((test_vec_linear_solve<double, 4>(1000)));
+    STAGE((test_vec_linear_solve<double, 7>(1000)));
+    STAGE((test_decomp_and_cholesky(999)));
+    STAGE((test_orthogonal_nullspace<double, 3>(500)));
+    STAGE((test_orthogonal_nullspace<double, 4>(500)));
+    STAGE((test_orthogonal_nullspace<float, 4>(500)));
+    STAGE((test_orthogonal_nullspace<double, 7>(300)));
+    STAGE((test_simplex_queries<float, 3>(2000)));
+    STAGE((test_simplex_queries<double, 2>(1000)));
+    STAGE((test_simplex_queries<double, 3>(1000)));
+    STAGE((test_simplex_queries<double, 5>(500)));
+    STAGE((test_affine<float, 3>(3000)));
+    STAGE((test_affine<double, 2>(1000)));
+    STAGE((test_affine<double, 3>(1000)));
+    STAGE((test_affine<double, 6>(400)));
     std::printf(failures ? "FAILED (%d)\n" : "batch.hpp OK (%d failures)\n", failures);
     return failures ? 1 : 0;
 }

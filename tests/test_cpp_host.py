@@ -14,7 +14,7 @@ LIBDIR = os.path.join(ROOT, "geomc_b200")
 
 def build(tmp_path, with_geomc):
     out = str(tmp_path / ("t_geomc" if with_geomc else "t_plain"))
-    cmd = ["g++", "-O1", "-w", "-I", os.path.join(ROOT, "include"), SRC, "-L", LIBDIR, "-lgeomc_b200",
+    cmd = ["g++", "-O1", "-g", "-rdynamic", "-w", "-I", os.path.join(ROOT, "include"), SRC, "-L", LIBDIR, "-lgeomc_b200",
            f"-Wl,-rpath,{LIBDIR}", "-o", out]
     if with_geomc:
         cmd[1:1] = ["-std=c++23", "-DWITH_GEOMC", "-include", os.path.join(ROOT, "oracle", "shim", "prelude.h"),

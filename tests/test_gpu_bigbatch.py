@@ -128,3 +128,150 @@ def test_speculative_solve_in_place(gm):
         assert bits_equal(down(xin), down(x0)), first_diff(down(xin), down(x0))
     finally:
         gm.set_option("rowfast", -1)
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [5, 6, 7, 8])
+def test_lane_solve_is_the_exact_solve(gm, orc, n, dt, soa):
+    """gmb_lane.cuh: one thread per system, speculative (rows never move) + exact re-solve of the systems handed back: the
+    bits of the exact kernels (option lanesolve = 0) and of the reference for every system of a hostile 2^18 batch, one and
+    three right-hand sides, both matrix orders, skip > 0, x aliasing b."""
+    if dt == np.float64 and n > 6:
+        pytest.skip("double: n = 5, 6 only (registers)")
+    rng = np.random.default_rng(2000 * n + np.dtype(dt).itemsize + int(soa))
+    B = 1 << 18
+    A, b1 = hostile_batch(rng, B, n, dt)
+    from oracle import pyoracle as po
+    b3 = po.exact_grid(rng, (B, 3 * n), dt)
+    dA = up(gm, A, soa)
+    try:
+        for m, b in ((1, b1), (3, b3)):
+            db = up(gm, b, soa)
+            for rm, skip in ((True, 0), (False, 0), (True, 2)):
+                gm.set_option("lanesolve", 1)
+                x1, ok1 = gm.linear_solve(dA, db, n, m, skip, rm)
+                xin = db.clone()
+                gm.linear_solve(dA, xin, n, m, skip, rm, x_out=xin)                  # in place
+                gm.set_option("lanesolve", 0)
+                x0, ok0 = gm.linear_solve(dA, db, n, m, skip, rm)
+                x1, ok1, x0, ok0, xin = down(x1), down(ok1), down(x0), down(ok0), down(xin)
+                tag = f"n={n} m={m} rm={rm} skip={skip}"
+                assert bits_equal(ok1, ok0), f"ok {tag}: {first_diff(ok1, ok0)}"
+                assert bits_equal(x1, x0), f"x {tag}: {first_diff(x1, x0)}"
+                assert bits_equal(xin, x0), f"x in place {tag}: {first_diff(xin, x0)}"
+                assert 0 < int((ok0 == 0).sum()) < B // 8
+                S = 1 << 15
+                with np.errstate(all="ignore"):
+                    _, xe, oke = orc.linear_solve(A[:S], b[:S], n, m, skip, rm)
+                assert bits_equal(ok1[:S], oke), f"ok vs {orc.kind} {tag}: {first_diff(ok1[:S], oke)}"
+                assert bits_equal(x1[:S], xe), f"x vs {orc.kind} {tag}: {first_diff(x1[:S], xe)}"
+    finally:
+        gm.set_option("lanesolve", -1)
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [5, 6, 7, 8])
+def test_lane_cholesky_is_the_row_cholesky(gm, orc, n, dt, soa):
+    """gmb_lane.cuh k_lane_chol (staged ingest, one thread per system) against the row kernel (option lanechol = 0) and the
+    reference: factor, ok flags and the fused solve, SPD and non-SPD systems, extreme scalings."""
+    if dt == np.float64 and n > 6:
+        pytest.skip("double: n = 5, 6 only (registers)")
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(3000 * n + np.dtype(dt).itemsize + int(soa))
+    B = (1 << 16) + 77
+    S = po.spd_exact(rng, B, n, dt)
+    S[::53, 0] = -1                                              # not positive definite
+    S[7::211] = 0
+    kmax = 30 if dt == np.float32 else 200
+    k = rng.integers(-kmax, kmax + 1, size=(B, n))
+    k[::3] = 0
+    with np.errstate(all="ignore"):
+        S = np.ldexp(S.astype(np.float64).reshape(B, n, n), k[:, :, None] + k[:, None, :]).astype(dt).reshape(B, n * n)
+    b1 = po.exact_grid(rng, (B, n), dt)
+    b2 = po.exact_grid(rng, (B, 2 * n), dt)
+    dS = up(gm, S, soa)
+    try:
+        for rm in (True, False):
+            for m, b in ((1, b1), (2, b2)):
+                db = up(gm, b, soa)
+                gm.set_option("lanechol", 1)
+                x1, ok1, L1 = gm.cholesky_solve(dS, db, n, m, rm, want_l=True)
+                Lf1, okf1 = gm.cholesky(dS, n, rm)
+                gm.set_option("lanechol", 0)
+                if m == 1:
+                    x0, ok0, L0 = gm.cholesky_solve(dS, db, n, m, rm, want_l=True)
+                    assert bits_equal(down(x1), down(x0)), f"x n={n} rm={rm}: {first_diff(down(x1), down(x0))}"
+                    assert bits_equal(down(L1), down(L0)), f"L n={n} rm={rm}: {first_diff(down(L1), down(L0))}"
+                    assert bits_equal(down(ok1), down(ok0))
+                with np.errstate(all="ignore"):
+                    Le, oke = orc.cholesky(S, n, rm)
+                    xe = po.port().cholesky_solve(Le, b, n, m, rm)       # the reference has no Cholesky solve: the port's definition
+                assert bits_equal(down(L1), Le), f"L vs {orc.kind} n={n} rm={rm}: {first_diff(down(L1), Le)}"
+                assert bits_equal(down(Lf1), Le), f"cholesky() vs {orc.kind} n={n} rm={rm}: {first_diff(down(Lf1), Le)}"
+                assert bits_equal(down(ok1), oke) and bits_equal(down(okf1), oke)
+                assert bits_equal(down(x1), xe), f"x vs port n={n} m={m} rm={rm}: {first_diff(down(x1), xe)}"
+                assert 0 < int((oke == 0).sum()) < B // 8
+    finally:
+        gm.set_option("lanechol", -1)
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [5, 7, 9, 12, 16])
+def test_multi_rhs_solve_takes_the_subwarp_kernel(gm, orc, n, dt, soa):
+    """m = 2..4 right-hand sides for n >= 5 ride through k_sub_plu as extra columns (no local-memory generic kernel)."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(4000 * n + np.dtype(dt).itemsize + int(soa))
+    B = (1 << 13) + 5
+    A, _ = hostile_batch(rng, B, n, dt)
+    dA = up(gm, A, soa)
+    launches = gm.lib().gmb_launch_count
+    for m in (2, 3, 4):
+        b = po.exact_grid(rng, (B, m * n), dt)
+        db = up(gm, b, soa)
+        for rm, skip in ((True, 0), (False, 1)):
+            x, ok, lu = gm.linear_solve(dA, db, n, m, skip, rm, want_lu=True)
+            with np.errstate(all="ignore"):
+                lue, xe, oke = orc.linear_solve(A, b, n, m, skip, rm)
+            tag = f"n={n} m={m} rm={rm} skip={skip}"
+            assert bits_equal(down(ok), oke), f"ok {tag}: {first_diff(down(ok), oke)}"
+            assert bits_equal(down(x), xe), f"x {tag}: {first_diff(down(x), xe)}"
+            assert bits_equal(down(lu), lue), f"lu {tag}: {first_diff(down(lu), lue)}"
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10])
+def test_deferred_rider_inverse_is_the_reference_inverse(gm, orc, n, dt, soa):
+    """k_sub_plu MODE_INVD (one lane per system, the identity is NOT carried through the elimination; the columns of the
+    inverse are produced in i-space and stored at their permuted positions) against the kernels that carry the riders
+    (option invd = 0) and against the reference, on a hostile 2^17 batch: singular systems (destination untouched), ties,
+    NaN / Inf (dense forward sweep inside the kernel), huge / tiny scalings (IEEE-division redo), all four layout pairs."""
+    if dt == np.float64 and n > 7:
+        pytest.skip("double: n <= 7 (registers)")
+    rng = np.random.default_rng(5000 * n + np.dtype(dt).itemsize + int(soa))
+    B = (1 << 17) + 33
+    A, _ = hostile_batch(rng, B, n, dt, every=37)
+    dA = up(gm, A, soa)
+    try:
+        for srm in (True, False):
+            for drm in (True, False):
+                init = np.full_like(A, 7)
+                gm.set_option("invd", 1)
+                o1, k1 = gm.inv(dA, n, srm, drm, out=up(gm, init, soa))
+                gm.set_option("invd", 0)
+                o0, k0 = gm.inv(dA, n, srm, drm, out=up(gm, init, soa))
+                o1, k1, o0, k0 = down(o1), down(k1), down(o0), down(k0)
+                tag = f"n={n} {srm}->{drm}"
+                assert bits_equal(k1, k0), f"ok {tag}: {first_diff(k1, k0)}"
+                assert bits_equal(o1, o0), f"inverse {tag}: {first_diff(o1, o0)}"
+                assert 0 < int((k0 == 0).sum()) < B // 4
+                S = 1 << 14
+                with np.errstate(all="ignore"):
+                    oe, ke = orc.inv(A[:S], n, srm, drm, init[:S])
+                assert bits_equal(k1[:S], ke), f"ok vs {orc.kind} {tag}: {first_diff(k1[:S], ke)}"
+                assert bits_equal(o1[:S], oe), f"inverse vs {orc.kind} {tag}: {first_diff(o1[:S], oe)}"
+    finally:
+        gm.set_option("invd", -1)
