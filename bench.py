@@ -557,6 +557,7 @@ def config_c5(c, steps=3, log2_b=23):
     rows.append(row(c, f"C5: 16x16 f32 fused PLU solve, 2^{log2_b} systems per GPU, AoS", "C5", B, total, steps, 1152,
                     {"verified_systems": int(sum_over_ranks(c, count)), "mismatches": int(sum_over_ranks(c, int(bad.sum()))),
                      "oracle": orc.kind, "failed_systems": int(sum_over_ranks(c, int((ok == 0).sum().item())))}))
+    rows[-1]["issue_roofline"] = issue_roofline(c, rows[-1], "c5_aos_warp_inst_per_system")
     As, bs_ = gm.BatchSoA.from_aos(A), gm.BatchSoA.from_aos(b)
     del A
     xs = bs_.empty_like()
@@ -565,7 +566,28 @@ def config_c5(c, steps=3, log2_b=23):
     rows.append(row(c, f"C5: 16x16 f32 fused PLU solve, 2^{log2_b} systems per GPU, SoA container", "C5", B, total, steps, 1152,
                     {"verified_systems": int(sum_over_ranks(c, B)), "mismatches": int(sum_over_ranks(c, 0 if same else 1)),
                      "verified": "whole batch bit-identical to the AoS run (which is checked against the oracle)"}))
+    rows[-1]["issue_roofline"] = issue_roofline(c, rows[-1], "c5_soa_warp_inst_per_system")
     return rows
+
+
+def issue_roofline(c, r, key):
+    """The bound that actually binds for n >= 9: instruction issue.  warp instructions per system (ncu smsp__inst_executed.sum
+    of this kernel / systems, profiles/traffic.json) x systems/s against 148 SMs x 4 schedulers x the SM clock."""
+    t = read_traffic()
+    inst = t.get(key)
+    if inst is None:
+        return None
+    sms, clock_hz = 148, 1.965e9
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        clock_hz = float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    except Exception:
+        pass
+    peak_issue = sms * 4 * clock_hz                          # warp instructions per second per GPU
+    per_gpu = r["systems_per_s"] / c.world
+    return {"warp_inst_per_system": inst, "issue_slots_frac": per_gpu * inst / peak_issue,
+            "systems_per_s_at_full_issue": peak_issue / inst, "hbm_roofline_systems_per_s": c.peak * 1e9 / r["alg_bytes_per_system"],
+            "source": t.get("c5_source")}
 
 
 def main():
@@ -681,6 +703,25 @@ def main():
         # the host path and the resident SoA path must agree bit for bit
         same = bool(torch.equal(hx.cuda(dev).view(torch.int32), x.to_aos().view(torch.int32)))
         e2e["matches_resident_path"] = same
+        # the bound of this number is PCIe / host memory, not the kernel: the plain pinned-copy rates of the same buffers
+        try:
+            dA = torch.empty((Be, n * n), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dA.copy_(hA, non_blocking=True)
+            torch.cuda.synchronize()
+            h2d = 3 * hA.numel() * 4 / max_over_ranks(c, time.perf_counter() - t0) / 1e9
+            t0 = time.perf_counter()
+            for _ in range(3):
+                hA.copy_(dA, non_blocking=True)
+            torch.cuda.synchronize()
+            d2h = 3 * hA.numel() * 4 / max_over_ranks(c, time.perf_counter() - t0) / 1e9
+            e2e["pinned_copy_GBps_per_gpu"] = {"h2d": h2d, "d2h": d2h, "note": "slowest rank, all ranks copying at once"}
+            e2e["pcie_bound_systems_per_s"] = world * min(h2d * 1e9 / (4 * (n * n + n)), d2h * 1e9 / (4 * n + 1))
+            del dA
+        except Exception as ex:
+            e2e["pinned_copy_GBps_per_gpu"] = {"error": repr(ex)[:200]}
         del hA, hb, hx, hok
     except Exception as ex:
         e2e = {"value": None, "unit": "systems/s", "error": repr(ex)[:300]}

@@ -22,7 +22,6 @@ std::atomic<int> g_opt_rowdecomp_min_n{-1};  // decomp_plu: row-distributed kern
 std::atomic<int> g_opt_rowinv{-1};           // inverse n >= 5: 0 = column-distributed kernel, 1 = row-distributed
 std::atomic<int> g_opt_rowfast{-1};          // speculative solve (gmb_rowfast.cuh): 0 = off, 1 = wherever it exists
 std::atomic<int> g_opt_invd{-1};             // deferred-rider inverse (k_sub_plu MODE_INVD): 0 = off, 1 = wherever it exists
-std::atomic<int> g_opt_lanesolve{-1};        // one-thread-per-system speculative solve, n = 5..8 (gmb_lane.cuh): 0 = off, 1 = on
 std::atomic<int> g_opt_lanechol{-1};         // one-thread-per-system Cholesky with staged ingest, n = 5..8: 0 = off, 1 = on
 
 // gmb_small.cu
@@ -39,6 +38,7 @@ template <typename T> int small_residual(int, int64_t, const T*, const T*, const
 template <typename T> int subwarp_plu_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T, int XC> int subwarp_plu_solve_m(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int subwarp_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
+template <typename T> int subwarp_rect(int, int, int64_t, const T*, T*, uint8_t*, int, cudaStream_t);
 template <typename T> int subwarp_invd(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int subwarp_lup(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int subwarp_inv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
@@ -51,7 +51,6 @@ template <typename T> int row_backsolve(int, int, int, int64_t, const T*, const 
 // gmb_rowfast_*.cu
 template <typename T> int rowfast_solve(int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 // gmb_lane_*.cu
-template <typename T> int lane_solve(int, int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int lane_cholesky(int, int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, bool, cudaStream_t);
 // gmb_generic.cu
 template <typename T> int generic_decomp(int, int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, bool, cudaStream_t);
@@ -75,17 +74,18 @@ template <typename T> int xf_translation(int, int64_t, const T*, T*, int, int, b
 template <typename T> int xf_compose(int, int64_t, const T*, const T*, T*, int, int, cudaStream_t);
 template <typename T> int xf_apply(int, int, int64_t, const T*, bool, const T*, T*, int, cudaStream_t);
 
-// Which fused-solve kernel serves (T, n)?  Measured on B200 (2^20 systems, AoS, CUDA events;
-// profiles/r1d_row_vs_column.md, profiles/r1h_row_exchange.md).  With an LU output the row-distributed kernel
-// (bounce-buffer exchange of whole rows) wins for float n in {12, 14, 15, 16} and for double n = 10 and n >= 12;
-// without one -- the common call -- only the live part of a row travels and the register-only shuffle exchange
-// applies: the row kernel then wins for every float n >= 8 and for double n = 7, 8 and n >= 10.
+// Which fused-solve kernel serves (T, n)?  Measured on B200 (profiles/r2e_row_vs_subwarp.md: working sets > 2 x L2, AoS and
+// SoA, CUDA events).  With an LU output the row-distributed kernel (bounce-buffer exchange of whole rows) wins for float n
+// in {12, 14, 15, 16} and for double n = 10 and n >= 12 (round 1).  Without one -- the common call -- only the live part of
+// a row travels and the register-only shuffle exchange applies; since the one-lane-per-system sub-warp kernel got its
+// staged record I/O (round 2) it wins up to float n = 9 (n = 8: 0.49 / 0.61 of the peak AoS / SoA against 0.48 / 0.49;
+// n = 9: 0.50 / 0.57 against 0.37 / 0.47), the row kernel from float n = 10 on and for double n = 7, 8 and n >= 10.
 // gmb_set_option("rowplu_min_n", n) overrides the table (17 disables the row kernel, 9 forces it).
 template <typename T>
 static bool use_row_kernel(int n, bool want_lu) {
     const int forced = g_opt_rowplu_min_n.load(std::memory_order_relaxed);
     if (forced >= 0) return n >= forced;
-    if (!want_lu) return sizeof(T) == 4 ? n >= 8 : (n == 7 || n == 8 || n >= 10);
+    if (!want_lu) return sizeof(T) == 4 ? n >= 10 : (n == 7 || n == 8 || n >= 10);
     if (n < 9) return false;
     if (sizeof(T) == 4) return n == 12 || n >= 14;
     return n == 10 || n >= 12;
@@ -100,14 +100,6 @@ static bool use_rowfast(int n) {
     return sizeof(T) == 4 && (n == 13 || n >= 15);
 }
 
-// One thread per system (gmb_lane.cuh): float n = 5..8, double n = 5..6.
-template <typename T>
-static bool use_lane_solve(int n, int m) {
-    if (n < 5 || n > (sizeof(T) == 4 ? 8 : 6) || m > 4) return false;
-    const int forced = g_opt_lanesolve.load(std::memory_order_relaxed);
-    if (forced >= 0) return forced != 0;
-    return false;
-}
 // Cholesky: the row kernel (one lane per system for these sizes, staged AoS ingest) serves one right-hand side; the
 // lane kernel serves 2..4 of them (the row kernel carries one rider).  Option "lanechol": 1 = lane kernel for m = 1 too
 // (tests), 0 = never (m > 1 then falls to the generic kernel).
@@ -202,12 +194,6 @@ int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* o
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && n >= 2 && n <= 4 && m <= 4) {
         int rc = small_plu_solve<T>(n, m, B, A, Bm, X, ok, LU, skip, layout, rm, st);
-        if (rc != GMB_ERR_UNSUPPORTED) return rc;
-    }
-    // n = 5..8 (double: 5, 6), up to four right-hand sides, no LU output: one thread per system, speculative, with the
-    // exact re-solve of the systems it hands back (gmb_lane.cuh)
-    if (fast && LU == nullptr && use_lane_solve<T>(n, m)) {
-        int rc = lane_solve<T>(n, m, B, A, Bm, X, ok, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     // n >= 9, one right-hand side, no LU output: speculative kernel + exact re-solve of the systems it hands back
@@ -316,6 +302,10 @@ int orthogonal(int n, int64_t B, const T* V, T* out, int layout, void* stream) {
     const bool fast = all_aligned16(V, out);
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && n <= 4) return small_orthogonal<T>(n, B, V, out, layout, as_stream(stream));
+    if (fast && n >= 5) {                                    // register kernel: rectangular (n-1) x n PLU + back-substitution
+        int rc = subwarp_rect<T>(n, n - 1, B, V, out, nullptr, layout, as_stream(stream));
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
     return generic_orthogonal<T>(n, B, V, out, layout, as_stream(stream));
 }
 
@@ -366,6 +356,10 @@ int nullspace(int N, int nb, int64_t B, const T* bases, T* null, uint8_t* ok, in
     if (B < 0 || N < 3 || nb < 1 || nb >= N || bad_layout(layout) || (B > 0 && (bases == nullptr || null == nullptr)))
         return GMB_ERR_INVALID_ARG;
     if (N > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    if (N >= 5 && all_aligned16(bases, null)) {
+        int rc = subwarp_rect<T>(N, nb, B, bases, null, ok, layout, as_stream(stream));
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
     return generic_nullspace<T>(N, nb, B, bases, null, ok, layout, as_stream(stream));
 }
 
@@ -663,7 +657,6 @@ int gmb_set_option(const char* name, int value) {
                           : !std::strcmp(name, "rowinv")          ? &g_opt_rowinv
                           : !std::strcmp(name, "rowfast")         ? &g_opt_rowfast
                           : !std::strcmp(name, "invd")            ? &g_opt_invd
-                          : !std::strcmp(name, "lanesolve")       ? &g_opt_lanesolve
                           : !std::strcmp(name, "lanechol")        ? &g_opt_lanechol
                                                                   : nullptr;
     if (!o) return GMB_ERR_INVALID_ARG;

@@ -165,51 +165,6 @@ g_solve(int n, int m, int64_t B, const T* A, const uint8_t* perm, const T* Bm, T
     store_local(X, atX, s, rm, n, m, x);
 }
 
-// The fused solve (g_solve, MODE 3) on a LIST of systems: the speculative kernels (gmb_lane.cuh) hand back the systems
-// that need the reference's exact rules -- ties, zero columns, operands outside the fast division window, NaN / Inf.
-// A grid-stride loop over list[0 .. *count); count lives on the device (no host synchronisation).
-template <typename T>
-__global__ void __launch_bounds__(kGenThreads)
-g_solve_list(int n, int m, const T* A, const T* Bm, T* X, uint8_t* ok, int skip, int layout, int rm,
-             const int32_t* __restrict__ list, const int* __restrict__ count) {
-    const int total = *count;
-    for (int idx = blockIdx.x * kGenThreads + threadIdx.x; idx < total; idx += gridDim.x * kGenThreads) {
-        const int64_t s = list[idx];
-        T a[kMaxN * kMaxN];
-        T x[kMaxN * GMB_MAX_M];
-        uint8_t p[kMaxN];
-        Addr<T> atA{layout, n * n}, atX{layout, n * m};
-        load_local(A, atA, s, rm != 0, n, n, a);
-        bool par;
-        const int d = lu_local<T, false>(a, n, n, p, par);
-        if (ok) ok[s] = d == 0 ? 1 : 0;
-        if (d > 0) {                                    // LUDecomp.h:391-393: x untouched
-            if (X != Bm)
-                for (int e = 0; e < n * m; ++e) X[atX(s, e)] = Bm[atX(s, e)];
-            continue;
-        }
-        for (int r = 0; r < n; ++r)
-            for (int i = 0; i < m; ++i) x[m * r + i] = Bm[atX(s, midx(rm != 0, n, m, p[r], i))];
-        backsolve_local(a, n, m, x, skip);
-        store_local(X, atX, s, rm != 0, n, m, x);
-    }
-}
-
-template <typename T>
-int generic_solve_list(int n, int m, const T* A, const T* Bm, T* X, uint8_t* ok, int skip, int layout, int rm,
-                       const int32_t* list, const int* count, int64_t B, cudaStream_t st) {
-    if (n > kMaxN || m > GMB_MAX_M) return GMB_ERR_UNSUPPORTED;
-    const int64_t want = ceil_div(B, kGenThreads);
-    const unsigned grid = (unsigned)(want < 296 ? want : 296);
-    if (grid == 0) return GMB_OK;
-    g_solve_list<T><<<grid, kGenThreads, 0, st>>>(n, m, A, Bm, X, ok, skip, layout, rm, list, count);
-    return after_launch();
-}
-template int generic_solve_list<float>(int, int, const float*, const float*, float*, uint8_t*, int, int, int, const int32_t*,
-                                       const int*, int64_t, cudaStream_t);
-template int generic_solve_list<double>(int, int, const double*, const double*, double*, uint8_t*, int, int, int, const int32_t*,
-                                        const int*, int64_t, cudaStream_t);
-
 template <typename T, bool SOLVE>
 __global__ void __launch_bounds__(kGenThreads)
 g_cholesky(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok, T* L_out, int layout, int rm) {

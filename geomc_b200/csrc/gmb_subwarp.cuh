@@ -39,6 +39,7 @@ constexpr int MODE_SOLVE = 0;   // A, Bm -> X, ok (, LU)
 constexpr int MODE_DECOMP = 1;  // A in place, perm, parity, degenerate
 constexpr int MODE_INV = 2;     // A -> Ainv, ok
 constexpr int MODE_INVD = 3;    // A -> Ainv, ok: one lane per system, riders deferred (see k_sub_plu)
+constexpr int MODE_RECT = 4;    // nb x N bases (nb < N rows, runtime) -> null basis / orthogonal vector, ok (Orthogonal.h:73-178)
 
 constexpr int sub_lc(int n, int xc, int g) { return (n + xc + g - 1) / g; }
 // does ANY lane of the group hold a rider column / a column beyond `i` at local index j?  (static)
@@ -114,6 +115,11 @@ __device__ __forceinline__ void sub_lane_store(T* __restrict__ base, int64_t s, 
 // elements of the largest record a G == 1 AoS kernel moves (matrix, or the rider block)
 constexpr int sub_lane_emax(int n, int xc) { return n * (n > xc ? n : xc); }
 
+// MODE_RECT (XC = 0, G = 1): orthogonal (Orthogonal.h:73-98) and nullspace (:136-178).  Both run the RECTANGULAR row-pivot
+// decomposition of the nb x N matrix whose rows are the given vectors (nb = `skip`, a run-time value, nb < N) and then a
+// small back-substitution.  The matrix is held as N x N with rows >= nb zero: a zero row never wins the strict pivot
+// comparison (:205-213) and its multipliers are 0 / pivot, so rows < nb see exactly the rectangular algorithm provided
+// the elimination stops after min(nb, N) - 1 = nb - 1 steps, as the reference's does (:203).
 // MODE_INVD (XC = 0, G = 1): invNxN (MatrixInv.h:219-231) without carrying the identity through the elimination.  The
 // reference decomposes, sets out(i, p[i]) = 1 and runs backsolve_lu on the n columns of `out`.  Column p[i] of that
 // right-hand side is e_i, so its forward sweep (LUDecomp.h:345-353) is y(r) = 0 for r < i, y(i) = 1 and the reference's
@@ -170,7 +176,15 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
 
     // ---- load the local block -------------------------------------------------------------
     T a[N][LC];
-    if constexpr (LANE_IO) {
+    if constexpr (MODE == MODE_RECT) {
+        static_assert(G == 1 && XC == 0, "rectangular mode: one lane per system");
+        const int nb = skip;
+        const int64_t baseV = BatchAddr<T, SOA>::base(s, N * nb);       // nb vectors of N: row-major nb x N
+#pragma unroll
+        for (int r = 0; r < N; ++r)
+#pragma unroll
+            for (int c = 0; c < N; ++c) a[r][c] = (r < nb) ? A[baseV + (int64_t)(N * r + c) * ST] : (T)0;
+    } else if constexpr (LANE_IO) {
         T qa[N * N];
         sub_lane_load<T, N * N>(A, s_raw, threadIdx.x & 31, lane_full, valid, qa, lane_sm);
 #pragma unroll
@@ -218,6 +232,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     // ---- elimination ----------------------------------------------------------------------
 #pragma unroll
     for (int i = 0; i < N - 1; ++i) {
+        if (MODE == MODE_RECT && i >= skip - 1) break;       // rectangular: min(rows, cols) - 1 steps (warp-uniform)
         const int owner = i / LC;          // static
         const int k = i % LC;              // static local column of the pivot column in the owner lane
         // pivot search on local column k (meaningful in the owner lane only)
@@ -333,6 +348,63 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     }
 
     const bool good = degenerate == 0;
+
+    if constexpr (MODE == MODE_RECT) {
+        const int nb = skip, nn = N - nb;
+        const int64_t baseO = BatchAddr<T, SOA>::base(s, N * nn);
+        if (valid && ok_out) ok_out[s] = (nn == 1 || good) ? 1 : 0;     // N - n == 1 returns true whatever happened (:138-142)
+        if (nn == 1) {
+            // orthogonal (:73-98): o = 0 when the decomposition reports a degenerate column; else o(N-1) = 1 and, for
+            // r = N-2 .. 0, o(r) = (0 - sum_{c = N-1 .. r+1} o(c) m(r,c)) / m(r,r)
+            T o[N];
+#pragma unroll
+            for (int e = 0; e < N; ++e) o[e] = (T)0;
+            if (good) {
+                o[N - 1] = (T)1;
+#pragma unroll
+                for (int r = N - 2; r >= 0; --r) {
+                    T acc = (T)0;
+#pragma unroll
+                    for (int c = N - 1; c > r; --c) acc = fma_rn(-o[c], a[r][c], acc);
+                    o[r] = div_rn(acc, a[r][r]);
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) X[baseO + (int64_t)e * ST] = o[e];
+            }
+            return;
+        }
+        // nullspace (:144-176): null vector b has 1 at row nb + b, x(r) = (-m(r, nb + b) - sum_{c = r+1 .. nb-1} m(r,c) x(c)) / m(r,r)
+        // for r = nb-1 .. 0, zeros elsewhere; all-zero vectors when the decomposition reports a degenerate column
+#pragma unroll
+        for (int b = 0; b < N - 1; ++b) {
+            if (b >= nn) break;
+            T x[N];
+#pragma unroll
+            for (int r = N - 1; r >= 0; --r) {
+                x[r] = (T)0;
+                if (r < nb && r <= N - 3) {
+                    T t = (T)0;
+#pragma unroll
+                    for (int c = 1; c < N; ++c) t = (c == nb + b) ? a[r][c] : t;       // m(r, nb + b): run-time column
+                    T xi = -t;
+#pragma unroll
+                    for (int c = r + 1; c <= N - 3; ++c)
+                        if (c < nb) xi = fma_rn(-a[r][c], x[c], xi);
+                    x[r] = div_rn(xi, a[r][r]);
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int e = 0; e < N; ++e) {
+                    const T v = !good ? (T)0 : (e < nb ? x[e] : (e == nb + b ? (T)1 : (T)0));
+                    X[baseO + (int64_t)(N * b + e) * ST] = v;
+                }
+            }
+        }
+        return;
+    }
 
     if constexpr (MODE == MODE_INVD) {
         static_assert(G == 1 && XC == 0, "deferred-rider inverse: one lane per system");
@@ -651,6 +723,20 @@ int subwarp_lup_impl(int n, int64_t B, T* A, uint8_t* perm, uint8_t* parity, uin
 // inv for n >= 5 (MatrixInv.h:243-249 + 219-231): the working copy has the DESTINATION's layout and
 // is then treated as row-major, i.e. the kernel reads A with a_rm = (src layout == dst layout)
 // and writes the result flat row-major into the destination buffer.
+// orthogonal / nullspace (MODE_RECT) for the sizes whose matrix fits one lane (float N <= 10, double N <= 7): nb vectors of N
+template <typename T>
+int subwarp_rect_impl(int N_, int nb, int64_t B, const T* bases, T* null_basis, uint8_t* ok, int layout, cudaStream_t st) {
+    int rc = GMB_ERR_UNSUPPORTED;
+    if (nb < 1 || nb >= N_) return rc;
+    dispatch_int<5, 6, 7, 8, 9, 10>(N_, [&](auto N) {
+        if constexpr (sub_group(N.value, 0, (int)sizeof(T) / 4) == 1) {
+            rc = launch_sub<T, N.value, 0, MODE_RECT>(bases, nullptr, null_basis, nullptr, ok, nullptr, nullptr, nullptr, nb, B, layout,
+                                                      1, 1, st);
+        }
+    });
+    return rc;
+}
+
 // deferred-rider inverse (MODE_INVD): the sizes whose matrix alone fits one lane (float n <= 10, double n <= 7)
 template <typename T>
 int subwarp_invd_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm,

@@ -6,4 +6,8 @@ template <> int subwarp_lup<double>(int n, int64_t B, double* A, uint8_t* perm, 
                                 cudaStream_t st) {
     return subwarp_lup_impl<double>(n, B, A, perm, parity, degen, layout, rm, st);
 }
+template <typename T> int subwarp_rect(int, int, int64_t, const T*, T*, uint8_t*, int, cudaStream_t);
+template <> int subwarp_rect<double>(int N, int nb, int64_t B, const double* bases, double* null_basis, uint8_t* ok, int layout, cudaStream_t st) {
+    return subwarp_rect_impl<double>(N, nb, B, bases, null_basis, ok, layout, st);
+}
 }  // namespace gmb

@@ -13,7 +13,7 @@ import geomc_b200 as gm  # noqa: E402
 
 peak = 6548.8
 try:
-    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbps"]["burst"])
+    peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
 dev = torch.device("cuda", 0)

@@ -82,6 +82,18 @@ def run(case):
         A, b = grid((B, n * n), dt), grid((B, n), dt)
         x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.linear_solve(A, b, n, x_out=x, ok_out=ok)
+    if case == "c1soa":                   # the metric kernel at the bench size: 2^24 4x4 float systems, SoA container
+        B = 1 << 24
+        A, b = gm.BatchSoA(B, 16, f32, dev), gm.BatchSoA(B, 4, f32, dev)
+        A.data.copy_(grid(A.data.shape, f32))
+        b.data.copy_(grid(b.data.shape, f32))
+        x, ok = b.empty_like(), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.linear_solve(A, b, 4, 1, 0, True, x_out=x, ok_out=ok)
+    if case == "c5big":                   # C5 at its stated size: 2^23 16x16 float systems, AoS
+        B = 1 << 23
+        A, b = grid((B, 256), f32), grid((B, 16), f32)
+        x, ok = torch.empty_like(b), torch.zeros(B, dtype=torch.uint8, device=dev)
+        return lambda: gm.linear_solve(A, b, 16, x_out=x, ok_out=ok)
     if case.startswith("ssolve"):         # ssolve<f|d><n>: fused PLU solve, SoA container, n x n
         dt = f32 if case[6] == "f" else f64
         n = int(case[7:])

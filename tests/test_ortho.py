@@ -69,7 +69,7 @@ def test_verify_nullspace_property(port, n):
 @pytest.mark.gpu
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("tag", ["f32", "f64"])
-def test_gpu_matches_golden_and_oracle(port, tag, soa):
+def test_gpu_matches_golden_and_oracle(port, orc, tag, soa):
     torch = pytest.importorskip("torch")
     import geomc_b200 as gm
     gm.lib()
@@ -104,3 +104,24 @@ def test_gpu_matches_golden_and_oracle(port, tag, soa):
                 x, ok = gm.nullspace(up(bs), n, nb)
                 xe, oke = port.nullspace(bs, n, nb)
                 assert bits_equal(down(x), xe) and np.array_equal(down(ok), oke), f"random nullspace N={n} nb={nb}"
+        # every basis count for the sizes served by the register kernel (k_sub_plu MODE_RECT: float N <= 10, double N <= 7) and
+        # its neighbours, against the compiled reference: dependent vectors, zero vectors, ties, huge / tiny scalings
+        for n in range(5, 12):
+            for nb in range(1, n):
+                bs = rng.standard_normal((257, nb * n)).astype(dt)
+                bs[::29] = 0
+                bs[5::31, :n] = 1.0                                  # ties in the first vector
+                if nb >= 2:
+                    bs[7::37, n:2 * n] = bs[7::37, :n]               # two equal vectors: degenerate
+                bs[11::41] *= dt(1e20 if dt == np.float32 else 1e150)
+                bs[13::43] *= dt(1e-20 if dt == np.float32 else 1e-150)
+                x, ok = gm.nullspace(up(bs), n, nb)
+                xe, oke = orc.nullspace(bs, n, nb)
+                assert bits_equal(down(x), xe), f"nullspace vs {orc.kind} N={n} nb={nb} soa={soa}: {first_diff(down(x), xe)}"
+                assert np.array_equal(down(ok), oke), f"nullspace ok N={n} nb={nb}"
+            v = rng.standard_normal((513, (n - 1) * n)).astype(dt)
+            v[3::17, n:2 * n] = v[3::17, :n]
+            v[11::41] *= dt(1e20 if dt == np.float32 else 1e150)
+            oe = orc.orthogonal(v, n)
+            got = down(gm.orthogonal(up(v), n))
+            assert bits_equal(got, oe), f"orthogonal vs {orc.kind} n={n} soa={soa}: {first_diff(got, oe)}"
