@@ -703,6 +703,34 @@ def main():
         # the host path and the resident SoA path must agree bit for bit
         same = bool(torch.equal(hx.cuda(dev).view(torch.int32), x.to_aos().view(torch.int32)))
         e2e["matches_resident_path"] = same
+        # the same call with the INPUT batches in write-combined pinned memory (gmb_host_alloc_wc): the DMA reads skip the
+        # CPU-cache snoop -- tried because the 8-GPU e2e number is bound by the host feeding eight PCIe links
+        try:
+            import ctypes
+            nA, nb_ = Be * n * n, Be * n
+            pA, pb = L.gmb_host_alloc_wc(nA * 4), L.gmb_host_alloc_wc(nb_ * 4)
+            if pA and pb:
+                wA = np.ctypeslib.as_array((ctypes.c_float * nA).from_address(pA)).reshape(Be, n * n)
+                wb = np.ctypeslib.as_array((ctypes.c_float * nb_).from_address(pb)).reshape(Be, n)
+                wA[...] = hA.numpy()
+                wb[...] = hb.numpy()
+                hx2 = torch.empty_like(hx).pin_memory()
+                gm.host_linear_solve(wA, wb, hx2.numpy(), hok.numpy(), n, device=local_rank)
+                if world > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    gm.host_linear_solve(wA, wb, hx2.numpy(), hok.numpy(), n, device=local_rank)
+                dtw = max_over_ranks(c, time.perf_counter() - t0)
+                e2e["write_combined_inputs"] = {"value": Be * world * e2e_steps / dtw, "unit": "systems/s",
+                                                "matches": bool(torch.equal(hx2.view(torch.int32), hx.view(torch.int32)))}
+                del wA, wb, hx2
+            if pA:
+                L.gmb_host_free(pA)
+            if pb:
+                L.gmb_host_free(pb)
+        except Exception as ex:
+            e2e["write_combined_inputs"] = {"error": repr(ex)[:200]}
         # the bound of this number is PCIe / host memory, not the kernel: the plain pinned-copy rates of the same buffers
         try:
             dA = torch.empty((Be, n * n), dtype=torch.float32, device=dev)

@@ -65,7 +65,8 @@ _TYPED = {
 UNTYPED = ["gmb_version", "gmb_error_string", "gmb_device_count", "gmb_soa_tile_width", "gmb_soa_elems",
            "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count", "gmb_set_option", "gmb_set_device",
            "gmb_device_alloc", "gmb_device_free", "gmb_memcpy_h2d", "gmb_memcpy_d2h", "gmb_memset_device",
-           "gmb_stream_synchronize", "gmb_get_device", "gmb_host_register", "gmb_host_unregister", "gmb_shard_range"]
+           "gmb_stream_synchronize", "gmb_get_device", "gmb_host_register", "gmb_host_unregister", "gmb_shard_range",
+           "gmb_host_alloc_wc"]
 EXPORTS = UNTYPED + [f"{k}_{s}" for k in _TYPED for s in ("f32", "f64")]
 
 
@@ -96,6 +97,8 @@ def lib() -> C.CDLL:
     L.gmb_checksum_bytes.argtypes = [_vp, _i64, _i64, _vp, _vp]
     L.gmb_host_alloc.restype = _vp
     L.gmb_host_alloc.argtypes = [C.c_size_t]
+    L.gmb_host_alloc_wc.restype = _vp
+    L.gmb_host_alloc_wc.argtypes = [C.c_size_t]
     L.gmb_host_free.restype = None
     L.gmb_host_free.argtypes = [_vp]
     L.gmb_launch_count.restype = _i64

@@ -125,13 +125,15 @@ static bool all_aligned16(P... ptrs) {
     return ((reinterpret_cast<uintptr_t>(ptrs) % 16 == 0) && ...);
 }
 
-// Same question for decomp_plu (option "rowdecomp_min_n" overrides).  Measured (2^21 systems, SoA, in place):
-// the row kernel wins for float n >= 9 (n = 16: 1.35x) and double n >= 10 (n = 16: 2.3x); ties below.
+// Same question for decomp_plu (option "rowdecomp_min_n" overrides).  Measured again in round 2 (profiles/r2e_row_vs_subwarp.md,
+// profiles/r2f_sweep_norow.md; working sets > 2 x L2, in place, AoS / SoA): with its staged record I/O the sub-warp kernel wins
+// for float n <= 14 (n = 9: 0.93 / 0.79 of the peak against 0.35 / 0.46; n = 13: 0.44 / 0.52 against 0.32 / 0.39) and double
+// n <= 11; the row kernel keeps float n = 15, 16 and double n >= 12.
 template <typename T>
 static bool use_row_decomp(int n) {
     const int forced = g_opt_rowdecomp_min_n.load(std::memory_order_relaxed);
     if (forced >= 0) return n >= forced;
-    return sizeof(T) == 4 ? n >= 9 : n >= 10;
+    return sizeof(T) == 4 ? n >= 15 : n >= 12;
 }
 
 // ------------------------------------------------------------------ typed implementations
@@ -667,6 +669,14 @@ int gmb_set_option(const char* name, int value) {
 void* gmb_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void* gmb_host_alloc_wc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined | cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }

@@ -269,6 +269,9 @@ int gmb_checksum_bytes(const void* data, int64_t nbytes, int64_t word_offset, ui
  * over several streams on `device`; it returns when the results are in the host buffers.
  * Pinned buffers (gmb_host_alloc, or cudaHostRegister'ed memory) give full PCIe bandwidth. */
 void* gmb_host_alloc(size_t bytes);
+/* Write-combined pinned memory for INPUT batches the host only writes (fills) and the GPU only reads: the DMA engine
+ * does not have to snoop the CPU caches.  Reading it back on the CPU is slow; free with gmb_host_free. */
+void* gmb_host_alloc_wc(size_t bytes);
 void gmb_host_free(void* p);
 /* Pin / unpin memory the application already owns (an array of SimpleMatrix objects, a std::vector's storage) so that
  * the host entry points reach full PCIe bandwidth on it without a copy into a pinned staging buffer.  Returns a

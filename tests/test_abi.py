@@ -70,3 +70,25 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in text and "liboracle" not in text and "libgeomc_ref" not in text, f
+
+
+def test_c_and_python_shard_ranges_agree():
+    """gmb_shard_range (used by the multi-device host entry points) == geomc_b200.sharding.shard_range (used by bench.py and the
+    gloo tests): every system belongs to exactly one shard, boundaries on multiples of `align`."""
+    import ctypes
+    from geomc_b200 import _lib
+    from geomc_b200.sharding import shard_range
+    L = _lib.lib()
+    for B in (0, 1, 7, 1023, 1024, 150001, 1 << 24):
+        for world in (1, 2, 3, 8):
+            for align in (1, 64, 128, 1024):
+                covered = 0
+                for r in range(world):
+                    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+                    assert L.gmb_shard_range(B, r, world, align, ctypes.byref(lo), ctypes.byref(hi)) == 0
+                    assert (lo.value, hi.value) == shard_range(B, r, world, align)
+                    assert lo.value == covered and (lo.value % align == 0 or lo.value == B)
+                    covered = hi.value
+                assert covered == B
+    lo, hi = ctypes.c_int64(), ctypes.c_int64()
+    assert L.gmb_shard_range(10, 2, 2, 1, ctypes.byref(lo), ctypes.byref(hi)) != 0      # rank out of range

@@ -336,6 +336,52 @@ def test_host_api_matches_device_api(gm, orc):
     check(par, e[2], "host decomp parity")
 
 
+def test_multi_device_host_entry_points(gm, orc):
+    """gmb_host_*_multi_*: the batch is sharded contiguously (gmb_shard_range, 1024-system granules) over the listed devices,
+    one pipeline and one host thread per device.  Runs on every device the box has (one is enough: the sharding, the
+    thread-per-device driver and the offset arithmetic are the same); results are those of the single-device call."""
+    import ctypes
+    ndev = gm.lib().gmb_device_count()
+    devs = list(range(ndev))
+    rng = np.random.default_rng(19)
+    B, n = 150001, 4
+    A = rng.standard_normal((B, n * n)).astype(np.float32)
+    A[::997] = 0
+    b = rng.standard_normal((B, n)).astype(np.float32)
+    with np.errstate(all="ignore"):
+        _, xe, oke = orc.linear_solve(A, b, n)
+        ie, ike = orc.inv(A, n, True, True, np.full_like(A, 3))
+    for use in ([0], devs, devs[::-1]):
+        x, ok = np.zeros_like(b), np.zeros(B, np.uint8)
+        gm.host_linear_solve(A, b, x, ok, n, device=list(use))
+        check(x, xe, f"multi-device linear_solve x on {use}")
+        check(ok, oke, f"multi-device linear_solve ok on {use}")
+        out = np.full_like(A, 3)
+        gm.host_inv(A, out, ok, n, device=list(use))
+        check(out, ie, f"multi-device inv on {use}")
+        check(ok, ike, f"multi-device inv ok on {use}")
+    A6 = rng.standard_normal((B // 5, 36))
+    e = orc.decomp_plu(A6, 6)
+    lu, p = A6.copy(), np.zeros((B // 5, 6), np.uint8)
+    par, dg = np.zeros(B // 5, np.uint8), np.zeros(B // 5, np.uint8)
+    gm.host_decomp_plu(lu, p, par, dg, 6, device=devs)
+    check(lu, e[0], "multi-device decomp lu")
+    check(p.astype(np.int64), e[1], "multi-device decomp perm")
+    check(par, e[2], "multi-device decomp parity")
+    # the C and Python shard helpers agree (bench.py and the gloo tests use the Python one)
+    from geomc_b200.sharding import shard_range
+    for Bq, world, align in ((150001, 3, 1024), (7, 8, 1), (1 << 20, 8, 128), (0, 2, 64)):
+        for r in range(world):
+            lo, hi = ctypes.c_int64(), ctypes.c_int64()
+            assert gm.lib().gmb_shard_range(Bq, r, world, align, ctypes.byref(lo), ctypes.byref(hi)) == 0
+            assert (lo.value, hi.value) == shard_range(Bq, r, world, align), (Bq, world, align, r)
+    # argument errors: duplicate / out-of-range devices
+    with pytest.raises(Exception):
+        gm.host_linear_solve(A, b, x, ok, n, device=[0, 0])
+    with pytest.raises(Exception):
+        gm.host_linear_solve(A, b, x, ok, n, device=[ndev])
+
+
 def test_full_size_properties(gm):
     """BASELINE-size batch (2^24 4x4 float systems): size-independent properties instead of the oracle.
     (1) residual of A x = b stays small on every system, (2) inverse round trip inv(inv(A)) ~ A,
