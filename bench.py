@@ -356,7 +356,8 @@ def config_c2(c, steps=5):
     B = 1 << 24
     g = t.Generator(device=c.dev).manual_seed(2000 + c.rank)
     R = t.randint(-128, 128, (B, 3, 3), device=c.dev, generator=g).double() * 2.0 ** -5
-    S = (R @ R.transpose(1, 2) + t.eye(3, device=c.dev, dtype=t.float64)).reshape(B, 9).contiguous()
+    # S = R R^T + I with element-wise kernels (exact on this grid in any order; no library GEMM in this process)
+    S = ((R.unsqueeze(2) * R.unsqueeze(1)).sum(dim=3) + t.eye(3, device=c.dev, dtype=t.float64)).reshape(B, 9).contiguous()
     bs = grid_f(c, (B, 3), t.float64, g)
     del R
     Ss, bss = gm.BatchSoA.from_aos(S), gm.BatchSoA.from_aos(bs)
@@ -731,23 +732,43 @@ def main():
                 L.gmb_host_free(pb)
         except Exception as ex:
             e2e["write_combined_inputs"] = {"error": repr(ex)[:200]}
-        # the bound of this number is PCIe / host memory, not the kernel: the plain pinned-copy rates of the same buffers
+        # the bound of this number is PCIe / the host's I/O fabric, not the kernel: plain pinned copies of the same buffers, ALL
+        # ranks at once (barrier before each timing), one direction at a time and both together
         try:
             dA = torch.empty((Be, n * n), dtype=torch.float32, device=dev)
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                dA.copy_(hA, non_blocking=True)
-            torch.cuda.synchronize()
-            h2d = 3 * hA.numel() * 4 / max_over_ranks(c, time.perf_counter() - t0) / 1e9
-            t0 = time.perf_counter()
-            for _ in range(3):
-                hA.copy_(dA, non_blocking=True)
-            torch.cuda.synchronize()
-            d2h = 3 * hA.numel() * 4 / max_over_ranks(c, time.perf_counter() - t0) / 1e9
-            e2e["pinned_copy_GBps_per_gpu"] = {"h2d": h2d, "d2h": d2h, "note": "slowest rank, all ranks copying at once"}
-            e2e["pcie_bound_systems_per_s"] = world * min(h2d * 1e9 / (4 * (n * n + n)), d2h * 1e9 / (4 * n + 1))
-            del dA
+            dX = torch.empty((Be, n), dtype=torch.float32, device=dev)
+            s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+            def sync_all():
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+
+            def rate(nbytes, fn):
+                sync_all()
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                return 3 * nbytes / max_over_ranks(c, time.perf_counter() - t0) / 1e9
+
+            def both():
+                with torch.cuda.stream(s_up):
+                    dA.copy_(hA, non_blocking=True)
+                with torch.cuda.stream(s_dn):
+                    hx.copy_(dX, non_blocking=True)
+
+            h2d = rate(hA.numel() * 4, lambda: dA.copy_(hA, non_blocking=True))
+            d2h = rate(hA.numel() * 4, lambda: hA.copy_(dA, non_blocking=True))
+            mixed = rate(hA.numel() * 4 + hx.numel() * 4, both)
+            e2e["pinned_copy_GBps_per_gpu"] = {"h2d_only": h2d, "d2h_only": d2h, "h2d_and_d2h_together": mixed,
+                                               "note": f"slowest rank, all {world} rank(s) copying at once"}
+            e2e["host_io_GBps_aggregate"] = {"h2d_only": h2d * world, "d2h_only": d2h * world, "together": mixed * world,
+                                             "e2e_path_moves": e2e["value"] * (4 * (n * n + 2 * n) + 1) / 1e9}
+            e2e["pcie_bound_systems_per_s"] = world * min(h2d * 1e9 / (4 * (n * n + n)), d2h * 1e9 / (4 * n + 1),
+                                                          mixed * 1e9 / (4 * (n * n + 2 * n) + 1))
+            del dA, dX
         except Exception as ex:
             e2e["pinned_copy_GBps_per_gpu"] = {"error": repr(ex)[:200]}
         del hA, hb, hx, hok

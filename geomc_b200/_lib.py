@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgeomc_b200.so")
+# GMB_LIB_PATH: an alternative build of the SAME library (tuning experiments with different compile-time constants)
+LIB_PATH = os.environ.get("GMB_LIB_PATH") or os.path.join(_HERE, "libgeomc_b200.so")
 
 LAYOUT_AOS = 0
 LAYOUT_SOA = 1
@@ -66,7 +67,7 @@ UNTYPED = ["gmb_version", "gmb_error_string", "gmb_device_count", "gmb_soa_tile_
            "gmb_checksum_bytes", "gmb_host_alloc", "gmb_host_free", "gmb_launch_count", "gmb_set_option", "gmb_set_device",
            "gmb_device_alloc", "gmb_device_free", "gmb_memcpy_h2d", "gmb_memcpy_d2h", "gmb_memset_device",
            "gmb_stream_synchronize", "gmb_get_device", "gmb_host_register", "gmb_host_unregister", "gmb_shard_range",
-           "gmb_host_alloc_wc"]
+           "gmb_host_alloc_wc", "gmb_bind_thread_near_device", "gmb_host_alloc_near"]
 EXPORTS = UNTYPED + [f"{k}_{s}" for k in _TYPED for s in ("f32", "f64")]
 
 
@@ -97,6 +98,10 @@ def lib() -> C.CDLL:
     L.gmb_checksum_bytes.argtypes = [_vp, _i64, _i64, _vp, _vp]
     L.gmb_host_alloc.restype = _vp
     L.gmb_host_alloc.argtypes = [C.c_size_t]
+    L.gmb_bind_thread_near_device.restype = _i
+    L.gmb_bind_thread_near_device.argtypes = [_i]
+    L.gmb_host_alloc_near.restype = _vp
+    L.gmb_host_alloc_near.argtypes = [C.c_size_t, _i]
     L.gmb_host_alloc_wc.restype = _vp
     L.gmb_host_alloc_wc.argtypes = [C.c_size_t]
     L.gmb_host_free.restype = None

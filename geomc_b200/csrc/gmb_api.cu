@@ -1,11 +1,13 @@
 // gmb_api.cu -- the extern "C" boundary (include/geomc_b200.h): argument checks and dispatch to
 // the register (n <= 4), sub-warp cooperative (n = 5..16) and generic kernels, plus the
 // host-buffer pipelines.  No CPU fallback anywhere: every entry point ends in a kernel launch.
+#include <cctype>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
+#include <sched.h>
 #include <vector>
 
 #include "gmb_common.cuh"
@@ -47,6 +49,7 @@ template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*
 template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int rowinv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
+template <typename T> int rowinvd(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int row_backsolve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
 // gmb_rowfast_*.cu
 template <typename T> int rowfast_solve(int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
@@ -284,6 +287,12 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
         int rc = subwarp_invd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
+    // the same deferred-rider scheme on the row-distributed decomposition for the sizes above (float n >= 11, double n >= 8)
+    if (fast && n > (sizeof(T) == 4 ? 10 : 7) && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
+        g_opt_rowinv.load(std::memory_order_relaxed) < 0) {
+        int rc = rowinvd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
     const int row_inv = g_opt_rowinv.load(std::memory_order_relaxed);
     const bool use_row_inv = row_inv >= 0 ? row_inv == 1 : n >= (sizeof(T) == 4 ? 8 : 6);
     if (fast && n >= 5 && use_row_inv) {
@@ -483,6 +492,57 @@ static int run_host_pipeline(int device, int64_t B, std::vector<HostArg>& args, 
     return rc;
 }
 
+// ------------------------------------------------------------------ NUMA placement
+// A box with several GPUs has several host memory nodes; a pinned buffer that lives on the far node reaches its GPU over the
+// inter-socket link, and all of a process's buffers on ONE node make that node's memory feed every PCIe link of the box.  The
+// kernel exposes the CPUs next to a PCI device in sysfs; a thread that runs there allocates (first touch) and drives copies
+// locally.  Returns false when the topology cannot be read (single-node boxes, containers without sysfs): nothing is changed.
+static bool cpus_near_device(int device, cpu_set_t* set) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    for (char* c = bus; *c; ++c) *c = (char)std::tolower((unsigned char)*c);
+    char path[128];
+    std::snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = std::fopen(path, "r");
+    if (!f) return false;
+    char line[4096] = {0};
+    const bool got = std::fgets(line, sizeof(line), f) != nullptr;
+    std::fclose(f);
+    if (!got) return false;
+    CPU_ZERO(set);
+    int count = 0;
+    for (char* tok = std::strtok(line, ",\n"); tok; tok = std::strtok(nullptr, ",\n")) {
+        int lo = 0, hi = 0;
+        const int k = std::sscanf(tok, "%d-%d", &lo, &hi);
+        if (k < 1) continue;
+        if (k == 1) hi = lo;
+        for (int c = lo; c <= hi && c < CPU_SETSIZE; ++c) {
+            CPU_SET(c, set);
+            ++count;
+        }
+    }
+    // keep only CPUs this process may use at all (cgroup / taskset limits)
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        int usable = 0;
+        for (int c = 0; c < CPU_SETSIZE; ++c) {
+            if (CPU_ISSET(c, set) && !CPU_ISSET(c, &allowed)) CPU_CLR(c, set);
+            if (CPU_ISSET(c, set)) ++usable;
+        }
+        count = usable;
+    }
+    return count > 0;
+}
+
+static int bind_thread_near_device(int device) {
+    cpu_set_t set;
+    if (!cpus_near_device(device, &set)) return 0;
+    return sched_setaffinity(0, sizeof(set), &set) == 0 ? 1 : 0;
+}
+
 // ------------------------------------------------------------------ several devices of one box
 // Independent systems: device k of `ndev` serves the contiguous shard shard_range(B, k, ndev, 1024) through its own
 // host pipeline on its own host thread.  No collective, no peer traffic; the shards of the host arrays are disjoint.
@@ -514,7 +574,10 @@ static int run_multi_device(int64_t B, const int* devices, int ndev, Shard&& sha
         if (ndev == 1) {
             rcs[0] = shard(lo, hi, devices[0]);
         } else {
-            workers.emplace_back([&, k, lo, hi] { rcs[(size_t)k] = shard(lo, hi, devices[k]); });
+            workers.emplace_back([&, k, lo, hi] {
+                bind_thread_near_device(devices[k]);         // the copy-issuing thread runs next to its GPU
+                rcs[(size_t)k] = shard(lo, hi, devices[k]);
+            });
         }
     }
     for (auto& w : workers) w.join();
@@ -686,6 +749,27 @@ void gmb_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int gmb_bind_thread_near_device(int device) {
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || device < 0 || device >= have) {
+        cudaGetLastError();
+        return GMB_ERR_INVALID_ARG;
+    }
+    return bind_thread_near_device(device);
+}
+void* gmb_host_alloc_near(size_t bytes, int device) {
+    cpu_set_t before;
+    const bool have_before = sched_getaffinity(0, sizeof(before), &before) == 0;
+    const int bound = bind_thread_near_device(device);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        p = nullptr;
+    }
+    if (p) std::memset(p, 0, bytes);                         // first touch on the device's memory node
+    if (bound == 1 && have_before) sched_setaffinity(0, sizeof(before), &before);
+    return p;
+}
 int gmb_host_register(void* p, size_t bytes) {
     if (!p || bytes == 0) return GMB_ERR_INVALID_ARG;
     const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);

@@ -33,7 +33,13 @@ constexpr int kSubThreads = 128;
 #ifndef GMB_SUB_MIN_BLOCKS
 #define GMB_SUB_MIN_BLOCKS 3      // cap at 128 registers: occupancy matters more than a few spills here (ncu: 12% -> 25%)
 #endif
-constexpr int kRegBudgetWords = 100;      // register words for the local block
+#ifndef GMB_SUB_REG_BUDGET
+#define GMB_SUB_REG_BUDGET 100            // register words for the local block (picks G)
+#endif
+#ifndef GMB_SUB_REG_BUDGET_XC0
+#define GMB_SUB_REG_BUDGET_XC0 GMB_SUB_REG_BUDGET   // ... when no rider columns are carried (decomposition, deferred-rider inverse)
+#endif
+constexpr int kRegBudgetWords = GMB_SUB_REG_BUDGET;
 
 constexpr int MODE_SOLVE = 0;   // A, Bm -> X, ok (, LU)
 constexpr int MODE_DECOMP = 1;  // A in place, perm, parity, degenerate
@@ -57,7 +63,7 @@ constexpr bool sub_stage_in(int n, int mode, bool soa) {
 constexpr bool sub_stage_out(int mode, bool soa) { return !soa && mode != MODE_SOLVE; }
 constexpr int sub_group(int n, int xc, int words) {
     for (int g = 1; g <= 16; g *= 2)
-        if (n * sub_lc(n, xc, g) * words <= kRegBudgetWords) return g;
+        if (n * sub_lc(n, xc, g) * words <= (xc == 0 ? GMB_SUB_REG_BUDGET_XC0 : kRegBudgetWords)) return g;
     return 16;
 }
 

@@ -272,6 +272,13 @@ void* gmb_host_alloc(size_t bytes);
 /* Write-combined pinned memory for INPUT batches the host only writes (fills) and the GPU only reads: the DMA engine
  * does not have to snoop the CPU caches.  Reading it back on the CPU is slow; free with gmb_host_free. */
 void* gmb_host_alloc_wc(size_t bytes);
+/* NUMA placement on boxes with several host memory nodes.  gmb_bind_thread_near_device pins the CALLING thread to the CPUs the
+ * kernel lists as local to `device` (sysfs local_cpulist of its PCI function): memory it allocates and touches afterwards
+ * lives on that node, and the copies it issues start there.  Returns 1 when bound, 0 when the topology is not readable
+ * (nothing changed), < 0 for a bad device.  gmb_host_alloc_near = bind, pinned allocation, first touch, restore the
+ * caller's affinity.  The worker threads of the gmb_host_*_multi_* entry points bind themselves the same way. */
+int gmb_bind_thread_near_device(int device);
+void* gmb_host_alloc_near(size_t bytes, int device);
 void gmb_host_free(void* p);
 /* Pin / unpin memory the application already owns (an array of SimpleMatrix objects, a std::vector's storage) so that
  * the host entry points reach full PCIe bandwidth on it without a copy into a pinned staging buffer.  Returns a

@@ -203,16 +203,15 @@ def test_multi_rhs_solve_takes_the_subwarp_kernel(gm, orc, n, dt, soa):
 
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10])
+@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10, 11, 12, 13, 16])
 def test_deferred_rider_inverse_is_the_reference_inverse(gm, orc, n, dt, soa):
     """k_sub_plu MODE_INVD (one lane per system, the identity is NOT carried through the elimination; the columns of the
     inverse are produced in i-space and stored at their permuted positions) against the kernels that carry the riders
     (option invd = 0) and against the reference, on a hostile 2^17 batch: singular systems (destination untouched), ties,
     NaN / Inf (dense forward sweep inside the kernel), huge / tiny scalings (IEEE-division redo), all four layout pairs."""
-    if dt == np.float64 and n > 7:
-        pytest.skip("double: n <= 7 (registers)")
+    # one lane per system (k_sub_plu MODE_INVD) up to float n = 10 / double n = 7, rows over G lanes (row_solve_one INVD) above
     rng = np.random.default_rng(5000 * n + np.dtype(dt).itemsize + int(soa))
-    B = (1 << 17) + 33
+    B = ((1 << 17) if n <= 10 else (1 << 15)) + 33
     A, _ = hostile_batch(rng, B, n, dt, every=37)
     dA = up(gm, A, soa)
     try:
