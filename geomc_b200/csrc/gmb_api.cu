@@ -287,8 +287,8 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
         int rc = subwarp_invd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
-    // the same deferred-rider scheme on the row-distributed decomposition for the sizes above (float n >= 11, double n >= 8)
-    if (fast && n > (sizeof(T) == 4 ? 10 : 7) && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
+    // the same deferred-rider scheme on the row-distributed decomposition: measured for every larger size, wins for float n = 11
+    if (fast && sizeof(T) == 4 && n == 11 && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
         g_opt_rowinv.load(std::memory_order_relaxed) < 0) {
         int rc = rowinvd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;

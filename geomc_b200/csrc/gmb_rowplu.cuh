@@ -522,15 +522,18 @@ int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* 
     return rc;
 }
 
-// Deferred-rider inverse on the row-distributed decomposition (row_solve_one, INVD): the sizes the one-lane-per-system
-// form (k_sub_plu MODE_INVD) does not reach.  `a_rm` as in the other inverse kernels: the working copy has the
-// destination's layout and is treated as row-major.
-template <typename T, int NMIN>
+// Deferred-rider inverse on the row-distributed decomposition (row_solve_one, INVD): beyond the sizes of the
+// one-lane-per-system form (k_sub_plu MODE_INVD).  `a_rm` as in the other inverse kernels: the working copy has the
+// destination's layout and is treated as row-major.  Measured for float n = 11..16 and double n = 8..16
+// (profiles/r2j_row_invd.md): bit-identical everywhere, but faster than k_row_inv only for float n = 11 (0.24 / 0.28 of
+// the HBM peak against 0.15 / 0.22) -- the bounce-buffer decomposition it rides on runs at 200+ registers and two lanes
+// per system -- so only the sizes in [NMIN, NMAX] are instantiated.
+template <typename T, int NMIN, int NMAX>
 int rowinvd_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm, cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     const bool a_rm = (src_rm != 0) == (dst_rm != 0);
     dispatch_int<8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
-        if constexpr (N.value >= NMIN) {
+        if constexpr (N.value >= NMIN && N.value <= NMAX) {
             constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
             const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
             if (grid == 0) {

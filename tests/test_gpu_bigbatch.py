@@ -203,13 +203,15 @@ def test_multi_rhs_solve_takes_the_subwarp_kernel(gm, orc, n, dt, soa):
 
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10, 11, 12, 13, 16])
+@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10, 11])
 def test_deferred_rider_inverse_is_the_reference_inverse(gm, orc, n, dt, soa):
     """k_sub_plu MODE_INVD (one lane per system, the identity is NOT carried through the elimination; the columns of the
     inverse are produced in i-space and stored at their permuted positions) against the kernels that carry the riders
     (option invd = 0) and against the reference, on a hostile 2^17 batch: singular systems (destination untouched), ties,
     NaN / Inf (dense forward sweep inside the kernel), huge / tiny scalings (IEEE-division redo), all four layout pairs."""
-    # one lane per system (k_sub_plu MODE_INVD) up to float n = 10 / double n = 7, rows over G lanes (row_solve_one INVD) above
+    # one lane per system (k_sub_plu MODE_INVD) up to float n = 10 / double n = 7, rows over G lanes (row_solve_one INVD) for float
+    # n = 11 (the other sizes of that form were bit-exact too and slower than k_row_inv: profiles/r2j_row_invd.md); where no
+    # deferred-rider kernel exists both arms run the same kernel and the comparison with the reference is what counts
     rng = np.random.default_rng(5000 * n + np.dtype(dt).itemsize + int(soa))
     B = ((1 << 17) if n <= 10 else (1 << 15)) + 33
     A, _ = hostile_batch(rng, B, n, dt, every=37)
@@ -234,3 +236,37 @@ def test_deferred_rider_inverse_is_the_reference_inverse(gm, orc, n, dt, soa):
                 assert bits_equal(o1[:S], oe), f"inverse vs {orc.kind} {tag}: {first_diff(o1[:S], oe)}"
     finally:
         gm.set_option("invd", -1)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_million_system_differential_register_kernels(gm, orc, n, dt):
+    """2^20 systems through the register kernels (n <= 4: the metric kernel's family) against the compiled reference, with the
+    hostile structures AND row / element scalings far outside the normal exponent range -- the once-per-10^7 cases of the IEEE
+    division slow path: fused solve, decomposition, inverse, SoA container."""
+    rng = np.random.default_rng(7000 + 10 * n + np.dtype(dt).itemsize)
+    B = 1 << 20
+    A, b = hostile_batch(rng, B, n, dt, every=53)
+    kmax = 60 if dt == np.float32 else 480
+    with np.errstate(all="ignore"):
+        scale = np.ldexp(1.0, rng.integers(-kmax, kmax + 1, size=(B, n, 1)))
+        scale[::2] = 1.0
+        A = (A.reshape(B, n, n).astype(np.float64) * scale).astype(dt).reshape(B, n * n)
+        sub = rng.integers(0, B, size=B // 64)
+        A[sub, 0] = np.ldexp(A[sub, 0].astype(np.float64), -(140 if dt == np.float32 else 1040)).astype(dt)   # subnormal / underflowing entries
+    dA, db = up(gm, A, True), up(gm, b, True)
+    with np.errstate(all="ignore"):
+        x, ok = gm.linear_solve(dA, db, n)
+        _, xe, oke = orc.linear_solve(A, b, n)
+        assert bits_equal(down(ok), oke), f"ok n={n}: {first_diff(down(ok), oke)}"
+        assert bits_equal(down(x), xe), f"x n={n}: {first_diff(down(x), xe)}"
+        lu, p, par, dg = gm.decomp_plu(dA, n)
+        e = orc.decomp_plu(A, n)
+        assert bits_equal(down(lu), e[0]), f"lu n={n}: {first_diff(down(lu), e[0])}"
+        assert bits_equal(down(p).astype(np.int64), e[1]) and bits_equal(down(par), e[2])
+        assert bits_equal(down(dg).astype(np.int64), e[3])
+        init = np.full_like(A, 7)
+        out, oki = gm.inv(dA, n, out=up(gm, init, True))
+        ie, ike = orc.inv(A, n, True, True, init)
+        assert bits_equal(down(oki), ike), f"inv ok n={n}"
+        assert bits_equal(down(out), ie), f"inv n={n}: {first_diff(down(out), ie)}"
