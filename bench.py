@@ -344,10 +344,11 @@ def config_c1_small(c, steps=24):
     ms = timed(c, fn, steps, 4)
     total = max_over_ranks(c, sum(ms))
     nv, bad = verify_solve_sample(c, sets[(k[0] - 1) % 4][0], sets[(k[0] - 1) % 4][1], xs[(k[0] - 1) % 4], ok, 4, B, t.float32)
-    return row(c, "C1 literal: 4x4 f32 PLU solve, 2^20 systems per launch, 24 launches rotating over 4 buffer sets (384 MB > L2), SoA",
-               "C1s", B, total, steps, 96,
-               {"median_launch_ms": statistics.median(ms), "best_launch_ms": min(ms), "verified_systems": int(sum_over_ranks(c, nv)),
-                "mismatches": int(sum_over_ranks(c, bad)), "oracle": oracle(c).kind})
+    r1 = row(c, "C1 literal: 4x4 f32 PLU solve, 2^20 systems per launch, 24 launches rotating over 4 buffer sets (384 MB > L2), SoA, one stream",
+             "C1s", B, total, steps, 96,
+             {"median_launch_ms": statistics.median(ms), "best_launch_ms": min(ms), "verified_systems": int(sum_over_ranks(c, nv)),
+              "mismatches": int(sum_over_ranks(c, bad)), "oracle": oracle(c).kind})
+    return [r1]
 
 
 # ---------------------------------------------------------------------------------------- C2

@@ -143,7 +143,9 @@ constexpr int sub_lane_emax(int n, int xc) { return n * (n > xc ? n : xc); }
 // (:152) sit in ROW i of the view (one per column, computed by the lane that owns the column, pivot broadcast with one
 // shuffle) and the unscaled M(i,c) (:157) is COLUMN i of the view, broadcast from its owner with n-1-i shuffles --
 // the same number of shuffles as decomp_plu, with the roles of the two factors exchanged.
-template <typename T, int N, int XC, int MODE, bool SOA, bool A_RM, bool X_RM, bool COLPIV = false>
+// NO_L = true (one lane per system, fused solve, no LU output asked for): nobody reads the multipliers afterwards, so they
+// are neither stored nor exchanged -- only columns >= i of a row travel (a quarter of the exchange's selects for n = 7).
+template <typename T, int N, int XC, int MODE, bool SOA, bool A_RM, bool X_RM, bool COLPIV = false, bool NO_L = false>
 __global__ void __launch_bounds__(kSubThreads, GMB_SUB_MIN_BLOCKS)
 k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ perm_out,
           uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B) {
@@ -236,6 +238,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     bool parity = false;
 
     // ---- elimination ----------------------------------------------------------------------
+    static_assert(!NO_L || (MODE == MODE_SOLVE && G == 1), "NO_L: fused solve, one lane per system");
 #pragma unroll
     for (int i = 0; i < N - 1; ++i) {
         if (MODE == MODE_RECT && i >= skip - 1) break;       // rectangular: min(rows, cols) - 1 steps (warp-uniform)
@@ -250,24 +253,36 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
             gt[p] = v > biggest;
             biggest = gt[p] ? v : biggest;
         }
-        unsigned info = 0;
+        // one-hot "row p is the pivot row" flags: the LAST strict improvement of the scan wins (= first strict maximum)
+        bool swp[N];
         bool later = false;
 #pragma unroll
         for (int p = N - 1; p > i; --p) {
-            info |= (gt[p] && !later) ? (1u << p) : 0u;
+            swp[p] = gt[p] && !later;
             later = later || gt[p];
         }
-        info |= (biggest == (T)0) ? 0x80000000u : 0u;
-        info = shfl_u<G>(info, owner);
-        const bool dead = (info & 0x80000000u) != 0;
+        bool dead = biggest == (T)0;
+        if constexpr (G > 1) {
+            // the owner's flags travel as ONE word (a mask, not an index, so the exchange below stays in registers)
+            unsigned info = 0;
+#pragma unroll
+            for (int p = N - 1; p > i; --p) info |= swp[p] ? (1u << p) : 0u;
+            info |= dead ? 0x80000000u : 0u;
+            info = shfl_u<G>(info, owner);
+            dead = (info & 0x80000000u) != 0;
+            later = (info & 0x7fffffffu) != 0;
+#pragma unroll
+            for (int p = i + 1; p < N; ++p) swp[p] = ((info >> p) & 1u) != 0;
+        }
         degenerate += dead ? 1 : 0;
-        parity = parity != ((info & 0x7fffffffu) != 0);
-        // exchange rows i <-> pvt in the local columns
+        parity = parity != later;
+        // exchange rows i <-> pvt in the local columns (NO_L: columns < i hold dead multipliers and stay where they are)
+        const int JDEAD = NO_L ? i : 0;                        // first local column that must travel (static after unrolling)
 #pragma unroll
         for (int p = i + 1; p < N; ++p) {
-            const bool sw = ((info >> p) & 1u) != 0;
+            const bool sw = swp[p];
 #pragma unroll
-            for (int j = 0; j < LC; ++j) {
+            for (int j = JDEAD; j < LC; ++j) {
                 const T t = a[i][j];
                 a[i][j] = sw ? a[p][j] : t;
                 a[p][j] = sw ? t : a[p][j];
@@ -339,7 +354,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
         for (int r = i + 1; r < N; ++r) {
             T b = shfl_t<G>(bq[r], owner);
             const bool upd = !dead && (b != (T)0);
-            if (mine) a[r][k] = dead ? a[r][k] : b;             // L(r,i)
+            if (mine && !NO_L) a[r][k] = dead ? a[r][k] : b;    // L(r,i)
 #pragma unroll
             for (int j = 0; j < LC; ++j) {
                 if ((G - 1) * LC + j > i) {                       // static: some lane's column at j is right of i
@@ -664,7 +679,9 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
             // riders: linear_solve uses the matrix' own layout flag; invNxN always writes row-major
             constexpr bool XRM = (MODE == MODE_INV || MODE == MODE_INVD) ? true : ARM.value;
             (void)x_rm;
-            auto kern = k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM, COLPIV>;
+            constexpr bool CAN_NO_L = (G == 1) && (MODE == MODE_SOLVE) && !COLPIV;
+            auto kern = (CAN_NO_L && LU == nullptr) ? k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM, COLPIV, CAN_NO_L>
+                                                    : k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM, COLPIV, false>;
             // AoS: one staging buffer of 32/G systems per warp (dynamic shared memory)
             const size_t smem = (G == 1 && (!SOA.value || MODE == MODE_INVD))
                                     ? (size_t)(kSubThreads / 32) * 32 * (sub_lane_emax(N, XC) + 1) * sizeof(T)
@@ -672,8 +689,8 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
                                     ? 0
                                     : (size_t)(kSubThreads / 32) * (32 / G) * stage_stride<N * N>() * sizeof(T);
             if (smem > 48 * 1024) {
-                static std::atomic<uint64_t> raised{0};   // per instantiation, one bit per device
-                raise_dyn_smem(kern, smem, raised);
+                static std::atomic<uint64_t> raised[2];   // per instantiation (with / without the L part), one bit per device
+                raise_dyn_smem(kern, smem, raised[(CAN_NO_L && LU == nullptr) ? 1 : 0]);
             }
             kern<<<grid, kSubThreads, smem, st>>>(A, Bm, X, LU, ok, perm, parity, degen, skip, B);
         });
