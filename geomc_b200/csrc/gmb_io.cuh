@@ -259,6 +259,47 @@ __device__ __forceinline__ void aos_load_staged(const T* __restrict__ base, int6
     __syncwarp();                                            // the buffer may be reused right away
 }
 
+// The same ingest in two halves, with the global -> shared copy done by cp.async (LDGSTS: no register staging, and the copies
+// of SEVERAL record arrays -- matrix and right-hand sides -- are all in flight before anybody waits: one DRAM latency instead of
+// one per array).  aos_stage_issue for every array, then cp_async_wait_all_() + __syncwarp(), then aos_stage_read for each.
+template <typename T, int E>
+__device__ __forceinline__ void aos_stage_issue(const T* __restrict__ base, int64_t s_warp0, int lane, unsigned char* sm) {
+    constexpr int R = E * (int)sizeof(T);
+    using Cfg = StageCfg<R>;
+    const uint4* g = reinterpret_cast<const uint4*>(base + s_warp0 * (int64_t)E);
+    constexpr int NCH = 2 * R;                               // 32 * R / 16
+#pragma unroll
+    for (int c0 = 0; c0 < NCH; c0 += 32) {
+        const int c = c0 + lane;
+        if (NCH % 32 == 0 || c < NCH) {
+            int pos = c;
+            if constexpr (Cfg::swz) pos = Cfg::chunk(c / Cfg::CH, c % Cfg::CH);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + pos * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + c) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <typename T, int E>
+__device__ __forceinline__ void aos_stage_read(int lane, T (&q)[E], const unsigned char* sm) {
+    constexpr int R = E * (int)sizeof(T);
+    using Cfg = StageCfg<R>;
+    if constexpr (Cfg::vec16) {
+        using VT = typename VecOf<T>::type;
+        constexpr int V = soa_v<T>();
+#pragma unroll
+        for (int j = 0; j < Cfg::CH; ++j) {
+            T t[V];
+            unpack(*reinterpret_cast<const VT*>(sm + Cfg::chunk(lane, j) * 16), t);
+#pragma unroll
+            for (int v = 0; v < V; ++v) q[j * V + v] = t[v];
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; ++e) q[e] = *reinterpret_cast<const T*>(sm + lane * R + e * (int)sizeof(T));
+    }
+}
+
 template <typename T, int E>
 __device__ __forceinline__ void aos_store_staged(T* __restrict__ base, int64_t s_warp0, int lane, const T (&q)[E],
                                                  unsigned char* sm = stage_buffer<T, E>()) {

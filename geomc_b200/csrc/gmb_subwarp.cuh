@@ -118,8 +118,9 @@ __device__ __forceinline__ void sub_lane_store(T* __restrict__ base, int64_t s, 
         aos_store<T, E>(base, s, q);
     }
 }
-// elements of the largest record a G == 1 AoS kernel moves (matrix, or the rider block)
-constexpr int sub_lane_emax(int n, int xc) { return n * (n > xc ? n : xc); }
+// elements per system of a G == 1 AoS kernel's staging buffer: the matrix and the rider block side by side (both are in
+// flight at once), never less than n*n + 1 (the deferred-rider inverse uses the buffer as an odd-stride scratch)
+constexpr int sub_lane_emax(int n, int xc, int mode) { return n * n + (mode == 0 /* MODE_SOLVE */ ? n * xc : 0); }
 
 // MODE_RECT (XC = 0, G = 1): orthogonal (Orthogonal.h:73-98) and nullspace (:136-178).  Both run the RECTANGULAR row-pivot
 // decomposition of the nb x N matrix whose rows are the given vectors (nb = `skip`, a run-time value, nb < N) and then a
@@ -178,7 +179,7 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     const bool stage = (STAGE_IN || STAGE_OUT) && (s_warp0 + NSYS <= B);   // warp-uniform
     const int64_t s_raw = (int64_t)blockIdx.x * kSubThreads + threadIdx.x; // LANE_IO: this thread's system before clamping
     const bool lane_full = LANE_IO && (s_warp0 + 32 <= B);                 // warp-uniform
-    unsigned char* lane_sm = gmb_dyn_smem + (size_t)(threadIdx.x >> 5) * (32 * (sub_lane_emax(N, XC) + 1) * sizeof(T));
+    unsigned char* lane_sm = gmb_dyn_smem + (size_t)(threadIdx.x >> 5) * (32 * (sub_lane_emax(N, XC, MODE) + 1) * sizeof(T));
     const T* sms = smw + ((threadIdx.x & 31) / G) * SA + (A_RM ? c0 : N * c0);   // this lane's system, first local column
     if (STAGE_IN && stage) warp_stage_in<T, N * N, NSYS>(A + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
 
@@ -194,14 +195,28 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
             for (int c = 0; c < N; ++c) a[r][c] = (r < nb) ? A[baseV + (int64_t)(N * r + c) * ST] : (T)0;
     } else if constexpr (LANE_IO) {
         T qa[N * N];
-        sub_lane_load<T, N * N>(A, s_raw, threadIdx.x & 31, lane_full, valid, qa, lane_sm);
+        T qb[MODE == MODE_SOLVE ? N * XC : 1];
+        constexpr bool STAGE_B = MODE == MODE_SOLVE && StageCfg<N * XC * (int)sizeof(T)>::use;
+        const int lane = threadIdx.x & 31;
+        if (lane_full) {
+            // matrix and right-hand sides: every global -> shared copy is issued (cp.async) before anybody waits
+            aos_stage_issue<T, N * N>(A, s_warp0, lane, lane_sm);
+            if constexpr (STAGE_B) aos_stage_issue<T, N * XC>(Bm, s_warp0, lane, lane_sm + 32 * N * N * sizeof(T));
+            if constexpr (MODE == MODE_SOLVE && !STAGE_B) aos_load<T, N * XC>(Bm, s_raw, qb);     // records under 32 bytes: direct
+            cp_async_wait_all_();
+            __syncwarp();
+            aos_stage_read<T, N * N>(lane, qa, lane_sm);
+            if constexpr (STAGE_B) aos_stage_read<T, N * XC>(lane, qb, lane_sm + 32 * N * N * sizeof(T));
+            __syncwarp();                                      // the buffer is reused by the staged stores
+        } else {
+            sub_lane_load<T, N * N>(A, s_raw, lane, false, valid, qa, lane_sm);
+            if constexpr (MODE == MODE_SOLVE) sub_lane_load<T, N * XC>(Bm, s_raw, lane, false, valid, qb, lane_sm);
+        }
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
             for (int c = 0; c < N; ++c) a[r][c] = qa[A_RM ? N * r + c : N * c + r];
         if constexpr (MODE == MODE_SOLVE) {
-            T qb[N * XC];
-            sub_lane_load<T, N * XC>(Bm, s_raw, threadIdx.x & 31, lane_full, valid, qb, lane_sm);
 #pragma unroll
             for (int r = 0; r < N; ++r)
 #pragma unroll
@@ -684,7 +699,7 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
                                                     : k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM, COLPIV, false>;
             // AoS: one staging buffer of 32/G systems per warp (dynamic shared memory)
             const size_t smem = (G == 1 && (!SOA.value || MODE == MODE_INVD))
-                                    ? (size_t)(kSubThreads / 32) * 32 * (sub_lane_emax(N, XC) + 1) * sizeof(T)
+                                    ? (size_t)(kSubThreads / 32) * 32 * (sub_lane_emax(N, XC, MODE) + 1) * sizeof(T)
                                 : !(sub_stage_in<T>(N, MODE, SOA.value) || sub_stage_out(MODE, SOA.value))
                                     ? 0
                                     : (size_t)(kSubThreads / 32) * (32 / G) * stage_stride<N * N>() * sizeof(T);

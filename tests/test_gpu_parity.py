@@ -382,6 +382,42 @@ def test_multi_device_host_entry_points(gm, orc):
         gm.host_linear_solve(A, b, x, ok, n, device=[ndev])
 
 
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("n", [5, 6, 8, 9, 12, 13, 16])
+def test_double_pivots_near_dbl_max(gm, orc, n, soa):
+    """RcpOf<double> (gmb_math.cuh): the reciprocal of a divisor beyond 2^1022 is subnormal and rcp.approx.ftz flushes it -- such
+    pivots must take the IEEE division (nvcc's own in-line __ddiv_rn sends |b| >= 2^1017 to its subroutine too).  Matrices whose
+    entries sit in [2^1015, DBL_MAX), so that pivots and diagonal entries do, with right-hand sides of every magnitude: every
+    kernel family that shares a reciprocal per pivot, against the reference."""
+    rng = np.random.default_rng(900 + n)
+    B = 2049
+    with np.errstate(all="ignore"):
+        A = np.ldexp(rng.uniform(0.5, 1.0, (B, n * n)) * rng.choice([-1.0, 1.0], (B, n * n)), rng.integers(1016, 1025, (B, n * n)))
+        A[::3] = np.ldexp(A[::3], -rng.integers(0, 40, (A[::3].shape[0], 1)))          # some systems a little lower
+        A = A.astype(np.float64)
+        b = np.ldexp(rng.standard_normal((B, n)), rng.integers(-300, 1000, (B, n))).astype(np.float64)
+        assert np.isfinite(A).all() and np.isfinite(b).all()
+        dA, db = up(gm, A, soa), up(gm, b, soa)
+        x, ok = gm.linear_solve(dA, db, n)
+        _, xe, oke = orc.linear_solve(A, b, n)
+        check(down(ok), oke, f"ok n={n}")
+        check(down(x), xe, f"linear_solve with pivots near DBL_MAX n={n} soa={soa}")
+        lu, p, par, dg = gm.decomp_plu(dA, n)
+        e = orc.decomp_plu(A, n)
+        check(down(lu), e[0], f"decomp_plu near DBL_MAX n={n}")
+        check(down(p).astype(np.int64), e[1], "perm")
+        init = np.full_like(A, 7)
+        out, oki = gm.inv(dA, n, out=up(gm, init, soa))
+        ie, ike = orc.inv(A, n, True, True, init)
+        check(down(oki), ike, f"inv ok n={n}")
+        check(down(out), ie, f"inv near DBL_MAX n={n}")
+        lu2, p2, _, _ = gm.decomp_lup(dA, n)
+        e2 = orc.decomp_lup(A, n)
+        check(down(lu2), e2[0], f"decomp_lup near DBL_MAX n={n}")
+        xb = gm.backsolve_plu(lu, p, db, n)
+        check(down(xb), orc.backsolve_plu(e[0], e[1], b, n), f"backsolve_plu near DBL_MAX n={n}")
+
+
 @pytest.mark.parametrize("n", [3, 6, 8, 13])
 def test_cholesky_solve_against_a_long_double_host_solve(gm, n):
     """cholesky_solve has no counterpart in the reference (PARITY UNPINNED: the definition is this framework's, oracle.c
@@ -402,7 +438,6 @@ def test_cholesky_solve_against_a_long_double_host_solve(gm, n):
     rel = (res / scale).max()
     assert rel <= 1e-12, f"relative residual {rel} (n={n})"
     # and the long-double solution itself: forward / backward substitution on the long-double Cholesky factor
-    L = np.linalg.cholesky(S.reshape(B, n, n))                      # float64 LAPACK factor, refined below only through the residual
     y = np.linalg.solve(S.reshape(B, n, n), b[..., None])[..., 0]
     cond = np.linalg.cond(S.reshape(B, n, n))
     err = np.abs(y - x).max(axis=1) / np.abs(y).max(axis=1)
