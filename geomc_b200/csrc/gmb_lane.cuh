@@ -107,9 +107,15 @@ k_lane_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_ou
     const bool valid = s < B;
     const bool full = (s - lane) + 32 <= B;
 
+    // AoS: matrix and right-hand sides enter through ONE staging buffer side by side when that fits the static shared-memory
+    // limit (both cp.async copies in flight before anybody waits), else one after the other
+    constexpr bool STAGE_B = SOLVE && StageCfg<N * M * (int)sizeof(T)>::use;
+    constexpr bool OVERLAP = !SOA && (size_t)(N * N + (STAGE_B ? N * M : 0)) * 32 * sizeof(T) * (kLaneThreads / 32) <= 48 * 1024;
+    constexpr int EBUF = OVERLAP ? N * N + (STAGE_B ? N * M : 0) : (N > M ? N * N : N * M);
     unsigned char* sm = nullptr;
-    if constexpr (!SOA) sm = lane_stage_buffer<T, (N > M ? N * N : N * M)>();
+    if constexpr (!SOA) sm = lane_stage_buffer<T, EBUF>();
     T a[N][N];
+    T x[N][M];
     if constexpr (SOA) {
         // the container gives element planes: the strict upper triangle is never read (Cholesky.h:42-44)
         constexpr int W = soa_w<T>();
@@ -118,22 +124,40 @@ k_lane_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_ou
         for (int r = 0; r < N; ++r)
 #pragma unroll
             for (int c = 0; c < N; ++c) a[r][c] = (c <= r && valid) ? __ldg(p + (RM ? N * r + c : N * c + r) * W) : (T)0;
+        if constexpr (SOLVE) {
+            T qb[N * M];
+            lane_load<T, N * M, SOA>(Bm, s, lane, full, valid, qb, sm);
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < M; ++j) x[r][j] = qb[RM ? M * r + j : N * j + r];
+        }
     } else {
         T qa[N * N];
-        lane_load<T, N * N, false>(A, s, lane, full, valid, qa, sm);
+        T qb[SOLVE ? N * M : 1];
+        if (OVERLAP && full) {
+            aos_stage_issue<T, N * N>(A, s - lane, lane, sm);
+            if constexpr (STAGE_B) aos_stage_issue<T, N * M>(Bm, s - lane, lane, sm + 32 * N * N * sizeof(T));
+            if constexpr (SOLVE && !STAGE_B) aos_load<T, N * M>(Bm, s, qb);
+            cp_async_wait_all_();
+            __syncwarp();
+            aos_stage_read<T, N * N>(lane, qa, sm);
+            if constexpr (STAGE_B) aos_stage_read<T, N * M>(lane, qb, sm + 32 * N * N * sizeof(T));
+            __syncwarp();
+        } else {
+            lane_load<T, N * N, false>(A, s, lane, full, valid, qa, sm);
+            if constexpr (SOLVE) lane_load<T, N * M, false>(Bm, s, lane, full, valid, qb, sm);
+        }
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
             for (int c = 0; c < N; ++c) a[r][c] = qa[RM ? N * r + c : N * c + r];
-    }
-    T x[N][M];
-    if constexpr (SOLVE) {
-        T qb[N * M];
-        lane_load<T, N * M, SOA>(Bm, s, lane, full, valid, qb, sm);
+        if constexpr (SOLVE) {
 #pragma unroll
-        for (int r = 0; r < N; ++r)
+            for (int r = 0; r < N; ++r)
 #pragma unroll
-            for (int j = 0; j < M; ++j) x[r][j] = qb[RM ? M * r + j : N * j + r];
+                for (int j = 0; j < M; ++j) x[r][j] = qb[RM ? M * r + j : N * j + r];
+        }
     }
 
     bool ok = true;

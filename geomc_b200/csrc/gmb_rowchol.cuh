@@ -45,33 +45,33 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
     // multiples of 16 bytes (n = 5, 6, 7, 9, ...) used to be read with scalar loads at a stride of one record.
     constexpr bool LANE_IO = (G == 1) && !SOA;
     extern __shared__ __align__(16) unsigned char gmb_dyn_smem[];
-    unsigned char* lane_sm = gmb_dyn_smem + (size_t)(threadIdx.x >> 5) * (32 * N * N * sizeof(T));
+    unsigned char* lane_sm = gmb_dyn_smem + (size_t)(threadIdx.x >> 5) * (32 * (N * N + N) * sizeof(T));
     const int64_t s_raw = (int64_t)blockIdx.x * kRowThreads + threadIdx.x;
     const bool lane_full = LANE_IO && ((s_raw - (threadIdx.x & 31)) + 32 <= B);
     if constexpr (LANE_IO) {
         T qa[N * N];
-        if (StageCfg<N * N * (int)sizeof(T)>::use && lane_full) {
-            aos_load_staged<T, N * N>(A, s_raw - (threadIdx.x & 31), threadIdx.x & 31, qa, lane_sm);
+        T qb[N];
+        constexpr bool STAGE_B = SOLVE && StageCfg<N * (int)sizeof(T)>::use;
+        if (lane_full) {
+            // matrix and right-hand side: both cp.async copies are in flight before anybody waits
+            aos_stage_issue<T, N * N>(A, s_raw - (threadIdx.x & 31), threadIdx.x & 31, lane_sm);
+            if constexpr (STAGE_B) aos_stage_issue<T, N>(Bm, s_raw - (threadIdx.x & 31), threadIdx.x & 31, lane_sm + 32 * N * N * sizeof(T));
+            if constexpr (SOLVE && !STAGE_B) aos_load<T, N>(Bm, s, qb);
+            cp_async_wait_all_();
+            __syncwarp();
+            aos_stage_read<T, N * N>(threadIdx.x & 31, qa, lane_sm);
+            if constexpr (STAGE_B) aos_stage_read<T, N>(threadIdx.x & 31, qb, lane_sm + 32 * N * N * sizeof(T));
+            __syncwarp();
         } else {
             aos_load<T, N * N>(A, s, qa);
+            if (SOLVE) aos_load<T, N>(Bm, s, qb);
         }
 #pragma unroll
         for (int r = 0; r < N; ++r)
 #pragma unroll
             for (int c = 0; c < N; ++c) a[r][c] = (c <= r) ? qa[RM ? N * r + c : N * c + r] : (T)0;
-        if (SOLVE) {
-            T qb[N];
-            if (StageCfg<N * (int)sizeof(T)>::use && lane_full) {
-                aos_load_staged<T, N>(Bm, s_raw - (threadIdx.x & 31), threadIdx.x & 31, qb, lane_sm);
-            } else {
-                aos_load<T, N>(Bm, s, qb);
-            }
 #pragma unroll
-            for (int r = 0; r < N; ++r) y[r] = qb[r];
-        } else {
-#pragma unroll
-            for (int r = 0; r < N; ++r) y[r] = (T)0;
-        }
+        for (int r = 0; r < N; ++r) y[r] = SOLVE ? qb[r] : (T)0;
     } else
 #pragma unroll
     for (int k = 0; k < RL; ++k) {
@@ -253,7 +253,7 @@ int rowchol_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t
                 dispatch_bool(rm != 0, [&](auto RM) {
                     auto kern = k_row_chol<T, N.value, SOLVE.value, SOA.value, RM.value>;
                     // one lane per system on an AoS batch: one staging buffer of 32 records per warp
-                    const size_t smem = (G == 1 && !SOA.value) ? (size_t)(kRowThreads / 32) * 32 * N.value * N.value * sizeof(T) : 0;
+                    const size_t smem = (G == 1 && !SOA.value) ? (size_t)(kRowThreads / 32) * 32 * (N.value * N.value + N.value) * sizeof(T) : 0;
                     if (smem > 48 * 1024) {
                         static std::atomic<uint64_t> raised{0};
                         raise_dyn_smem(kern, smem, raised);
