@@ -49,7 +49,6 @@ template <typename T> int subwarp_cholesky(int, int, int64_t, const T*, const T*
 template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uint8_t*, T*, int, int, int, cudaStream_t);
 template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int rowinv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
-template <typename T> int rowinvd(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int row_backsolve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
 // gmb_rowfast_*.cu
 template <typename T> int rowfast_solve(int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
@@ -81,14 +80,16 @@ template <typename T> int xf_apply(int, int, int64_t, const T*, bool, const T*, 
 // SoA, CUDA events).  With an LU output the row-distributed kernel (bounce-buffer exchange of whole rows) wins for float n
 // in {12, 14, 15, 16} and for double n = 10 and n >= 12 (round 1).  Without one -- the common call -- only the live part of
 // a row travels and the register-only shuffle exchange applies; since the one-lane-per-system sub-warp kernel got its
-// staged record I/O (round 2) it wins up to float n = 9 (n = 8: 0.49 / 0.61 of the peak AoS / SoA against 0.48 / 0.49;
-// n = 9: 0.50 / 0.57 against 0.37 / 0.47), the row kernel from float n = 10 on and for double n = 7, 8 and n >= 10.
+// staged record I/O (round 2) it wins wherever one lane holds the system: up to float n = 10 (n = 8: 0.49 / 0.61 of the peak
+// AoS / SoA against 0.48 / 0.49; n = 9: 0.50 / 0.57 against 0.37 / 0.47; n = 10: 0.55 / 0.57 against 0.39 / 0.52; n = 11: 0.54 / 0.49
+// against 0.35 / 0.43) and double n = 7 (0.74 / 0.67 against 0.43 / 0.59); the row kernel from float n = 12 on and for double
+// n = 8 and n >= 10.
 // gmb_set_option("rowplu_min_n", n) overrides the table (17 disables the row kernel, 9 forces it).
 template <typename T>
 static bool use_row_kernel(int n, bool want_lu) {
     const int forced = g_opt_rowplu_min_n.load(std::memory_order_relaxed);
     if (forced >= 0) return n >= forced;
-    if (!want_lu) return sizeof(T) == 4 ? n >= 10 : (n == 7 || n == 8 || n >= 10);
+    if (!want_lu) return sizeof(T) == 4 ? n >= 12 : (n == 8 || n >= 10);
     if (n < 9) return false;
     if (sizeof(T) == 4) return n == 12 || n >= 14;
     return n == 10 || n >= 12;
@@ -281,16 +282,10 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
     // The row-distributed kernel (gmb_rowinv.cuh) is 1.2x (7 x 7 double) to 3x (16 x 16 float) faster than the
     // column-distributed one from n = 8 (float) / n = 6 (double) on and slower below (profiles/r1j_row_inverse.md);
     // option "rowinv" = 0 / 1 forces the column / row kernel for every n >= 5 (tests).
-    // one lane per system with deferred riders (float n <= 10, double n <= 7): option "invd" = 0 switches it off
-    if (fast && n >= 5 && n <= (sizeof(T) == 4 ? 10 : 7) && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
+    // one lane per system with deferred riders (float n <= 11, double n <= 7): option "invd" = 0 switches it off
+    if (fast && n >= 5 && n <= (sizeof(T) == 4 ? 11 : 7) && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
         g_opt_rowinv.load(std::memory_order_relaxed) < 0) {
         int rc = subwarp_invd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
-        if (rc != GMB_ERR_UNSUPPORTED) return rc;
-    }
-    // the same deferred-rider scheme on the row-distributed decomposition: measured for every larger size, wins for float n = 11
-    if (fast && sizeof(T) == 4 && n == 11 && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
-        g_opt_rowinv.load(std::memory_order_relaxed) < 0) {
-        int rc = rowinvd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     const int row_inv = g_opt_rowinv.load(std::memory_order_relaxed);

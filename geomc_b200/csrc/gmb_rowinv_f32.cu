@@ -6,9 +6,4 @@ template <> int rowinv<float>(int n, int64_t B, const float* A, float* Ainv, uin
                            cudaStream_t st) {
     return rowinv_impl<float>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
 }
-template <typename T> int rowinvd(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
-template <> int rowinvd<float>(int n, int64_t B, const float* A, float* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm,
-                            cudaStream_t st) {
-    return rowinvd_impl<float, 11, 11>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
-}
 }  // namespace gmb

@@ -6,9 +6,4 @@ template <> int rowinv<double>(int n, int64_t B, const double* A, double* Ainv, 
                            cudaStream_t st) {
     return rowinv_impl<double>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
 }
-template <typename T> int rowinvd(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
-template <> int rowinvd<double>(int n, int64_t B, const double* A, double* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm,
-                            cudaStream_t st) {
-    return rowinvd_impl<double, 17, 16>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);   // no double size wins (measured)
-}
 }  // namespace gmb

@@ -62,7 +62,7 @@ template <> struct InfOf<float>  { __device__ static __forceinline__ float get()
 template <> struct InfOf<double> { __device__ static __forceinline__ double get() { return __longlong_as_double(0x7ff0000000000000LL); } };
 
 // One system's solve / decomposition by the G lanes that own it (body of k_row_solve and k_row_solve_list).
-template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G, bool WANT_LU, bool SHFLX, int THREADS, bool INVD = false>
+template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G, bool WANT_LU, bool SHFLX, int THREADS>
 __device__ __forceinline__ void
 row_solve_one(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
               uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
@@ -305,91 +305,7 @@ row_solve_one(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, ui
         }
     }
 
-    if constexpr (INVD) {
-        // ---- deferred-rider inverse (invNxN, MatrixInv.h:219-231), rows distributed over G lanes -----------------------
-        // The decomposition above ran WITHOUT the identity (DECOMP: the rider is the row's source index, i.e. p[]).  The
-        // inverse is now produced one column at a time in i-space: right-hand side e_i, forward sweep column by column from
-        // c = i (the terms with c < i multiply exact zeros: with finite multipliers they leave +0, bit for bit; a warp that
-        // holds a system with a non-finite multiplier sweeps from c = 0 instead -- same bits for every system), backward
-        // sweep as in the fused solve, one reciprocal per diagonal entry shared by all n columns.  Column i belongs at
-        // out(., p[i]) (`out(i, p[i]) = 1`, :226): a run-time position, reached through a shared-memory scratch.
-        static_assert(DECOMP && WANT_LU, "the deferred-rider inverse runs on the full decomposition");
-        T* smw = reinterpret_cast<T*>(gmb_dyn_smem) + (threadIdx.x >> 5) * (NSYS * SA);
-        T* scr = smw + ((threadIdx.x & 31) / G) * SA;                       // this system's n x n scratch, row-major
-        T fin = (T)0;
-#pragma unroll
-        for (int k = 0; k < RL; ++k)
-#pragma unroll
-            for (int c = 0; c < N; ++c) fin = fma_rn(a[k][c], (T)0, fin);   // stays 0 unless some entry is Inf / NaN
-#pragma unroll
-        for (int off = G / 2; off >= 1; off >>= 1) fin += __shfl_xor_sync(0xffffffffu, fin, off, G);
-        const bool wdense = __any_sync(0xffffffffu, !(fin == (T)0));        // warp-uniform
-        T dk[RL], ry[RL];
-        bool rs[RL];
-#pragma unroll
-        for (int k = 0; k < RL; ++k) {
-            T d = a[k][k * G < N ? k * G : 0];
-#pragma unroll
-            for (int g = 1; g < G; ++g)
-                if (k * G + g < N) d = (lane_g == g) ? a[k][k * G + g] : d;  // this lane's diagonal entry of slot k
-            const RcpOf<T> rc(d);
-            dk[k] = d;
-            ry[k] = rc.y;
-            rs[k] = rc.safe;
-        }
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            T x[RL];
-#pragma unroll
-            for (int k = 0; k < RL; ++k) x[k] = (k * G + lane_g == i) ? (T)1 : (T)0;
-            // forward: L y = e_i, column-oriented (for every row the terms arrive with c ascending, :345-353)
-#pragma unroll
-            for (int c = 0; c < N - 1; ++c) {
-                if (c >= i || wdense) {
-                    const T xc = (G == 1) ? x[c / G] : __shfl_sync(0xffffffffu, x[c / G], c % G, G);
-#pragma unroll
-                    for (int sl = 0; sl < RL; ++sl) {
-                        if (sl >= c / G) {                                   // static
-                            const int p = sl * G + lane_g;
-                            const T v = fma_rn(-xc, a[sl][c], x[sl]);
-                            if (p > c && p < N) x[sl] = v;
-                        }
-                    }
-                }
-            }
-            // backward: U x = y (:356-365)
-#pragma unroll
-            for (int c = N - 1; c >= 0; --c) {
-                const int oc_lane = c % G, oc_slot = c / G;                  // static
-                bool okq;
-                T q = RcpOf<T>(dk[oc_slot], ry[oc_slot], rs[oc_slot]).fast(x[oc_slot], okq);
-                if (!okq) q = div_rn(x[oc_slot], dk[oc_slot]);
-                const T xc = (G == 1) ? q : __shfl_sync(0xffffffffu, q, oc_lane, G);
-                if (lane_g == oc_lane) x[oc_slot] = q;
-#pragma unroll
-                for (int k = 0; k <= oc_slot; ++k) {
-                    const int p = k * G + lane_g;
-                    const T v = fma_rn(-xc, a[k][c], x[k]);
-                    if (p < c) x[k] = v;
-                }
-            }
-            const T pcv = (G == 1) ? a[i / G][N] : __shfl_sync(0xffffffffu, a[i / G][N], i % G, G);
-            const int pc = (int)pcv;
-#pragma unroll
-            for (int k = 0; k < RL; ++k) {
-                const int p = k * G + lane_g;
-                if (p < N) scr[N * p + pc] = x[k];
-            }
-        }
-        __syncwarp();
-        // ---- egress: `out` untouched where the matrix is singular
-        if (!SOA && s_warp0 + NSYS <= B && __all_sync(0xffffffffu, good)) {
-            warp_stage_out<T, N * N, NSYS>(X + s_warp0 * (int64_t)(N * N), smw, threadIdx.x & 31);
-        } else if (valid && good) {
-            for (int e = lane_g; e < N * N; e += G) X[baseA + (int64_t)e * ST] = scr[e];
-        }
-        if (valid && lane_g == 0 && ok_out) ok_out[s] = good ? 1 : 0;
-    } else if constexpr (DECOMP) {
+    if constexpr (DECOMP) {
         if (valid) {
 #pragma unroll
             for (int k = 0; k < RL; ++k) {
@@ -439,7 +355,7 @@ row_solve_one(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, ui
 //                 so after the exchanges slot p holds reorder[p]; no rider arithmetic, no backward sweep.
 //                 (A is then read and written through `LU`; perm / parity / degenerate counts are stored.)
 template <typename T, int N, bool SOA, bool RM, bool DECOMP, int G = row_group(N, (int)sizeof(T) / 4), int MINB = GMB_ROW_MIN_BLOCKS,
-          bool WANT_LU = true, bool SHFLX = false, int THREADS = kRowThreads, bool INVD = false>
+          bool WANT_LU = true, bool SHFLX = false, int THREADS = kRowThreads>
 __global__ void __launch_bounds__(THREADS, MINB)
 k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint8_t* __restrict__ ok_out,
             uint8_t* __restrict__ perm_out, uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip,
@@ -448,8 +364,8 @@ k_row_solve(const T* __restrict__ A, const T* Bm, T* X, T* __restrict__ LU, uint
     const bool valid = s < B;
     if (!valid) s = B - 1;                                     // keep all lanes for the shuffles / syncwarp
     const int64_t s_warp0 = ((int64_t)blockIdx.x * THREADS + (threadIdx.x & ~31u)) / G;
-    row_solve_one<T, N, SOA, RM, DECOMP, G, WANT_LU, SHFLX, THREADS, INVD>(A, Bm, X, LU, ok_out, perm_out, parity_out, degen_out, skip,
-                                                                          B, s, valid, s_warp0);
+    row_solve_one<T, N, SOA, RM, DECOMP, G, WANT_LU, SHFLX, THREADS>(A, Bm, X, LU, ok_out, perm_out, parity_out, degen_out, skip, B, s,
+                                                                    valid, s_warp0);
 }
 
 // The same solve for the systems named in list[0 .. *count): the exact re-solve of the systems that the speculative
@@ -518,39 +434,6 @@ int rowplu_solve_impl(int n, int64_t B, const T* A, const T* Bm, T* X, uint8_t* 
             });
         });
         rc = after_launch();
-    });
-    return rc;
-}
-
-// Deferred-rider inverse on the row-distributed decomposition (row_solve_one, INVD): beyond the sizes of the
-// one-lane-per-system form (k_sub_plu MODE_INVD).  `a_rm` as in the other inverse kernels: the working copy has the
-// destination's layout and is treated as row-major.  Measured for float n = 11..16 and double n = 8..16
-// (profiles/r2j_row_invd.md): bit-identical everywhere, but faster than k_row_inv only for float n = 11 (0.24 / 0.28 of
-// the HBM peak against 0.15 / 0.22) -- the bounce-buffer decomposition it rides on runs at 200+ registers and two lanes
-// per system -- so only the sizes in [NMIN, NMAX] are instantiated.
-template <typename T, int NMIN, int NMAX>
-int rowinvd_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_rm, int dst_rm, cudaStream_t st) {
-    int rc = GMB_ERR_UNSUPPORTED;
-    const bool a_rm = (src_rm != 0) == (dst_rm != 0);
-    dispatch_int<8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
-        if constexpr (N.value >= NMIN && N.value <= NMAX) {
-            constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
-            const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
-            if (grid == 0) {
-                rc = GMB_OK;
-                return;
-            }
-            dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
-                dispatch_bool(a_rm, [&](auto RM) {
-                    auto kern = k_row_solve<T, N.value, SOA.value, RM.value, true, G, GMB_ROW_MIN_BLOCKS, true, false, kRowThreads, true>;
-                    const size_t smem = row_stage_bytes<T, N.value>();
-                    static std::atomic<uint64_t> raised{0};   // per instantiation, one bit per device
-                    raise_dyn_smem(kern, smem, raised);
-                    kern<<<grid, kRowThreads, smem, st>>>(A, nullptr, Ainv, nullptr, ok, nullptr, nullptr, nullptr, 0, B);
-                });
-            });
-            rc = after_launch();
-        }
     });
     return rc;
 }

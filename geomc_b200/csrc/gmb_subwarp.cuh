@@ -33,11 +33,18 @@ constexpr int kSubThreads = 128;
 #ifndef GMB_SUB_MIN_BLOCKS
 #define GMB_SUB_MIN_BLOCKS 3      // cap at 128 registers: occupancy matters more than a few spills here (ncu: 12% -> 25%)
 #endif
+// Register words for the local block [A | riders] of one lane (picks G, the lanes per system).  Measured in round 2
+// (profiles/r2p_budget112.md): 132 words for the kernels that carry riders puts float n <= 11 (m = 1), float n <= 10 (m = 3) and
+// double n = 7 (m = 1) on ONE lane per system -- with the staged I/O and without the exchange of dead multiplier columns that
+// beats two lanes and the row kernel (double 7x7 fused solve 0.43 / 0.59 -> 0.78 / 0.67 of the HBM peak, float 10x10 0.39 / 0.52
+// -> 0.56 / 0.57, float 11x11 0.35 / 0.43 -> 0.54 / 0.49, float 10x10 with three right-hand sides 0.24 / 0.33 -> 0.56 / 0.55); the
+// rider-free kernels (decomposition, deferred-rider inverse, rectangular mode) take 121 = float n <= 11 (decomp_plu 11x11 from
+// AoS records 0.54 -> 0.74; 130 words spilled: double 8x8).
 #ifndef GMB_SUB_REG_BUDGET
-#define GMB_SUB_REG_BUDGET 100            // register words for the local block (picks G)
+#define GMB_SUB_REG_BUDGET 132
 #endif
 #ifndef GMB_SUB_REG_BUDGET_XC0
-#define GMB_SUB_REG_BUDGET_XC0 GMB_SUB_REG_BUDGET   // ... when no rider columns are carried (decomposition, deferred-rider inverse)
+#define GMB_SUB_REG_BUDGET_XC0 121
 #endif
 constexpr int kRegBudgetWords = GMB_SUB_REG_BUDGET;
 
@@ -766,7 +773,7 @@ template <typename T>
 int subwarp_rect_impl(int N_, int nb, int64_t B, const T* bases, T* null_basis, uint8_t* ok, int layout, cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     if (nb < 1 || nb >= N_) return rc;
-    dispatch_int<5, 6, 7, 8, 9, 10>(N_, [&](auto N) {
+    dispatch_int<5, 6, 7, 8, 9, 10, 11>(N_, [&](auto N) {
         if constexpr (sub_group(N.value, 0, (int)sizeof(T) / 4) == 1) {
             rc = launch_sub<T, N.value, 0, MODE_RECT>(bases, nullptr, null_basis, nullptr, ok, nullptr, nullptr, nullptr, nb, B, layout,
                                                       1, 1, st);
@@ -781,7 +788,7 @@ int subwarp_invd_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int la
                       cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     const int a_rm = ((src_rm != 0) == (dst_rm != 0)) ? 1 : 0;
-    dispatch_int<5, 6, 7, 8, 9, 10>(n, [&](auto N) {
+    dispatch_int<5, 6, 7, 8, 9, 10, 11>(n, [&](auto N) {
         if constexpr (sub_group(N.value, 0, (int)sizeof(T) / 4) == 1) {
             rc = launch_sub<T, N.value, 0, MODE_INVD>(A, nullptr, Ainv, nullptr, ok, nullptr, nullptr, nullptr, 0, B, layout,
                                                       a_rm, 1, st);
