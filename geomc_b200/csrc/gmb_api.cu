@@ -80,16 +80,17 @@ template <typename T> int xf_apply(int, int, int64_t, const T*, bool, const T*, 
 // SoA, CUDA events).  With an LU output the row-distributed kernel (bounce-buffer exchange of whole rows) wins for float n
 // in {12, 14, 15, 16} and for double n = 10 and n >= 12 (round 1).  Without one -- the common call -- only the live part of
 // a row travels and the register-only shuffle exchange applies; since the one-lane-per-system sub-warp kernel got its
-// staged record I/O (round 2) it wins wherever one lane holds the system: up to float n = 10 (n = 8: 0.49 / 0.61 of the peak
-// AoS / SoA against 0.48 / 0.49; n = 9: 0.50 / 0.57 against 0.37 / 0.47; n = 10: 0.55 / 0.57 against 0.39 / 0.52; n = 11: 0.54 / 0.49
-// against 0.35 / 0.43) and double n = 7 (0.74 / 0.67 against 0.43 / 0.59); the row kernel from float n = 12 on and for double
-// n = 8 and n >= 10.
+// staged record I/O (round 2) it wins wherever one lane holds the system -- since the "wide" one-lane kernels (255 registers,
+// gmb_subwarp.cuh sub_wide) that is float n <= 14 and double n <= 9 (profiles/r2t_wide_lane.md, 1 GB batches, AoS / SoA of the
+// peak, sub-warp against row kernel: double n = 8 0.74 / 0.58 against 0.55 / 0.55, double n = 9 0.71 / 0.67 against 0.36 / 0.35,
+// float n = 13 0.46 / 0.43 against 0.37 / 0.41 (speculative kernel), float n = 14 0.43 / 0.39 against 0.34 / 0.35).  Float n = 12
+// stays with the row kernel (0.42 / 0.49 against 0.43 / 0.45), as do float n >= 15 (speculative kernel first) and double n >= 10.
 // gmb_set_option("rowplu_min_n", n) overrides the table (17 disables the row kernel, 9 forces it).
 template <typename T>
 static bool use_row_kernel(int n, bool want_lu) {
     const int forced = g_opt_rowplu_min_n.load(std::memory_order_relaxed);
     if (forced >= 0) return n >= forced;
-    if (!want_lu) return sizeof(T) == 4 ? n >= 12 : (n == 8 || n >= 10);
+    if (!want_lu) return sizeof(T) == 4 ? (n == 12 || n >= 15) : n >= 10;
     if (n < 9) return false;
     if (sizeof(T) == 4) return n == 12 || n >= 14;
     return n == 10 || n >= 12;
@@ -100,8 +101,8 @@ static bool use_rowfast(int n) {
     const int forced = g_opt_rowfast.load(std::memory_order_relaxed);
     if (forced >= 0) return forced != 0;
     // measured against the exact row kernel (profiles/r2a_rowfast.md, 2^20 systems, AoS): float n = 13, 15, 16 win
-    // (16 x 16: 0.58 -> 0.39 ms); n <= 12 and 14 run two lanes per system in the exact kernel and stay there
-    return sizeof(T) == 4 && (n == 13 || n >= 15);
+    // (16 x 16: 0.58 -> 0.39 ms); n = 13 has since gone to the wide one-lane sub-warp kernel (0.46 / 0.43 against 0.37 / 0.41)
+    return sizeof(T) == 4 && n >= 15;
 }
 
 // Cholesky: the row kernel (one lane per system for these sizes, staged AoS ingest) serves one right-hand side; the
@@ -283,7 +284,7 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
     // column-distributed one from n = 8 (float) / n = 6 (double) on and slower below (profiles/r1j_row_inverse.md);
     // option "rowinv" = 0 / 1 forces the column / row kernel for every n >= 5 (tests).
     // one lane per system with deferred riders (float n <= 11, double n <= 7): option "invd" = 0 switches it off
-    if (fast && n >= 5 && n <= (sizeof(T) == 4 ? 11 : 7) && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
+    if (fast && n >= 5 && n <= (sizeof(T) == 4 ? 14 : 10) && g_opt_invd.load(std::memory_order_relaxed) != 0 &&
         g_opt_rowinv.load(std::memory_order_relaxed) < 0) {
         int rc = subwarp_invd<T>(n, B, A, Ainv, ok, layout, src_rm, dst_rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;

@@ -68,10 +68,31 @@ constexpr bool sub_stage_in(int n, int mode, bool soa) {
     return !soa && sizeof(T) == 4 && mode != MODE_INV && (n == 8 || n == 9);
 }
 constexpr bool sub_stage_out(int mode, bool soa) { return !soa && mode != MODE_SOLVE; }
+// "Wide" one-lane kernels (round 2, profiles/r2t_wide_lane.md): a local block [A | riders] of up to GMB_SUB_WIDE_WORDS register
+// words that exceeds the budgets above still runs on ONE lane per system, under the 255-register ceiling (two 128-thread
+// CTAs per SM) instead of two lanes with a shuffle per exchanged / broadcast element: double n = 8, 9, float n = 12, 13 and
+// the multi-right-hand-side solves just above the budget (double 7x7 / 8x8 and float 11x11 / 12x12 with three of them).
+#ifndef GMB_SUB_WIDE_WORDS
+#define GMB_SUB_WIDE_WORDS 210            // 0 switches the wide kernels off
+#endif
+constexpr bool sub_wide(int n, int xc, int words) {
+    const int block = words * n * (n + xc);
+    return block > (xc == 0 ? GMB_SUB_REG_BUDGET_XC0 : GMB_SUB_REG_BUDGET) && block <= GMB_SUB_WIDE_WORDS;
+}
 constexpr int sub_group(int n, int xc, int words) {
+    if (sub_wide(n, xc, words)) return 1;
     for (int g = 1; g <= 16; g *= 2)
         if (n * sub_lc(n, xc, g) * words <= (xc == 0 ? GMB_SUB_REG_BUDGET_XC0 : kRegBudgetWords)) return g;
     return 16;
+}
+// The one measured exception (profiles/r2t_wide_lane.md): the row-pivot decomposition of an SoA batch keeps two lanes per system
+// for float n = 12, 14 and double n = 10 (0.64 / 0.54 / 0.59 of the HBM peak against 0.57 / 0.51 / 0.46 on one wide lane).
+constexpr int sub_group_for(int n, int xc, int words, int mode, bool soa, bool colpiv) {
+    if (mode == MODE_DECOMP && soa && !colpiv && xc == 0 && ((words == 1 && (n == 12 || n == 14)) || (words == 2 && n == 10))) return 2;
+    return sub_group(n, xc, words);
+}
+constexpr int sub_min_blocks(int n, int xc, int words, int mode, bool soa, bool colpiv) {
+    return (sub_wide(n, xc, words) && sub_group_for(n, xc, words, mode, soa, colpiv) == 1) ? 2 : GMB_SUB_MIN_BLOCKS;
 }
 
 template <int G>
@@ -154,12 +175,12 @@ constexpr int sub_lane_emax(int n, int xc, int mode) { return n * n + (mode == 0
 // NO_L = true (one lane per system, fused solve, no LU output asked for): nobody reads the multipliers afterwards, so they
 // are neither stored nor exchanged -- only columns >= i of a row travel (a quarter of the exchange's selects for n = 7).
 template <typename T, int N, int XC, int MODE, bool SOA, bool A_RM, bool X_RM, bool COLPIV = false, bool NO_L = false>
-__global__ void __launch_bounds__(kSubThreads, GMB_SUB_MIN_BLOCKS)
+__global__ void __launch_bounds__(kSubThreads, sub_min_blocks(N, XC, (int)sizeof(T) / 4, MODE, SOA, COLPIV))
 k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ perm_out,
           uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B) {
     constexpr int ST = BatchAddr<T, SOA>::STRIDE;
     constexpr int WORDS = (int)sizeof(T) / 4;
-    constexpr int G = sub_group(N, XC, WORDS);
+    constexpr int G = sub_group_for(N, XC, WORDS, MODE, SOA, COLPIV);
     constexpr int NC = N + XC;
     constexpr int LC = sub_lc(N, XC, G);
     const int lane_g = (G == 1) ? 0 : (int)(threadIdx.x % G);
@@ -692,11 +713,10 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
 template <typename T, int N, int XC, int MODE, bool COLPIV = false>
 static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t* perm, uint8_t* parity, uint8_t* degen,
                       int skip, int64_t B, int layout, int a_rm, int x_rm, cudaStream_t st) {
-    constexpr int G = sub_group(N, XC, (int)sizeof(T) / 4);
-    const int64_t threads = B * G;
-    const unsigned grid = (unsigned)ceil_div(threads, kSubThreads);
-    if (grid == 0) return GMB_OK;
+    if (B == 0) return GMB_OK;
     dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+        constexpr int G = sub_group_for(N, XC, (int)sizeof(T) / 4, MODE, SOA.value, COLPIV);
+        const unsigned grid = (unsigned)ceil_div(B * G, kSubThreads);
         dispatch_bool(a_rm != 0, [&](auto ARM) {
             // riders: linear_solve uses the matrix' own layout flag; invNxN always writes row-major
             constexpr bool XRM = (MODE == MODE_INV || MODE == MODE_INVD) ? true : ARM.value;
@@ -773,7 +793,7 @@ template <typename T>
 int subwarp_rect_impl(int N_, int nb, int64_t B, const T* bases, T* null_basis, uint8_t* ok, int layout, cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     if (nb < 1 || nb >= N_) return rc;
-    dispatch_int<5, 6, 7, 8, 9, 10, 11>(N_, [&](auto N) {
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14>(N_, [&](auto N) {
         if constexpr (sub_group(N.value, 0, (int)sizeof(T) / 4) == 1) {
             rc = launch_sub<T, N.value, 0, MODE_RECT>(bases, nullptr, null_basis, nullptr, ok, nullptr, nullptr, nullptr, nb, B, layout,
                                                       1, 1, st);
@@ -788,7 +808,7 @@ int subwarp_invd_impl(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int la
                       cudaStream_t st) {
     int rc = GMB_ERR_UNSUPPORTED;
     const int a_rm = ((src_rm != 0) == (dst_rm != 0)) ? 1 : 0;
-    dispatch_int<5, 6, 7, 8, 9, 10, 11>(n, [&](auto N) {
+    dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14>(n, [&](auto N) {
         if constexpr (sub_group(N.value, 0, (int)sizeof(T) / 4) == 1) {
             rc = launch_sub<T, N.value, 0, MODE_INVD>(A, nullptr, Ainv, nullptr, ok, nullptr, nullptr, nullptr, 0, B, layout,
                                                       a_rm, 1, st);
