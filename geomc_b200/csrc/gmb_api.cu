@@ -24,6 +24,7 @@ std::atomic<int> g_opt_rowdecomp_min_n{-1};  // decomp_plu: row-distributed kern
 std::atomic<int> g_opt_rowinv{-1};           // inverse n >= 5: 0 = column-distributed kernel, 1 = row-distributed
 std::atomic<int> g_opt_rowfast{-1};          // speculative solve (gmb_rowfast.cuh): 0 = off, 1 = wherever it exists
 std::atomic<int> g_opt_invd{-1};             // deferred-rider inverse (k_sub_plu MODE_INVD): 0 = off, 1 = wherever it exists
+std::atomic<int> g_opt_lanebs{-1};           // one-lane backsolve with 1..4 right-hand sides (gmb_lanebs.cuh): 0 = off
 std::atomic<int> g_opt_lanechol{-1};         // one-thread-per-system Cholesky with staged ingest, n = 5..8: 0 = off, 1 = on
 
 // gmb_small.cu
@@ -50,6 +51,8 @@ template <typename T> int rowplu_solve(int, int64_t, const T*, const T*, T*, uin
 template <typename T> int rowplu_decomp(int, int64_t, T*, uint8_t*, uint8_t*, uint8_t*, int, int, cudaStream_t);
 template <typename T> int rowinv(int, int64_t, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 template <typename T> int row_backsolve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
+// gmb_lanebs_*.cu
+template <typename T> int lane_backsolve(int, int, int, int64_t, const T*, const uint8_t*, const T*, T*, int, int, int, cudaStream_t);
 // gmb_rowfast_*.cu
 template <typename T> int rowfast_solve(int, int64_t, const T*, const T*, T*, uint8_t*, int, int, int, cudaStream_t);
 // gmb_lane_*.cu
@@ -181,6 +184,12 @@ int lu_backsolve(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* 
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && n >= 2 && n <= 4 && m <= 4) {
         int rc = small_backsolve<T>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
+        if (rc != GMB_ERR_UNSUPPORTED) return rc;
+    }
+    // one lane per system, 1..4 right-hand sides in one pass, staged AoS records (float n <= 13, double n <= 9); option "lanebs" = 0
+    // leaves every call to the row kernel below (profiles/r2x_lane_backsolve.md)
+    if (fast && n >= 5 && m <= 4 && mode != 2 && g_opt_lanebs.load(std::memory_order_relaxed) != 0) {
+        int rc = lane_backsolve<T>(mode, n, m, B, LU, perm, Bm, X, skip, layout, rm, st);
         if (rc != GMB_ERR_UNSUPPORTED) return rc;
     }
     if (fast && n >= 5) {                                    // any number of right-hand sides: the LU rows are loaded once
@@ -718,6 +727,7 @@ int gmb_set_option(const char* name, int value) {
                           : !std::strcmp(name, "rowinv")          ? &g_opt_rowinv
                           : !std::strcmp(name, "rowfast")         ? &g_opt_rowfast
                           : !std::strcmp(name, "invd")            ? &g_opt_invd
+                          : !std::strcmp(name, "lanebs")          ? &g_opt_lanebs
                           : !std::strcmp(name, "lanechol")        ? &g_opt_lanechol
                                                                   : nullptr;
     if (!o) return GMB_ERR_INVALID_ARG;

@@ -497,6 +497,23 @@ def test_both_large_n_solve_kernels(force):
     assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
 
 
+def test_row_backsolve_kernel_without_the_lane_kernel():
+    """backsolve_lu / backsolve_plu with 1..4 right-hand sides take the one-lane kernel (gmb_lanebs.cuh) for float n <= 13 /
+    double n <= 9; option lanebs = 0 sends every call to the row kernel (run-time m) instead: rerun the oracle comparison for
+    n = 5..13 in a fresh process so that both kernels stay covered."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GMB_OPT_LANEBS="0")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = " or ".join(f"{n}-" for n in range(5, 14))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-m", "gpu",
+                        "-k", f"(test_random_vs_oracle or test_backsolve_single_rhs) and ({sel})"],
+                       env=env, capture_output=True, text=True, cwd=root, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("force", ["0", "1"])
 def test_both_large_n_inverse_kernels(force):
     """inv for n >= 5 has a row-distributed (gmb_rowinv.cuh) and a column-distributed kernel; the dispatcher picks per
@@ -633,3 +650,25 @@ def test_backsolve_single_rhs(gm, orc, dt, n, soa):
                       f"backsolve_lu n={n} rm={rm} skip={skip} soa={soa}")
                 check(down(gm.backsolve_plu(lu, p, up(gm, b, soa), n, 1, skip, rm)),
                       orc.backsolve_plu(lu_np, p_np, b, n, 1, skip, rm), f"backsolve_plu n={n} rm={rm} skip={skip} soa={soa}")
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [5, 8, 11, 13])
+def test_backsolve_two_and_four_rhs(gm, orc, dt, n, soa):
+    """backsolve_lu / backsolve_plu with m = 2 and m = 4 right-hand sides (the one-lane kernel's other instantiations; m = 1
+    and m = 3 are covered above and in run_all), skip = 0 and 1, both orders, a batch with a ragged last warp."""
+    rng = np.random.default_rng(991 * n + np.dtype(dt).itemsize)
+    B = 32 * 7 + 19
+    A = rng.standard_normal((B, n * n)).astype(dt)
+    for rm in (True, False):
+        lu_np, p_np, _, _ = orc.decomp_plu(A, n, n, rm)
+        lu, p = up(gm, lu_np, soa), torch.from_numpy(p_np.astype(np.uint8)).cuda()
+        for m in (2, 4):
+            b = rng.standard_normal((B, n * m)).astype(dt)
+            for skip in (0, 1):
+                with np.errstate(all="ignore"):
+                    check(down(gm.backsolve_lu(lu, up(gm, b, soa), n, m, skip, rm)), orc.backsolve_lu(lu_np, b, n, m, skip, rm),
+                          f"backsolve_lu n={n} m={m} rm={rm} skip={skip} soa={soa}")
+                    check(down(gm.backsolve_plu(lu, p, up(gm, b, soa), n, m, skip, rm)),
+                          orc.backsolve_plu(lu_np, p_np, b, n, m, skip, rm), f"backsolve_plu n={n} m={m} rm={rm} skip={skip} soa={soa}")
