@@ -24,6 +24,7 @@ std::atomic<int> g_opt_rowdecomp_min_n{-1};  // decomp_plu: row-distributed kern
 std::atomic<int> g_opt_rowinv{-1};           // inverse n >= 5: 0 = column-distributed kernel, 1 = row-distributed
 std::atomic<int> g_opt_rowfast{-1};          // speculative solve (gmb_rowfast.cuh): 0 = off, 1 = wherever it exists
 std::atomic<int> g_opt_invd{-1};             // deferred-rider inverse (k_sub_plu MODE_INVD): 0 = off, 1 = wherever it exists
+std::atomic<int> g_sub_prefetch{-1};         // one-lane sub-warp kernels: L2 prefetch distance in CTAs (gmb_subwarp.cuh); -1 = one wave, 0 = off
 std::atomic<int> g_opt_lanebs{-1};           // one-lane backsolve with 1..4 right-hand sides (gmb_lanebs.cuh): 0 = off
 std::atomic<int> g_opt_lanechol{-1};         // one-thread-per-system Cholesky with staged ingest, n = 5..8: 0 = off, 1 = on
 
@@ -728,6 +729,7 @@ int gmb_set_option(const char* name, int value) {
                           : !std::strcmp(name, "rowfast")         ? &g_opt_rowfast
                           : !std::strcmp(name, "invd")            ? &g_opt_invd
                           : !std::strcmp(name, "lanebs")          ? &g_opt_lanebs
+                          : !std::strcmp(name, "subprefetch")     ? &g_sub_prefetch
                           : !std::strcmp(name, "lanechol")        ? &g_opt_lanechol
                                                                   : nullptr;
     if (!o) return GMB_ERR_INVALID_ARG;

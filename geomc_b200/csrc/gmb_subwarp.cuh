@@ -95,6 +95,24 @@ constexpr int sub_min_blocks(int n, int xc, int words, int mode, bool soa, bool 
     return (sub_wide(n, xc, words) && sub_group_for(n, xc, words, mode, soa, colpiv) == 1) ? 2 : GMB_SUB_MIN_BLOCKS;
 }
 
+// cp.async.bulk.prefetch.L2: `bytes` (a multiple of 16) starting at the 16-byte aligned `p` are brought into L2; no destination
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// option "subprefetch": -1 = one wave ahead (SM count x resident CTAs), 0 = off, > 0 = that many CTAs ahead
+extern std::atomic<int> g_sub_prefetch;
+inline int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = cached[dev & 63].load(std::memory_order_relaxed);
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 template <int G>
 __device__ __forceinline__ unsigned shfl_u(unsigned v, int src_in_group) {
     if constexpr (G == 1) return v;
@@ -177,7 +195,7 @@ constexpr int sub_lane_emax(int n, int xc, int mode) { return n * n + (mode == 0
 template <typename T, int N, int XC, int MODE, bool SOA, bool A_RM, bool X_RM, bool COLPIV = false, bool NO_L = false>
 __global__ void __launch_bounds__(kSubThreads, sub_min_blocks(N, XC, (int)sizeof(T) / 4, MODE, SOA, COLPIV))
 k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict__ ok_out, uint8_t* __restrict__ perm_out,
-          uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B) {
+          uint8_t* __restrict__ parity_out, uint8_t* __restrict__ degen_out, int skip, int64_t B, int pf_dist) {
     constexpr int ST = BatchAddr<T, SOA>::STRIDE;
     constexpr int WORDS = (int)sizeof(T) / 4;
     constexpr int G = sub_group_for(N, XC, WORDS, MODE, SOA, COLPIV);
@@ -189,6 +207,26 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
     const bool valid = s < B;
     if (!valid) s = B - 1;                                    // keep every lane alive for the shuffles
 
+    // One lane per system: the 128 systems of a CTA are ONE contiguous range in either layout (AoS: 128 records; SoA: whole
+    // tiles, 128 % W == 0).  The CTA that will run `pf_dist` CTAs later (about one wave: the SM count times the resident CTAs)
+    // gets its range pulled into L2 now, so that its loads -- issued by the few warps the register footprint leaves -- meet an
+    // L2 latency instead of a DRAM one.  No extra traffic: every byte is still fetched from DRAM once.
+    if constexpr (G == 1 && MODE != MODE_RECT) {
+        const int64_t s_pf = ((int64_t)blockIdx.x + pf_dist) * kSubThreads;
+        if (pf_dist > 0 && s_pf + kSubThreads <= B) {
+            constexpr unsigned CHUNK = 8192;
+            constexpr unsigned BYTES_A = kSubThreads * N * N * (unsigned)sizeof(T);
+            const char* pa = reinterpret_cast<const char*>(A + s_pf * (int64_t)(N * N));
+            for (unsigned o = threadIdx.x * CHUNK; o < BYTES_A; o += kSubThreads * CHUNK)
+                l2_prefetch_bulk(pa + o, (BYTES_A - o < CHUNK) ? BYTES_A - o : CHUNK);
+            if constexpr (MODE == MODE_SOLVE) {
+                constexpr unsigned BYTES_B = kSubThreads * N * XC * (unsigned)sizeof(T);
+                const char* pb = reinterpret_cast<const char*>(Bm + s_pf * (int64_t)(N * XC));
+                for (unsigned o = threadIdx.x * CHUNK; o < BYTES_B; o += kSubThreads * CHUNK)
+                    l2_prefetch_bulk(pb + o, (BYTES_B - o < CHUNK) ? BYTES_B - o : CHUNK);
+            }
+        }
+    }
     const int64_t baseA = BatchAddr<T, SOA>::base(s, N * N);
     const int64_t baseX = BatchAddr<T, SOA>::base(s, N * (XC > 0 ? XC : 1));
     const T* Ap = A + baseA + (int64_t)c0 * (A_RM ? ST : N * ST);          // this lane's first column of A
@@ -734,7 +772,16 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
                 static std::atomic<uint64_t> raised[2];   // per instantiation (with / without the L part), one bit per device
                 raise_dyn_smem(kern, smem, raised[(CAN_NO_L && LU == nullptr) ? 1 : 0]);
             }
-            kern<<<grid, kSubThreads, smem, st>>>(A, Bm, X, LU, ok, perm, parity, degen, skip, B);
+            constexpr int MINB = sub_min_blocks(N, XC, (int)sizeof(T) / 4, MODE, SOA.value, COLPIV);
+            const int pf = g_sub_prefetch.load(std::memory_order_relaxed);
+            // Measured (profiles/r2ab_l2_prefetch.md): large gains in the SoA container up to 400-byte matrices and for the wide
+            // kernels up to 576 bytes (double 8x8 fused solve 0.58 -> 0.75 of the HBM peak, decomposition 0.73 -> 0.92, float 9x9
+            // decomposition 0.74 -> 1.02), small ones for AoS records up to 200 bytes; beyond that the prefetch bursts cost more
+            // than the latency they hide (float 11x11 decomposition 0.77 -> 0.70): off there unless the option forces a distance.
+            constexpr int REC = N * N * (int)sizeof(T);
+            constexpr bool PF_ON = G == 1 && (SOA.value ? (REC <= 400 || (MINB == 2 && REC <= 576)) : REC <= 200);
+            const int pf_dist = (G != 1 || pf == 0) ? 0 : pf > 0 ? pf : PF_ON ? sm_count() * MINB : 0;
+            kern<<<grid, kSubThreads, smem, st>>>(A, Bm, X, LU, ok, perm, parity, degen, skip, B, pf_dist);
         });
     });
     return after_launch();

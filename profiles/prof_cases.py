@@ -57,6 +57,14 @@ def run(case):
         A = grid((B, n * n), dt)
         out, ok = torch.empty_like(A), torch.zeros(B, dtype=torch.uint8, device=dev)
         return lambda: gm.inv(A, n, out=out, ok_out=ok)
+    if case.startswith("bs"):             # bs<f|d><n>: backsolve_plu with three right-hand sides, AoS records
+        dt = f32 if case[2] == "f" else f64
+        n = int(case[3:])
+        B = 1 << 20
+        A, b3 = grid((B, n * n), dt), grid((B, 3 * n), dt)
+        lu, perm, _, _ = gm.decomp_plu(A, n)
+        x = torch.empty_like(b3)
+        return lambda: gm.backsolve_plu(lu, perm, b3, n, 3, x_out=x) if "x_out" in gm.backsolve_plu.__code__.co_varnames else gm.backsolve_plu(lu, perm, b3, n, 3)
     if case.startswith("chol"):           # chol<f|d><n>: fused Cholesky + solve, SoA, SPD inputs
         dt = f32 if case[4] == "f" else f64
         n = int(case[5:])
