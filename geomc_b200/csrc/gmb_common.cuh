@@ -50,4 +50,22 @@ inline void raise_dyn_smem(K kern, size_t bytes, std::atomic<uint64_t>& done) {
     }
 }
 
+// cp.async.bulk.prefetch.L2: `bytes` (a multiple of 16) starting at the 16-byte aligned `p` are brought into L2; no destination
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// option "subprefetch": -1 = one wave ahead (SM count x resident CTAs), 0 = off, > 0 = that many CTAs ahead
+extern std::atomic<int> g_sub_prefetch;
+inline int sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int v = cached[dev & 63].load(std::memory_order_relaxed);
+    if (v == 0) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
 }  // namespace gmb

@@ -22,11 +22,27 @@
 
 namespace gmb {
 
+// Lanes per system.  The PLU row kernels' rule (row_group: whole rows of [A | b] within 140 words) is far too cautious here: only
+// the lower triangle is ever held, n (n + 1) / 2 + n words.  In the SoA container, where a lane reads its planes coalesced whatever
+// their number, ONE lane per system therefore serves every float size and double n <= 11 (no shuffles at all; round 2, run r2ad:
+// double 8x8 Cholesky + solve 0.47 -> 0.92 of the HBM peak, float 12x12 0.47 -> 0.84: profiles/r2ad_lane_cholesky.md).  AoS batches take one lane where the warp's staging buffer
+// (whole records, n * n + n elements per lane) still leaves two CTAs per SM: float n <= 14, double n <= 9.
+#ifndef GMB_CHOL_LANE_WORDS
+#define GMB_CHOL_LANE_WORDS 210
+#endif
+#ifndef GMB_CHOL_LANE_AOS_BYTES
+#define GMB_CHOL_LANE_AOS_BYTES 840       // AoS: bytes of [A | b] per system that the warp's staging buffer may take (two CTAs per SM)
+#endif
+constexpr int chol_group(int n, int words, bool soa) {
+    if (words * (n * (n + 1) / 2 + 2 * n) <= GMB_CHOL_LANE_WORDS && (soa || (n * n + n) * words * 4 <= GMB_CHOL_LANE_AOS_BYTES)) return 1;
+    return row_group(n, words);
+}
+
 template <typename T, int N, bool SOLVE, bool SOA, bool RM>
 __global__ void __launch_bounds__(kRowThreads, GMB_ROW_MIN_BLOCKS)
 k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out, int64_t B) {
     constexpr int WORDS = (int)sizeof(T) / 4;
-    constexpr int G = row_group(N, WORDS);
+    constexpr int G = chol_group(N, WORDS, SOA);
     constexpr int RL = row_rl(N, G);
     constexpr int ST = SOA ? soa_w<T>() : 1;
     constexpr int W = soa_w<T>();
@@ -242,14 +258,14 @@ int rowchol_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t
     if (solve && m != 1) return GMB_ERR_UNSUPPORTED;
     int rc = GMB_ERR_UNSUPPORTED;
     dispatch_int<5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16>(n, [&](auto N) {
-        constexpr int G = row_group(N.value, (int)sizeof(T) / 4);
-        const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
-        if (grid == 0) {
+        if (B == 0) {
             rc = GMB_OK;
             return;
         }
         dispatch_bool(solve, [&](auto SOLVE) {
             dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
+                constexpr int G = chol_group(N.value, (int)sizeof(T) / 4, SOA.value);
+                const unsigned grid = (unsigned)ceil_div(B * G, kRowThreads);
                 dispatch_bool(rm != 0, [&](auto RM) {
                     auto kern = k_row_chol<T, N.value, SOLVE.value, SOA.value, RM.value>;
                     // one lane per system on an AoS batch: one staging buffer of 32 records per warp
@@ -258,6 +274,8 @@ int rowchol_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t
                         static std::atomic<uint64_t> raised{0};
                         raise_dyn_smem(kern, smem, raised);
                     }
+                    // (an L2 prefetch of the next wave's lower-triangle planes, 512 bytes per plane, was measured in run r2af and
+                    // lost everywhere -- double 8x8 0.91 -> 0.74, float 12x12 0.84 -> 0.65 of the HBM peak: profiles/r2ad_lane_cholesky.md)
                     kern<<<grid, kRowThreads, smem, st>>>(A, Bm, X, L_out, ok, B);
                 });
             });
