@@ -85,16 +85,17 @@ template <typename T> int xf_apply(int, int, int64_t, const T*, bool, const T*, 
 // in {12, 14, 15, 16} and for double n = 10 and n >= 12 (round 1).  Without one -- the common call -- only the live part of
 // a row travels and the register-only shuffle exchange applies; since the one-lane-per-system sub-warp kernel got its
 // staged record I/O (round 2) it wins wherever one lane holds the system -- since the "wide" one-lane kernels (255 registers,
-// gmb_subwarp.cuh sub_wide) that is float n <= 14 and double n <= 9 (profiles/r2t_wide_lane.md, 1 GB batches, AoS / SoA of the
+// gmb_subwarp.cuh sub_wide) that is float n <= 14 and double n <= 10 (profiles/r2t_wide_lane.md, 1 GB batches, AoS / SoA of the
 // peak, sub-warp against row kernel: double n = 8 0.74 / 0.58 against 0.55 / 0.55, double n = 9 0.71 / 0.67 against 0.36 / 0.35,
 // float n = 13 0.46 / 0.43 against 0.37 / 0.41 (speculative kernel), float n = 14 0.43 / 0.39 against 0.34 / 0.35).  Float n = 12
-// stays with the row kernel (0.42 / 0.49 against 0.43 / 0.45), as do float n >= 15 (speculative kernel first) and double n >= 10.
+// stays with the row kernel (0.42 / 0.49 against 0.43 / 0.45), as do float n >= 15 (speculative kernel first) and double n >= 11
+// (double n = 10 on one lane with ~300 bytes of spills: 0.55 / 0.60 against 0.34 / 0.40, run r2ag).
 // gmb_set_option("rowplu_min_n", n) overrides the table (17 disables the row kernel, 9 forces it).
 template <typename T>
 static bool use_row_kernel(int n, bool want_lu) {
     const int forced = g_opt_rowplu_min_n.load(std::memory_order_relaxed);
     if (forced >= 0) return n >= forced;
-    if (!want_lu) return sizeof(T) == 4 ? (n == 12 || n >= 15) : n >= 10;
+    if (!want_lu) return sizeof(T) == 4 ? (n == 12 || n >= 15) : n >= 11;
     if (n < 9) return false;
     if (sizeof(T) == 4) return n == 12 || n >= 14;
     return n == 10 || n >= 12;

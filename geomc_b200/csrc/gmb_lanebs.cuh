@@ -4,7 +4,7 @@
 //
 // k_row_backsolve (gmb_rowchol.cuh) takes m at run time: it walks the columns of X one after the other, fetching each one with
 // dynamically addressed scalar loads (the gather through `reorder`, :294) between the sweeps and writing it back with
-// per-lane strided scalar stores -- half-used sectors on an AoS batch (profiles/r2w_sweep_final.md: 0.45 .. 0.55 of the HBM
+// per-lane strided scalar stores -- half-used sectors on an AoS batch (run r2w, before this kernel: 0.45 .. 0.55 of the HBM
 // peak for float n = 5 .. 8 with three right-hand sides, 0.72 from the SoA container).  Here
 //   * AoS records travel like the sub-warp kernels' (gmb_io.cuh): the warp's 32 LU records AND its 32 right-hand-side records
 //     are copied global -> shared with cp.async, all in flight together, as whole 16-byte chunks of one contiguous range;

@@ -70,10 +70,10 @@ constexpr bool sub_stage_in(int n, int mode, bool soa) {
 constexpr bool sub_stage_out(int mode, bool soa) { return !soa && mode != MODE_SOLVE; }
 // "Wide" one-lane kernels (round 2, profiles/r2t_wide_lane.md): a local block [A | riders] of up to GMB_SUB_WIDE_WORDS register
 // words that exceeds the budgets above still runs on ONE lane per system, under the 255-register ceiling (two 128-thread
-// CTAs per SM) instead of two lanes with a shuffle per exchanged / broadcast element: double n = 8, 9, float n = 12, 13 and
-// the multi-right-hand-side solves just above the budget (double 7x7 / 8x8 and float 11x11 / 12x12 with three of them).
+// CTAs per SM) instead of two lanes with a shuffle per exchanged / broadcast element: double n = 8, 9, 10, float n = 12, 13, 14 and
+// the multi-right-hand-side solves just above the budget (double 7x7 .. 9x9 and float 11x11 .. 13x13 with three of them).
 #ifndef GMB_SUB_WIDE_WORDS
-#define GMB_SUB_WIDE_WORDS 210            // 0 switches the wide kernels off
+#define GMB_SUB_WIDE_WORDS 220            // 0 switches the wide kernels off; 220 = double 10x10 with one rider (spills ~300 bytes, still 1.6x the row kernel)
 #endif
 constexpr bool sub_wide(int n, int xc, int words) {
     const int block = words * n * (n + xc);
