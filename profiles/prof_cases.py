@@ -63,8 +63,7 @@ def run(case):
         B = 1 << 20
         A, b3 = grid((B, n * n), dt), grid((B, 3 * n), dt)
         lu, perm, _, _ = gm.decomp_plu(A, n)
-        x = torch.empty_like(b3)
-        return lambda: gm.backsolve_plu(lu, perm, b3, n, 3, x_out=x) if "x_out" in gm.backsolve_plu.__code__.co_varnames else gm.backsolve_plu(lu, perm, b3, n, 3)
+        return lambda: gm.backsolve_plu(lu, perm, b3, n, 3)
     if case.startswith("chol"):           # chol<f|d><n>: fused Cholesky + solve, SoA, SPD inputs
         dt = f32 if case[4] == "f" else f64
         n = int(case[5:])

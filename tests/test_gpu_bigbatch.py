@@ -203,15 +203,15 @@ def test_multi_rhs_solve_takes_the_subwarp_kernel(gm, orc, n, dt, soa):
 
 @pytest.mark.parametrize("soa", [False, True])
 @pytest.mark.parametrize("dt", [np.float32, np.float64])
-@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10, 11])
+@pytest.mark.parametrize("n", [5, 6, 7, 8, 9, 10, 11, 12, 13, 14])
 def test_deferred_rider_inverse_is_the_reference_inverse(gm, orc, n, dt, soa):
     """k_sub_plu MODE_INVD (one lane per system, the identity is NOT carried through the elimination; the columns of the
     inverse are produced in i-space and stored at their permuted positions) against the kernels that carry the riders
     (option invd = 0) and against the reference, on a hostile 2^17 batch: singular systems (destination untouched), ties,
     NaN / Inf (dense forward sweep inside the kernel), huge / tiny scalings (IEEE-division redo), all four layout pairs."""
-    # one lane per system (k_sub_plu MODE_INVD) up to float n = 10 / double n = 7, rows over G lanes (row_solve_one INVD) for float
-    # n = 11 (the other sizes of that form were bit-exact too and slower than k_row_inv: profiles/r2j_row_invd.md); where no
-    # deferred-rider kernel exists both arms run the same kernel and the comparison with the reference is what counts
+    # one lane per system (k_sub_plu MODE_INVD) up to float n = 14 / double n = 10 (the wide 255-register instantiations from float
+    # n = 12 / double n = 8 on); where no deferred-rider kernel exists both arms run the same kernel and the comparison with the
+    # reference is what counts
     rng = np.random.default_rng(5000 * n + np.dtype(dt).itemsize + int(soa))
     B = ((1 << 17) if n <= 10 else (1 << 15)) + 33
     A, _ = hostile_batch(rng, B, n, dt, every=37)
@@ -270,3 +270,73 @@ def test_million_system_differential_register_kernels(gm, orc, n, dt):
         ie, ike = orc.inv(A, n, True, True, init)
         assert bits_equal(down(oki), ike), f"inv ok n={n}"
         assert bits_equal(down(out), ie), f"inv n={n}: {first_diff(down(out), ie)}"
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [8, 9, 11, 12, 13, 14, 16])
+def test_one_lane_cholesky_large_n(gm, orc, n, dt, soa):
+    """k_row_chol with ONE lane per system beyond n = 8 (chol_group: SoA every float size and double n <= 12, AoS float n <= 14 /
+    double n <= 9) on 2^14 systems: SPD, non-SPD (ok = 0 at different columns), all-zero and badly scaled systems; factor, ok flags
+    and the fused solve against the reference / the port's definition of the solve, both matrix orders."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(8000 * n + np.dtype(dt).itemsize + int(soa))
+    B = (1 << 14) + 45
+    S = po.spd_exact(rng, B, n, dt)
+    S[::53, 0] = -1                                              # fails at the first column
+    S[11::97, n * (n - 1) + (n - 1)] = -3                        # fails at the last diagonal entry
+    S[7::211] = 0
+    kmax = 30 if dt == np.float32 else 200
+    k = rng.integers(-kmax, kmax + 1, size=(B, n))
+    k[::3] = 0
+    with np.errstate(all="ignore"):
+        S = np.ldexp(S.astype(np.float64).reshape(B, n, n), k[:, :, None] + k[:, None, :]).astype(dt).reshape(B, n * n)
+    b = po.exact_grid(rng, (B, n), dt)
+    dS, db = up(gm, S, soa), up(gm, b, soa)
+    for rm in (True, False):
+        x, ok, L = gm.cholesky_solve(dS, db, n, 1, rm, want_l=True)
+        Lf, okf = gm.cholesky(dS, n, rm)
+        with np.errstate(all="ignore"):
+            Le, oke = orc.cholesky(S, n, rm)
+            xe = po.port().cholesky_solve(Le, b, n, 1, rm)       # the reference has no Cholesky solve: the port's definition
+        assert bits_equal(down(ok), oke) and bits_equal(down(okf), oke), f"ok n={n} rm={rm}"
+        assert bits_equal(down(L), Le), f"L n={n} rm={rm}: {first_diff(down(L), Le)}"
+        assert bits_equal(down(Lf), Le), f"cholesky() n={n} rm={rm}: {first_diff(down(Lf), Le)}"
+        assert bits_equal(down(x), xe), f"x n={n} rm={rm}: {first_diff(down(x), xe)}"
+        assert 0 < int((oke == 0).sum()) < B // 8
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [5, 8, 9, 11, 13, 14])
+def test_one_lane_backsolve_hostile(gm, orc, n, dt, soa):
+    """k_lane_backsolve (gmb_lanebs.cuh) on the LU factors of a hostile 2^14 batch -- zero and NaN pivots, Inf, huge and tiny
+    scalings: the sweeps divide by whatever sits on the diagonal, exactly as the reference does -- with 1..4 right-hand sides,
+    skip = 0 / 2, both orders, against the reference; and against the row kernel (option lanebs = 0) for the same bits."""
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(9000 * n + np.dtype(dt).itemsize + int(soa))
+    B = (1 << 14) + 21
+    A, _ = hostile_batch(rng, B, n, dt, every=29)
+    try:
+        for rm in (True, False):
+            with np.errstate(all="ignore"):
+                lu_np, p_np, _, _ = orc.decomp_plu(A, n, n, rm)
+            lu, p = up(gm, lu_np, soa), torch.from_numpy(p_np.astype(np.uint8)).cuda()
+            for m in (1, 2, 3, 4):
+                b = po.exact_grid(rng, (B, n * m), dt)
+                for skip in (0, 2):
+                    gm.set_option("lanebs", -1)
+                    x1 = down(gm.backsolve_plu(lu, p, up(gm, b, soa), n, m, skip, rm))
+                    y1 = down(gm.backsolve_lu(lu, up(gm, b, soa), n, m, skip, rm))
+                    gm.set_option("lanebs", 0)
+                    x0 = down(gm.backsolve_plu(lu, p, up(gm, b, soa), n, m, skip, rm))
+                    y0 = down(gm.backsolve_lu(lu, up(gm, b, soa), n, m, skip, rm))
+                    with np.errstate(all="ignore"):
+                        xe = orc.backsolve_plu(lu_np, p_np, b, n, m, skip, rm)
+                        ye = orc.backsolve_lu(lu_np, b, n, m, skip, rm)
+                    tag = f"n={n} m={m} rm={rm} skip={skip}"
+                    assert bits_equal(x1, xe), f"backsolve_plu vs {orc.kind} {tag}: {first_diff(x1, xe)}"
+                    assert bits_equal(y1, ye), f"backsolve_lu vs {orc.kind} {tag}: {first_diff(y1, ye)}"
+                    assert bits_equal(x1, x0) and bits_equal(y1, y0), f"lane kernel vs row kernel {tag}"
+    finally:
+        gm.set_option("lanebs", -1)
