@@ -280,6 +280,32 @@ __device__ __forceinline__ void aos_stage_issue(const T* __restrict__ base, int6
     }
 }
 __device__ __forceinline__ void cp_async_wait_all_() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// The SoA counterpart: the warp's 32 consecutive systems (s_warp0 a multiple of 32, all inside one tile of W systems) are a
+// 32-element segment of each of the E element planes.  The segments are copied global -> shared with cp.async as whole 16-byte
+// chunks (a plane segment is 128 / 256 contiguous bytes), plane e landing at sm + e * 32 * sizeof(T): element e of the lane's
+// system is then sm[e * 32 + lane] -- bank = lane, conflict-free for static and run-time e alike.  No registers are held while
+// the data travel, and the copies of several arrays are in flight together (same protocol as aos_stage_issue).
+template <typename T, int E>
+__device__ __forceinline__ void soa_stage_issue(const T* __restrict__ base, int64_t s_warp0, int lane, unsigned char* sm) {
+    constexpr int W = soa_w<T>();
+    constexpr int V = soa_v<T>();                             // elements per 16-byte chunk
+    constexpr int CPP = 32 / V;                               // chunks per plane segment
+    constexpr int NCH = E * CPP;
+    const T* g = base + (s_warp0 / W) * (int64_t)E * W + (s_warp0 % W);
+#pragma unroll
+    for (int c0 = 0; c0 < NCH; c0 += 32) {
+        const int c = c0 + lane;
+        if (NCH % 32 == 0 || c < NCH) {
+            const int e = c / CPP, w = c % CPP;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + c * 16);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + (int64_t)e * W + w * V) : "memory");
+        }
+    }
+}
+template <typename T>
+__device__ __forceinline__ T soa_stage_elem(int lane, int e, const unsigned char* sm) {
+    return reinterpret_cast<const T*>(sm)[e * 32 + lane];
+}
 template <typename T, int E>
 __device__ __forceinline__ void aos_stage_read(int lane, T (&q)[E], const unsigned char* sm) {
     constexpr int R = E * (int)sizeof(T);

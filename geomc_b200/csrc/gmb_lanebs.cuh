@@ -10,7 +10,9 @@
 //     are copied global -> shared with cp.async, all in flight together, as whole 16-byte chunks of one contiguous range;
 //     the gather b(reorder[r]) is a dynamically indexed read of the lane's record in shared memory; X leaves through the
 //     same buffer with coalesced 128-bit stores;
-//   * SoA planes are loaded directly (a plane is already coalesced), every right-hand side up front;
+//   * SoA batches travel the same way (soa_stage_issue: the warp's 32-system segment of every element plane, whole 16-byte chunks,
+//     plane e at [e][lane] in shared memory -- conflict-free for the gather's run-time e); X leaves with direct plane stores.
+//     Direct plane loads into registers measured 0.02 .. 0.2 of the peak lower (run r2am: float 13x13 0.69 -> 0.89);
 //   * all m columns ride through one forward and one backward sweep: a(r, c) is used m times per load, the m division
 //     chains of the backward sweep overlap.
 // Per element the operations and their order are those of backsolve_lu (c ascending in the forward sweep, c descending in the
@@ -53,15 +55,20 @@ k_lane_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, co
     const bool valid = s_raw < B;
     const int64_t s = valid ? s_raw : B - 1;
     const int64_t s_warp0 = s_raw - lane;
-    const bool full = !SOA && (s_warp0 + 32 <= B);            // warp-uniform: all 32 records exist
+    const bool full = s_warp0 + 32 <= B;                      // warp-uniform: all 32 systems exist (SoA: inside one tile, W % 32 == 0)
     unsigned char* smA = gmb_dyn_smem + (size_t)(threadIdx.x >> 5) * (32 * (EA + EX) * sizeof(T));
     unsigned char* smX = smA + 32 * EA * sizeof(T);
     const int64_t baseA = SOA ? (s / W) * (int64_t)EA * W + (s % W) : s * (int64_t)EA;
     const int64_t baseX = SOA ? (s / W) * (int64_t)EX * W + (s % W) : s * (int64_t)EX;
 
     if (full) {
-        aos_stage_issue<T, EA>(LUm, s_warp0, lane, smA);
-        aos_stage_issue<T, EX>(Bm, s_warp0, lane, smX);
+        if constexpr (SOA) {
+            soa_stage_issue<T, EA>(LUm, s_warp0, lane, smA);
+            soa_stage_issue<T, EX>(Bm, s_warp0, lane, smX);
+        } else {
+            aos_stage_issue<T, EA>(LUm, s_warp0, lane, smA);
+            aos_stage_issue<T, EX>(Bm, s_warp0, lane, smX);
+        }
     }
     int src[N];
 #pragma unroll
@@ -69,18 +76,29 @@ k_lane_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, co
 
     T a[N][N], x[N][M];
     if (full) {
-        T qa[EA];
         cp_async_wait_all_();
         __syncwarp();
-        aos_stage_read<T, EA>(lane, qa, smA);
+        if constexpr (SOA) {
 #pragma unroll
-        for (int r = 0; r < N; ++r)
+            for (int r = 0; r < N; ++r)
 #pragma unroll
-            for (int c = 0; c < N; ++c) a[r][c] = qa[RM ? N * r + c : N * c + r];
+                for (int c = 0; c < N; ++c) a[r][c] = soa_stage_elem<T>(lane, RM ? N * r + c : N * c + r, smA);
 #pragma unroll
-        for (int r = 0; r < N; ++r)
+            for (int r = 0; r < N; ++r)
 #pragma unroll
-            for (int j = 0; j < M; ++j) x[r][j] = aos_stage_elem<T, EX>(lane, RM ? M * src[r] + j : N * j + src[r], smX);
+                for (int j = 0; j < M; ++j) x[r][j] = soa_stage_elem<T>(lane, RM ? M * src[r] + j : N * j + src[r], smX);
+        } else {
+            T qa[EA];
+            aos_stage_read<T, EA>(lane, qa, smA);
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int c = 0; c < N; ++c) a[r][c] = qa[RM ? N * r + c : N * c + r];
+#pragma unroll
+            for (int r = 0; r < N; ++r)
+#pragma unroll
+                for (int j = 0; j < M; ++j) x[r][j] = aos_stage_elem<T, EX>(lane, RM ? M * src[r] + j : N * j + src[r], smX);
+        }
         __syncwarp();                                          // the buffer is reused by the staged store
     } else {
 #pragma unroll
@@ -124,7 +142,7 @@ k_lane_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, co
     for (int r = 0; r < N; ++r)
 #pragma unroll
         for (int j = 0; j < M; ++j) qx[RM ? M * r + j : N * j + r] = x[r][j];
-    if (full) {
+    if (full && !SOA) {
         aos_store_staged<T, EX>(X, s_warp0, lane, qx, smX);
     } else if (valid) {
 #pragma unroll
@@ -147,7 +165,7 @@ int lanebs_launch(int mode, int n, int64_t B, const T* LU, const uint8_t* perm, 
                 dispatch_bool(layout == GMB_LAYOUT_SOA, [&](auto SOA) {
                     dispatch_bool(rm != 0, [&](auto RM) {
                         auto kern = k_lane_backsolve<T, N.value, M, PLU.value, SOA.value, RM.value>;
-                        const size_t smem = SOA.value ? 0 : (size_t)(kLaneBsThreads / 32) * 32 * (N.value * (N.value + M)) * sizeof(T);
+                        const size_t smem = (size_t)(kLaneBsThreads / 32) * 32 * (N.value * (N.value + M)) * sizeof(T);
                         if (smem > 48 * 1024) {
                             static std::atomic<uint64_t> raised;          // per instantiation, one bit per device
                             raise_dyn_smem(kern, smem, raised);
