@@ -148,6 +148,10 @@ __device__ __forceinline__ void sub_lane_store(T* __restrict__ base, int64_t s, 
 }
 // elements per system of a G == 1 AoS kernel's staging buffer: the matrix and the rider block side by side (both are in
 // flight at once), never less than n*n + 1 (the deferred-rider inverse uses the buffer as an odd-stride scratch)
+// SoA batches of the one-lane kernels that are staged through shared memory (see the load section of k_sub_plu)
+constexpr bool sub_soa_stage(int n, int words, int mode, int g, bool soa) {
+    return soa && g == 1 && mode == 1 /* MODE_DECOMP */ && n * n * words * 4 >= 400 && !(words == 2 && n == 8);
+}
 constexpr int sub_lane_emax(int n, int xc, int mode) { return n * n + (mode == 0 /* MODE_SOLVE */ ? n * xc : 0); }
 
 // MODE_RECT (XC = 0, G = 1): orthogonal (Orthogonal.h:73-98) and nullspace (:136-178).  Both run the RECTANGULAR row-pivot
@@ -276,7 +280,39 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
 #pragma unroll
                 for (int j = 0; j < XC; ++j) a[r][N + j] = (r == j) ? (T)1 : (T)0;
         }
-    } else
+    } else {
+        // SoA, one lane per system, decompositions of matrices of 400 bytes and more (sub_soa_stage): the warp's 32-system segment
+        // of every element plane is copied global -> shared with cp.async (soa_stage_issue, gmb_io.cuh) and read back as
+        // [plane][lane] -- no registers held and no load / store queue slots taken while the data travel (ncu: LG throttle was
+        // the top stall of the direct plane loads).  Measured for every mode (profiles/r2ap_soa_staging.md): it wins for the
+        // decompositions from float n = 10 / double n = 9 on (float 11x11 0.63 -> 0.81 of the HBM peak, double 9x9 0.63 -> 0.79) and
+        // loses 0.03 .. 0.08 for the ALU-bound solves and inverses of the small sizes (extra shared-memory reads), which keep
+        // their direct plane loads.
+        bool soa_staged = false;
+        if constexpr (sub_soa_stage(N, WORDS, MODE, G, SOA)) {
+            if (s_warp0 + 32 <= B) {                               // warp-uniform; the 32 systems sit inside one tile (W % 32 == 0)
+                const int lane = threadIdx.x & 31;
+                unsigned char* smb = lane_sm + 32 * N * N * sizeof(T);
+                soa_stage_issue<T, N * N>(A, s_warp0, lane, lane_sm);
+                if constexpr (MODE == MODE_SOLVE) soa_stage_issue<T, N * XC>(Bm, s_warp0, lane, smb);
+                cp_async_wait_all_();
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int c = 0; c < N; ++c) a[r][c] = soa_stage_elem<T>(lane, A_RM ? N * r + c : N * c + r, lane_sm);
+#pragma unroll
+                for (int r = 0; r < N; ++r)
+#pragma unroll
+                    for (int j = 0; j < XC; ++j) {
+                        if (MODE == MODE_SOLVE) a[r][N + j] = soa_stage_elem<T>(lane, X_RM ? XC * r + j : N * j + r, smb);
+                        if (MODE == MODE_INV) a[r][N + j] = (r == j) ? (T)1 : (T)0;
+                    }
+                __syncwarp();                                      // the buffer is reused (deferred-rider scratch)
+                soa_staged = true;
+            }
+        }
+        if (!soa_staged) {
 #pragma unroll
     for (int r = 0; r < N; ++r)
 #pragma unroll
@@ -291,6 +327,8 @@ k_sub_plu(const T* __restrict__ A, const T* Bm, T* X, T* LU, uint8_t* __restrict
             }
             a[r][j] = v;
         }
+        }
+    }
 
     uint8_t perm[N];
     if (MODE == MODE_DECOMP || MODE == MODE_INVD) {
@@ -745,7 +783,7 @@ static int launch_sub(const T* A, const T* Bm, T* X, T* LU, uint8_t* ok, uint8_t
             auto kern = (CAN_NO_L && LU == nullptr) ? k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM, COLPIV, CAN_NO_L>
                                                     : k_sub_plu<T, N, XC, MODE, SOA.value, ARM.value, XRM, COLPIV, false>;
             // AoS: one staging buffer of 32/G systems per warp (dynamic shared memory)
-            const size_t smem = (G == 1 && (!SOA.value || MODE == MODE_INVD))
+            const size_t smem = (G == 1 && (!SOA.value || MODE == MODE_INVD || sub_soa_stage(N, (int)sizeof(T) / 4, MODE, G, true)))
                                     ? (size_t)(kSubThreads / 32) * 32 * (sub_lane_emax(N, XC, MODE) + 1) * sizeof(T)
                                 : !(sub_stage_in<T>(N, MODE, SOA.value) || sub_stage_out(MODE, SOA.value))
                                     ? 0
