@@ -348,9 +348,10 @@ def config_c1_small(c, steps=24):
              "C1s", B, total, steps, 96,
              {"median_launch_ms": statistics.median(ms), "best_launch_ms": min(ms), "verified_systems": int(sum_over_ranks(c, nv)),
               "mismatches": int(sum_over_ranks(c, bad)), "oracle": oracle(c).kind})
+    # the same 24 launches replayed from ONE CUDA graph (captured on a side stream through the same C-ABI call): what remains
+    # is the kernel, the inter-kernel gap of the graph and the short grid's tail -- the host launch path is gone
+    gms, err = None, None
     try:
-        # the same 24 launches replayed from ONE CUDA graph (captured on a side stream through the same C-ABI call): what remains
-        # is the kernel, the inter-kernel gap of the graph and the short grid's tail -- the host launch path is gone
         side = t.cuda.Stream(device=c.dev)
         side.wait_stream(t.cuda.current_stream(c.dev))
         graph = t.cuda.CUDAGraph()
@@ -364,16 +365,19 @@ def config_c1_small(c, steps=24):
             x.data.zero_()
         ok.zero_()
         gms = timed(c, graph.replay, 5, 3)
-        gtotal = max_over_ranks(c, statistics.median(gms))
-        nv2, bad2 = verify_solve_sample(c, sets[(steps - 1) % 4][0], sets[(steps - 1) % 4][1], xs[(steps - 1) % 4], ok, 4, B, t.float32)
-        r2 = row(c, "C1 literal, CUDA graph: the same 24 launches (2^20 systems each, 4 rotating buffer sets) captured once and replayed",
-                 "C1g", B, gtotal, steps, 96,
-                 {"launches_per_replay": steps, "replays_timed": 5, "verified_systems": int(sum_over_ranks(c, nv2)),
-                  "mismatches": int(sum_over_ranks(c, bad2)), "oracle": oracle(c).kind})
-        return [r1, r2]
-    except Exception as e:                                      # capture refused: keep the plain line
-        r1["cuda_graph_error"] = repr(e)[:200]
+    except Exception as e:                                      # capture refused on this rank
+        err = repr(e)[:200]
+    # every rank takes the same branch (the collectives below must match): one failed capture drops the row everywhere
+    if max_over_ranks(c, 0.0 if gms is not None else 1.0) != 0.0:
+        r1["cuda_graph_error"] = err or "capture failed on another rank"
         return [r1]
+    gtotal = max_over_ranks(c, statistics.median(gms))
+    nv2, bad2 = verify_solve_sample(c, sets[(steps - 1) % 4][0], sets[(steps - 1) % 4][1], xs[(steps - 1) % 4], ok, 4, B, t.float32)
+    r2 = row(c, "C1 literal, CUDA graph: the same 24 launches (2^20 systems each, 4 rotating buffer sets) captured once and replayed",
+             "C1g", B, gtotal, steps, 96,
+             {"launches_per_replay": steps, "replays_timed": 5, "verified_systems": int(sum_over_ranks(c, nv2)),
+              "mismatches": int(sum_over_ranks(c, bad2)), "oracle": oracle(c).kind})
+    return [r1, r2]
 
 
 # ---------------------------------------------------------------------------------------- C2
