@@ -85,10 +85,12 @@ constexpr int sub_group(int n, int xc, int words) {
         if (n * sub_lc(n, xc, g) * words <= (xc == 0 ? GMB_SUB_REG_BUDGET_XC0 : kRegBudgetWords)) return g;
     return 16;
 }
-// The one measured exception (profiles/r2t_wide_lane.md): the row-pivot decomposition of an SoA batch keeps two lanes per system
-// for float n = 12, 14 and double n = 10 (0.64 / 0.54 / 0.59 of the HBM peak against 0.57 / 0.51 / 0.46 on one wide lane).
+// Per-mode / per-layout hook.  Until the SoA plane segments were staged through shared memory (sub_soa_stage) the row-pivot
+// decomposition of an SoA batch kept two lanes per system for float n = 12, 14 and double n = 10 (0.64 / 0.54 / 0.59 of the HBM
+// peak against 0.57 / 0.51 / 0.46 on one wide lane with direct plane loads, profiles/r2t_wide_lane.md); with the staging the
+// one-lane form wins there too (run r2as) and the exception is gone.
 constexpr int sub_group_for(int n, int xc, int words, int mode, bool soa, bool colpiv) {
-    if (mode == MODE_DECOMP && soa && !colpiv && xc == 0 && ((words == 1 && (n == 12 || n == 14)) || (words == 2 && n == 10))) return 2;
+    (void)mode; (void)soa; (void)colpiv;
     return sub_group(n, xc, words);
 }
 constexpr int sub_min_blocks(int n, int xc, int words, int mode, bool soa, bool colpiv) {
