@@ -181,6 +181,7 @@ int lu_backsolve(int mode, int n, int m, int64_t B, const T* LU, const uint8_t* 
     if (B > 0 && (X == nullptr || Bm == nullptr || (mode != 2 && LU == nullptr) || (mode != 0 && perm == nullptr)))
         return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    if (B == 0) return GMB_OK;                             // an empty batch: nothing to launch
     cudaStream_t st = as_stream(stream);
     const bool fast = all_aligned16(LU, Bm, X);
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
@@ -207,6 +208,7 @@ int plu_solve(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* o
     if (B < 0 || n < 1 || m < 1 || skip < 0 || bad_layout(layout)) return GMB_ERR_INVALID_ARG;
     if (B > 0 && (A == nullptr || Bm == nullptr || X == nullptr)) return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    if (B == 0) return GMB_OK;                             // an empty batch: nothing to launch
     cudaStream_t st = as_stream(stream);
     const bool fast = all_aligned16(A, Bm, X, LU);
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
@@ -241,6 +243,7 @@ int linear_solve_vec(int n, int m, int64_t B, const T* bases, const T* Bv, T* X,
     if (B < 0 || n < 1 || m < 1 || skip < 0 || bad_layout(layout)) return GMB_ERR_INVALID_ARG;
     if (B > 0 && (bases == nullptr || Bv == nullptr || X == nullptr)) return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    if (B == 0) return GMB_OK;                             // an empty batch: nothing to launch
     cudaStream_t st = as_stream(stream);
     if (n < 5) {
         // inverse-then-multiply: LUDecomp.h:419-426 (skip is ignored on this path, as in the reference)
@@ -259,6 +262,7 @@ int cholesky(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t* ok
     if (B < 0 || n < 1 || bad_layout(layout) || (B > 0 && A == nullptr)) return GMB_ERR_INVALID_ARG;
     if (solve && (m < 1 || (B > 0 && (Bm == nullptr || X == nullptr)))) return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    if (B == 0) return GMB_OK;                             // an empty batch: nothing to launch
     cudaStream_t st = as_stream(stream);
     const bool fast = all_aligned16(A, Bm, X, L_out);
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
@@ -284,6 +288,7 @@ int inv(int n, int64_t B, const T* A, T* Ainv, uint8_t* ok, int layout, int src_
     cudaStream_t st = as_stream(stream);
     const bool fast = all_aligned16(A, Ainv);
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
+    if (B == 0) return GMB_OK;                             // an empty batch: nothing to launch (and no pointers to compare)
     if (n >= 5 && A == Ainv) return GMB_ERR_INVALID_ARG;   // invNxN: m must not alias out (MatrixInv.h:174)
     if (n >= 2 && n <= 4) {
         // adjugate (MatrixInv.h:49-165) in both cases: vectorised register kernel, or -- for an AoS batch that is only
@@ -317,6 +322,7 @@ template <typename T>
 int orthogonal(int n, int64_t B, const T* V, T* out, int layout, void* stream) {
     if (B < 0 || n < 2 || bad_layout(layout) || (B > 0 && (V == nullptr || out == nullptr))) return GMB_ERR_INVALID_ARG;
     if (n > GMB_MAX_N) return GMB_ERR_UNSUPPORTED;
+    if (B == 0) return GMB_OK;                             // an empty batch: nothing to launch
     const bool fast = all_aligned16(V, out);
     if (!fast && layout == GMB_LAYOUT_SOA) return GMB_ERR_INVALID_ARG;
     if (fast && n <= 4) return small_orthogonal<T>(n, B, V, out, layout, as_stream(stream));

@@ -672,3 +672,32 @@ def test_backsolve_two_and_four_rhs(gm, orc, dt, n, soa):
                           f"backsolve_lu n={n} m={m} rm={rm} skip={skip} soa={soa}")
                     check(down(gm.backsolve_plu(lu, p, up(gm, b, soa), n, m, skip, rm)),
                           orc.backsolve_plu(lu_np, p_np, b, n, m, skip, rm), f"backsolve_plu n={n} m={m} rm={rm} skip={skip} soa={soa}")
+
+
+@pytest.mark.parametrize("soa", [False, True])
+@pytest.mark.parametrize("n,dt", [(9, np.float64), (10, np.float64), (13, np.float32), (14, np.float32), (12, np.float32)])
+def test_tiny_batches_through_the_one_lane_kernels(gm, orc, n, dt, soa):
+    """Batches smaller than / not a multiple of a warp (B = 1, 31, 33) and the empty batch through the wide one-lane kernels, the
+    one-lane backsolve and the one-lane Cholesky: the staged (full-warp) and the per-lane (ragged warp) I/O paths of the same
+    kernel must agree with the reference."""
+    from oracle import pyoracle as po
+    for B in (1, 31, 33):
+        rng = np.random.default_rng(31337 + 7 * n + B)
+        A = rng.standard_normal((B, n * n)).astype(dt)
+        A[0] = 0
+        b1 = rng.standard_normal((B, n)).astype(dt)
+        b3 = rng.standard_normal((B, n * 3)).astype(dt)
+        S = po.spd_exact(rng, B, n, dt)
+        run_all(gm, orc, n, A, b1, b3, S, soa)
+    tdt = getattr(torch, TDT[np.dtype(dt)])
+    A0 = gm.BatchSoA(0, n * n, tdt) if soa else torch.empty((0, n * n), dtype=tdt, device="cuda")
+    b0 = gm.BatchSoA(0, n, tdt) if soa else torch.empty((0, n), dtype=tdt, device="cuda")
+    p0 = torch.empty((0, n), dtype=torch.uint8, device="cuda")
+    gm.decomp_plu(A0, n)
+    gm.decomp_lup(A0, n)
+    gm.linear_solve(A0, b0, n)
+    gm.inv(A0, n)
+    gm.cholesky_solve(A0, b0, n)
+    gm.backsolve_plu(A0, p0, b0, n, 1)
+    gm.backsolve_lu(A0, b0, n, 1)
+    torch.cuda.synchronize()
