@@ -152,7 +152,11 @@ __device__ __forceinline__ void sub_lane_store(T* __restrict__ base, int64_t s, 
 // flight at once), never less than n*n + 1 (the deferred-rider inverse uses the buffer as an odd-stride scratch)
 // SoA batches of the one-lane kernels that are staged through shared memory (see the load section of k_sub_plu)
 constexpr bool sub_soa_stage(int n, int words, int mode, int g, bool soa) {
-    return soa && g == 1 && mode == 1 /* MODE_DECOMP */ && n * n * words * 4 >= 400 && !(words == 2 && n == 8);
+    if (!soa || g != 1) return false;
+    if (mode == 1 /* MODE_DECOMP */) return n * n * words * 4 >= 400 && !(words == 2 && n == 8);
+    // the deferred-rider inverse: the two sizes where the staging measured a gain (run r2ap: double 7x7 0.65 -> 0.76, float 10x10 0.48 -> 0.53)
+    if (mode == 3 /* MODE_INVD */) return (words == 2 && n == 7) || (words == 1 && n == 10);
+    return false;
 }
 constexpr int sub_lane_emax(int n, int xc, int mode) { return n * n + (mode == 0 /* MODE_SOLVE */ ? n * xc : 0); }
 
