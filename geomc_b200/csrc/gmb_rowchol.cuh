@@ -33,6 +33,13 @@ namespace gmb {
 #ifndef GMB_CHOL_LANE_AOS_BYTES
 #define GMB_CHOL_LANE_AOS_BYTES 840       // AoS: bytes of [A | b] per system that the warp's staging buffer may take (two CTAs per SM)
 #endif
+// SoA batches whose lower-triangle planes are staged through shared memory (see the load section of k_row_chol).  Measured for
+// every size (run r2bb, fused Cholesky + solve, fraction of the HBM peak, direct plane loads -> staged): float n = 12..16 0.85 / 0.73 /
+// 0.70 / 0.54 / 0.53 -> 0.88 / 0.76 / 0.75 / 0.57 / 0.57, double n = 10..12 0.71 / 0.74 / 0.74 -> 0.76 / 0.80 / 0.78; the smaller sizes, at or
+// near the roofline with direct loads, lose 0.03 .. 0.13 to the extra shared-memory round trip and keep them.
+constexpr bool chol_soa_stage(int n, int words, bool soa, int g) {
+    return soa && g == 1 && n >= (words == 1 ? 12 : 10);
+}
 constexpr int chol_group(int n, int words, bool soa) {
     if (words * (n * (n + 1) / 2 + 2 * n) <= GMB_CHOL_LANE_WORDS && (soa || (n * n + n) * words * 4 <= GMB_CHOL_LANE_AOS_BYTES)) return 1;
     return row_group(n, words);
@@ -88,7 +95,53 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
             for (int c = 0; c < N; ++c) a[r][c] = (c <= r) ? qa[RM ? N * r + c : N * c + r] : (T)0;
 #pragma unroll
         for (int r = 0; r < N; ++r) y[r] = SOLVE ? qb[r] : (T)0;
-    } else
+    } else {
+    // SoA, one lane per system, the larger sizes (chol_soa_stage): the warp's 32-system segments of the LOWER-TRIANGLE planes (a
+    // contiguous run of planes per row / column) and of b go global -> shared with cp.async, packed [plane][lane]; no registers
+    // held and no load-queue slots taken by up to 136 + 16 direct plane loads per thread while the data travel
+    bool soa_staged = false;
+    if constexpr (chol_soa_stage(N, WORDS, SOA, G)) {
+        const int lane = threadIdx.x & 31;
+        const int64_t s_w0 = s_raw - lane;
+        if (s_w0 + 32 <= B) {                                  // warp-uniform; the 32 systems sit inside one tile (W % 32 == 0)
+            constexpr int V = soa_v<T>();
+            constexpr int CPP = 32 / V;                        // 16-byte chunks per plane segment
+            constexpr int TRI = N * (N + 1) / 2;
+            T* sm = reinterpret_cast<T*>(gmb_dyn_smem) + (size_t)(threadIdx.x >> 5) * (32 * (TRI + N));
+            const T* gA = A + (s_w0 / W) * (int64_t)(N * N) * W + (s_w0 % W);
+            const T* gB = Bm + (s_w0 / W) * (int64_t)N * W + (s_w0 % W);
+#pragma unroll
+            for (int k = 0; k <= N; ++k) {
+                if (k == N && !SOLVE) break;
+                // run k < N: row k, columns 0..k (row-major) or column k, rows k..N-1 (column-major); run N: the N planes of b
+                const int first = k == N ? 0 : (RM ? N * k : N * k + k);
+                const int cnt = k == N ? N : (RM ? k + 1 : N - k);
+                const int off = k == N ? TRI : (RM ? k * (k + 1) / 2 : k * N - k * (k - 1) / 2);
+                const T* g = k == N ? gB : gA;
+#pragma unroll
+                for (int c0 = 0; c0 < cnt * CPP; c0 += 32) {
+                    const int c = c0 + lane;
+                    if (c < cnt * CPP) {
+                        const int e = c / CPP, w = c % CPP;
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(sm + (off + e) * 32 + w * V);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(g + (int64_t)(first + e) * W + w * V)
+                                     : "memory");
+                    }
+                }
+            }
+            cp_async_wait_all_();
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < N; ++r) {
+#pragma unroll
+                for (int c = 0; c < N; ++c)
+                    a[r][c] = (c <= r) ? sm[(RM ? r * (r + 1) / 2 + c : c * N - c * (c - 1) / 2 + (r - c)) * 32 + lane] : (T)0;
+                y[r] = SOLVE ? sm[(TRI + r) * 32 + lane] : (T)0;
+            }
+            soa_staged = true;
+        }
+    }
+    if (!soa_staged) {
 #pragma unroll
     for (int k = 0; k < RL; ++k) {
         const int p = k * G + lane_g;
@@ -109,6 +162,8 @@ k_row_chol(const T* A, const T* Bm, T* X, T* L_out, uint8_t* __restrict__ ok_out
             }
         }
         y[k] = SOLVE ? Bm[baseX + (int64_t)pr * ST] : (T)0;
+    }
+    }
     }
 
     bool ok = true;
@@ -269,7 +324,10 @@ int rowchol_impl(int n, int m, int64_t B, const T* A, const T* Bm, T* X, uint8_t
                 dispatch_bool(rm != 0, [&](auto RM) {
                     auto kern = k_row_chol<T, N.value, SOLVE.value, SOA.value, RM.value>;
                     // one lane per system on an AoS batch: one staging buffer of 32 records per warp
-                    const size_t smem = (G == 1 && !SOA.value) ? (size_t)(kRowThreads / 32) * 32 * (N.value * N.value + N.value) * sizeof(T) : 0;
+                    const size_t smem = (G == 1 && !SOA.value) ? (size_t)(kRowThreads / 32) * 32 * (N.value * N.value + N.value) * sizeof(T)
+                                        : chol_soa_stage(N.value, (int)sizeof(T) / 4, SOA.value, G)
+                                            ? (size_t)(kRowThreads / 32) * 32 * (N.value * (N.value + 1) / 2 + N.value) * sizeof(T)
+                                            : 0;
                     if (smem > 48 * 1024) {
                         static std::atomic<uint64_t> raised{0};
                         raise_dyn_smem(kern, smem, raised);
