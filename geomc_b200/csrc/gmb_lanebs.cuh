@@ -72,7 +72,9 @@ k_lane_backsolve(const T* __restrict__ LUm, const uint8_t* __restrict__ perm, co
     }
     int src[N];
 #pragma unroll
-    for (int r = 0; r < N; ++r) src[r] = PLU ? (int)perm[s * N + r] : r;     // y(r) = b(reorder[r]) (:294)
+    // y(r) = b(reorder[r]) (:294).  The index addresses shared memory: a corrupt `reorder` entry (>= n, never produced by decomp_plu)
+    // is clamped so that it cannot leave the warp's staging buffer
+    for (int r = 0; r < N; ++r) src[r] = PLU ? min((int)perm[s * N + r], N - 1) : r;
 
     T a[N][N], x[N][M];
     if (full) {
