@@ -330,7 +330,8 @@ int64_t gmb_launch_count(void);
  * decomposition (17 = never); "rowinv": 0 / 1 = column- / row-distributed inverse for every n >= 5; "rowfast": 0 / 1 =
  * never / always use the speculative fused solve (n >= 9, one right-hand side, no LU output) with its exact re-solve.
  * "invd": 0 = no deferred-rider inverse; "lanechol": 0 / 1 = never / always the one-thread Cholesky for n = 5..8; "lanebs": 0 = the
- * backsolves never take the one-lane kernel with 1..4 right-hand sides (float n <= 13, double n <= 9).
+ * backsolves never take the one-lane kernel with 1..4 right-hand sides (float n <= 14, double n <= 9); "subprefetch": L2 prefetch
+ * distance of the one-lane sub-warp kernels in CTAs (0 = off, > 0 = that distance for every size, -1 = the measured rule).
  * Every choice computes the same bits; only the time differs.  Returns GMB_ERR_INVALID_ARG for an unknown name. */
 int gmb_set_option(const char* name, int value);
 
